@@ -1,0 +1,199 @@
+"""CPU: pin the oracle (oracle/) against fixtures produced by running the reference itself."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import unnan
+from oracle import oracle as O
+
+PNAMES = ["svj_default", "gbm_cfg1", "heston", "jumpy"]
+RTOL = 1e-12   # oracle vs reference on identical float64 inputs (libm vs numba exp: ~1 ulp per step)
+
+
+def P(golden, name):
+    return O.Params(**golden["params"][name])
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", PNAMES)
+@pytest.mark.parametrize("impl", ["c", "numpy"])
+def test_kernel_stored_inputs(golden, garr, name, impl):
+    p = P(golden, name)
+    f = O.simulate_svj if impl == "c" else O.simulate_svj_numpy
+    S, v, paths = f(22500.0, p.v0, p.r, p.q, 0.25, p.kappa, p.theta, p.xi, p.rho, p.lambda_j, p.mu_j, p.sigma_j,
+                    garr["k_small_Z1"], garr["k_small_Z2"], garr["k_small_Zj"], garr["k_small_Zjs"], 40, True)
+    np.testing.assert_allclose(S, garr[f"k_small_{name}_S"], rtol=RTOL)
+    np.testing.assert_allclose(v, garr[f"k_small_{name}_v"], rtol=RTOL, atol=1e-18)
+    np.testing.assert_allclose(paths, garr[f"k_small_{name}_paths"], rtol=RTOL)
+    assert paths.shape == (96, 41) and np.all(paths[:, 0] == 22500.0)
+
+
+def test_kernel_pcg64_inputs(golden, garr):
+    c = golden["cases"]["k_4096"]
+    p = P(golden, c["params"])
+    Z1, Z2, Zj, Zjs = O.draw_pcg64(c["seed"], c["n"], c["steps"])
+    assert sha(Z1) == c["Z_sha256"]["Z1"] and sha(Z2) == c["Z_sha256"]["Z2"]
+    assert sha(Zj) == c["Z_sha256"]["Zj"] and sha(Zjs) == c["Z_sha256"]["Zjs"]
+    np.testing.assert_allclose(Z1[0, :3], c["Z1_head"], rtol=0, atol=0)
+    S, v, empty = O._sim(p, c["spot"], c["T"], Z1, Z2, Zj, Zjs, c["steps"])
+    assert empty.shape == (0, 0)
+    np.testing.assert_allclose(S, garr["k_4096_S"], rtol=RTOL)
+    np.testing.assert_allclose(v, garr["k_4096_v"], rtol=RTOL, atol=1e-18)
+    # SURVEY.md 8c probe values
+    assert abs(S.mean() - 22787.2608410784) < 1e-6 and abs(S.std() - 2512.2146334655) < 1e-6
+    np.testing.assert_allclose(O._sim(p, c["spot"], c["T"], -Z1, -Z2, Zj, -Zjs, c["steps"])[0],
+                               garr["k_4096_S_anti"], rtol=RTOL)
+    np.testing.assert_allclose(O._sim(p, c["spot"], c["T"], Z1, Z2, Zj, Zjs, c["steps"], v0=p.v0 + 0.01)[0],
+                               garr["k_4096_S_v0up"], rtol=RTOL)
+
+
+def test_gbm_limit_identity(golden, garr):
+    """xi=0, lambda=0, theta=v0: the kernel equals the closed-form log-sum."""
+    p = P(golden, "gbm_cfg1")
+    Z1 = np.random.default_rng(7).standard_normal((512, 250))
+    S = O._sim(p, 2500.0, 1.0, Z1, np.zeros_like(Z1), np.ones_like(Z1), np.zeros_like(Z1), 250)[0]
+    np.testing.assert_allclose(S, garr["k_gbm_S"], rtol=RTOL)
+    dt = 1.0 / 250
+    closed = 2500.0 * np.exp((p.r - p.q - 0.5 * p.v0) * 1.0 + np.sqrt(p.v0 * dt) * Z1.sum(axis=1))
+    np.testing.assert_allclose(S, closed, rtol=1e-12)
+    assert golden["cases"]["k_gbm"]["max_abs_v_minus_v0"] < 1e-15
+
+
+def test_bs_closed_form(golden):
+    b = golden["cases"]["bs"]
+    assert O.bs_price(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, True) == pytest.approx(b["cfg1_call"], rel=1e-14)
+    assert O.bs_price(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, False) == pytest.approx(b["cfg1_put"], rel=1e-14)
+    assert O.bs_delta(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, True) == pytest.approx(b["cfg1_delta_call"], rel=1e-14)
+    assert O.bs_delta(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, False) == pytest.approx(b["cfg1_delta_put"], rel=1e-14)
+    assert O.bs_price(110.0, 100.0, 0.0, 0.05, 0.0, 0.2, True) == b["expired_call"] == 10.0
+    assert O.bs_delta(90.0, 100.0, 0.0, 0.05, 0.0, 0.2, False) == b["expired_put_delta"] == -1.0
+    assert O.bs_price(22500.0, 22500.0, 0.04, 0.065, 0.012, 0.2, True) == pytest.approx(b["verify_py"], rel=1e-14)
+    assert b["cfg1_call"] == pytest.approx(374.0712289657911, rel=1e-14)
+
+
+def _price_cases(golden, big):
+    return [c for c in golden["cases"]["price"] if (c["n"] > 5000) == big]
+
+
+def _check_price(golden, c):
+    eng = O.MonteCarloOracle(P(golden, c["params"]), c["n"], c["num_steps"], c["seed"],
+                             c["sobol"], c["anti"], c["cv"])
+    got = eng.price(c["spot"], c["strike"], c["T"], c["is_call"])
+    want = c["result"]
+    assert set(got) == set(want)
+    for k, w in want.items():
+        # std_error of the degenerate anti-off pseudo-CV is exactly 0 in the reference (quirk 2)
+        assert got[k] == pytest.approx(w, rel=1e-10, abs=1e-9), (k, c)
+
+
+def test_price_small(golden):
+    cases = _price_cases(golden, big=False)
+    assert len(cases) >= 24
+    for c in cases:
+        _check_price(golden, c)
+
+
+def test_price_cfg1_50k(golden):
+    """BASELINE config 1 at the reference's own size (50k x 250): a few seconds of NumPy RNG."""
+    cases = [c for c in _price_cases(golden, big=True) if c["is_call"]]
+    for c in cases:
+        _check_price(golden, c)
+    plain = [c for c in cases if not c["anti"] and not c["cv"]][0]["result"]
+    assert plain["price"] == pytest.approx(373.80196, abs=1e-5)
+    assert plain["std_error"] == pytest.approx(2.57214, abs=1e-5)
+
+
+def test_price_batch(golden):
+    for c in golden["cases"]["price_batch"]:
+        eng = O.MonteCarloOracle(P(golden, c["params"]), c["n"], c["num_steps"], c["seed"], False, c["anti"], c["cv"])
+        got = eng.price_batch(c["spot"], np.array(c["strikes"]), c["T"], c["is_call"])
+        assert len(got) == len(c["result"])
+        for g, w in zip(got, c["result"]):
+            assert set(g) == set(w)
+            for k in w:
+                assert g[k] == pytest.approx(w[k], rel=1e-10, abs=1e-9)
+
+
+def test_sample_paths(golden, garr):
+    got = O.MonteCarloOracle(P(golden, "svj_default"), 1000, seed=42).get_sample_paths(22500.0, 0.1, 8)
+    assert got.shape == garr["sample_paths_svj"].shape == (8, 51)
+    np.testing.assert_allclose(got, garr["sample_paths_svj"], rtol=RTOL)
+    got = O.MonteCarloOracle(P(golden, "gbm_cfg1"), 10, 250, seed=1).get_sample_paths(2500.0, 1.0, 5)
+    np.testing.assert_allclose(got, garr["sample_paths_gbm_1y"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_greeks_small(golden, idx):
+    c = [g for g in golden["cases"]["greeks"] if g["n"] <= 4096][idx]
+    g = O.GreeksOracle(P(golden, c["params"]), c["n"], c["num_steps"], c["seed"])
+    args = (c["spot"], c["strike"], c["T"], c["is_call"])
+    for name in ("delta", "vega", "gamma", "theta", "rho"):
+        got = getattr(g, name)(*args)
+        assert set(got) == set(c[name])
+        for k, w in c[name].items():
+            # theta/rho are finite differences of near-equal prices / 1e-4: allow the amplified ulp noise
+            tol = 1e-6 if name in ("theta", "rho") else 1e-9
+            assert got[k] == pytest.approx(w, rel=tol, abs=1e-9), (name, k)
+
+
+def test_greeks_cfg1_50k_delta_gamma(golden):
+    c = [g for g in golden["cases"]["greeks"] if g["n"] == 50_000 and g["is_call"]][0]
+    g = O.GreeksOracle(P(golden, c["params"]), c["n"], c["num_steps"], c["seed"])
+    d = g.delta(c["spot"], c["strike"], c["T"], True)
+    assert d["pathwise"] == pytest.approx(c["delta"]["pathwise"], rel=1e-10)
+    assert d["pathwise"] == pytest.approx(0.640732, abs=1e-6)
+
+
+def test_risk_metrics(golden, garr):
+    for c in golden["cases"]["risk"]:
+        got = O.risk_metrics(garr[f"risk_{c['name']}"], c["confidence"])
+        want = unnan(c["result"])
+        assert set(got) == set(want)
+        for k, w in want.items():
+            if np.isnan(w):
+                assert np.isnan(got[k]), (c["name"], k)
+            else:
+                assert got[k] == pytest.approx(w, rel=1e-12, abs=1e-15), (c["name"], k)
+
+
+def test_bb_order_and_reorder(golden, garr):
+    for k, want in golden["cases"]["bb_order"].items():
+        assert O.bb_order(int(k)) == want
+    out = O.bb_reorder(garr["bb_in"], 31)
+    np.testing.assert_allclose(out, garr["bb_out"], rtol=1e-13, atol=1e-16)
+    # quirk 1: the bridge pins W_T to 0
+    assert np.max(np.abs(out.sum(axis=1))) < 1e-12
+
+
+def test_sobol_front_end(garr):
+    np.testing.assert_array_equal(O.sobol_normals(100, 12, seed=3), garr["sobol_100x12_seed3"])
+
+
+def test_philox_kat(golden):
+    lib = O._load()
+    for kat in golden["cases"]["philox_kat"]:
+        ctr = np.array([int(x, 16) for x in kat["ctr"]], dtype=np.uint32)
+        key = np.array([int(x, 16) for x in kat["key"]], dtype=np.uint32)
+        want = np.array([int(x, 16) for x in kat["out"]], dtype=np.uint32)
+        np.testing.assert_array_equal(O.philox4x32_10(ctr, key), want)
+        out = np.zeros(4, dtype=np.uint32)
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        lib.oracle_philox4x32_10(ctr.ctypes.data_as(u32p), key.ctypes.data_as(u32p), out.ctypes.data_as(u32p))
+        np.testing.assert_array_equal(out, want)
+
+
+def test_philox_block_words_layout():
+    seed, off = 0x1234567890ABCDEF, (1 << 32) - 2       # crosses the path_lo carry
+    w = O.philox_block_words(seed, off, 5, 3, 1)
+    ctr = np.zeros((5, 3, 4), dtype=np.uint32)
+    for i in range(5):
+        for b in range(3):
+            p = off + i
+            ctr[i, b] = (p & 0xFFFFFFFF, p >> 32, b, 1)
+    key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32), (5, 3, 2))
+    np.testing.assert_array_equal(w, O.philox4x32_10(ctr, key))
