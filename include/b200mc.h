@@ -1,0 +1,217 @@
+/*
+ * b200mc.h -- C ABI of libb200mc.so, the B200 (sm_100a) Monte Carlo pricing core.
+ *
+ * This is the drop-in boundary for ONE hot path of Jay14090/Monte-Carlo-Option-Simulator: the SVJ/GBM
+ * path simulation and the payoff / Greek / VaR reductions built on it.  The reference has no FFI of its
+ * own (pure Python + Numba); each entry point below names the reference interface it replaces
+ * (file:line relative to the reference tree).  The Python host mirror that binds these with ctypes is
+ * monte_carlo_option_simulator_b200/_lib.py; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - Plain C types only.  Every buffer is allocated by the caller; the library never returns memory it owns.
+ *   - Every function returns 0 on success or a B200MC_E* code; it never aborts or throws across the ABI.
+ *     b200mc_last_error(h) gives the message of the last failure on that handle (NULL handle: the message of
+ *     the last failed b200mc_create on this thread).  The string is valid until the next call on the handle.
+ *   - A handle is bound to one CUDA device and owns one stream plus scratch; it is NOT thread-safe (one call
+ *     in flight per handle), matching the reference where every caller is serial (engine/app.py:130-236,
+ *     engine/calibration.py:202).  Calls are synchronous unless the name ends in _async.
+ *   - Host pointers may be pageable or pinned.  *_dev variants take device pointers valid on the handle's
+ *     device and run on the handle's stream.
+ *   - There is no CPU fallback: without a usable sm_100 device b200mc_create fails with B200MC_ENODEVICE.
+ *
+ * Random numbers (fused modes): counter-based Philox4x32-10, key = (seed_lo, seed_hi),
+ * counter = (path_lo, path_hi, block, stream) with `path` the GLOBAL path index (path_offset + i), so a
+ * path draws the same numbers whatever the launch geometry or the number of GPUs.  Streams:
+ *   B200MC_STREAM_GBM    block j -> 4 normals for steps 4j..4j+3: (z0,z1)=BM(w0,w1), (z2,z3)=BM(w2,w3)
+ *   B200MC_STREAM_HESTON block j -> steps 2j, 2j+1: (Z1,Z2)=BM(w0,w1) for 2j, BM(w2,w3) for 2j+1
+ *   B200MC_STREAM_SVJ    block j -> step j: (Z1,Z2)=BM(w0,w1), U_jump=(w2+0.5)/2^32, Z_jump_size=ICDF(w3)
+ * BM(wa,wb): u1 = 2 - f(wa) in (0,1], f(w) = float with mantissa w & 0x7fffff in [1,2);  R = sqrt(-2 ln u1);
+ * angle = 2 pi f(wb);  pair = (R cos, R sin).  b200mc_dump_normals returns exactly the values the fused
+ * kernels use, so the reference (or the oracle) can be fed identical draws.
+ */
+#ifndef B200MC_H
+#define B200MC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MC_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define B200MC_OK        0
+#define B200MC_EINVAL    1 /* bad argument (NULL pointer, n <= 0, ...)           */
+#define B200MC_ENODEVICE 2 /* no CUDA device / not an sm_100 part                */
+#define B200MC_ECUDA     3 /* CUDA runtime error (message has the CUDA string)   */
+#define B200MC_ENOMEM    4 /* device or pinned-host allocation failed            */
+
+/* flags for the fused entry points */
+#define B200MC_ANTITHETIC 0x1u  /* also evolve the twin (-Z1,-Z2,U,-Zjs): engine/monte_carlo.py:318-324 */
+#define B200MC_GREEKS     0x2u  /* fill the bump / pathwise accumulators of b200mc_sums                  */
+#define B200MC_FP64       0x4u  /* evolve the path state and the payoff in fp64 (draws are unchanged)    */
+#define B200MC_FORCE_SVJ  0x8u  /* use the general SVJ kernel even when xi == 0 and lambda_j == 0        */
+
+#define B200MC_STREAM_GBM    0u
+#define B200MC_STREAM_HESTON 1u
+#define B200MC_STREAM_SVJ    2u
+
+/* which array b200mc_dump_normals returns */
+#define B200MC_Z1         0
+#define B200MC_Z2         1
+#define B200MC_ZJUMP_U    2
+#define B200MC_ZJUMP_SIZE 3
+
+#define B200MC_F32 0
+#define B200MC_F64 1
+
+typedef struct b200mc_handle b200mc_handle;
+
+/* Field set of SVJParams, engine/models.py:31-44. */
+typedef struct {
+    double v0, r, q, kappa, theta, xi, rho, lambda_j, mu_j, sigma_j;
+} b200mc_svj_params;
+
+/* Bump sizes for the CRN finite-difference Greeks (all evaluated on the SAME draws as the base path). */
+typedef struct {
+    double spot_bump; /* relative: spot*(1 +- b); engine/greeks.py:54,79-80,168,179 (0.01)  */
+    double v0_up;     /* absolute bumped v0; engine/greeks.py:124 (v0 + 0.01)               */
+    double v0_dn;     /* engine/greeks.py:125 (max(v0 - 0.01, 0.001))                       */
+    double r_up;      /* absolute bumped rate; engine/greeks.py:235 (r + 1e-4)              */
+    double r_dn;      /* engine/greeks.py:239 (max(r - 1e-4, 0))                            */
+} b200mc_bumps;
+
+/*
+ * Per-strike sums over the paths of one launch (all fp64, all UNDISCOUNTED payoffs).
+ * a_i = payoff of the primary path, b_i = payoff of its antithetic twin (0 when ANTITHETIC is off).
+ * Everything MonteCarloEngine.price / price_batch return derives from n, sum_a, sum_b, sum_aa, sum_bb,
+ * sum_ab (engine/monte_carlo.py:327-373, :416-448); the Greek fields feed GreeksEngine (engine/greeks.py).
+ * Bumped payoffs use the primary path only (the reference's Greeks never use antithetic draws).
+ */
+typedef struct {
+    double n;            /* number of primary paths accumulated                                      */
+    double sum_a, sum_b, sum_aa, sum_bb, sum_ab;
+    double sum_s;        /* sum of S_T (pair average with ANTITHETIC): true control variate, E known */
+    double sum_ss;       /* sum of that quantity squared                                             */
+    double sum_ps;       /* sum of (pair-averaged payoff) * (pair-averaged S_T)                      */
+    /* --- filled only with B200MC_GREEKS (else 0) ------------------------------------------------- */
+    double sum_pw_delta; /* sum 1{ITM} S_T / S0                  engine/greeks.py:71-76              */
+    double sum_spot_up;  /* sum payoff(S_T (1+b))                engine/greeks.py:79,83 / :184,189   */
+    double sum_spot_dn;  /* sum payoff(S_T (1-b))                engine/greeks.py:80,84 / :185,190   */
+    double sum_v0_up;    /* sum payoff(S_T | v0 = v0_up)         engine/greeks.py:136-141,150        */
+    double sum_v0_dn;    /* sum payoff(S_T | v0 = v0_dn)         engine/greeks.py:142-147,151        */
+    double sum_r_up;     /* sum payoff(S_T e^{(r_up-r)T})  (discount with r_up on the host)          */
+    double sum_r_dn;     /* sum payoff(S_T e^{(r_dn-r)T})                                            */
+    double sum_pw_vega;  /* sum 1{ITM} S_T dlogS_T/dsigma, constant-variance (GBM) case only; new    */
+} b200mc_sums;
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+int b200mc_version(void);
+int b200mc_create(int device, b200mc_handle **out);
+int b200mc_destroy(b200mc_handle *h);
+const char *b200mc_last_error(const b200mc_handle *h);
+/* sm_count, max SM clock (kHz), HBM bytes, compute capability (major*10+minor) of the handle's device */
+int b200mc_device_info(const b200mc_handle *h, int *sm_count, int *sm_clock_khz, uint64_t *hbm_bytes, int *cc);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t b200mc_launch_count(const b200mc_handle *h);
+/* cudaStream_t of the handle as an integer, so a caller can record CUDA events on the launching stream */
+uint64_t b200mc_stream(const b200mc_handle *h);
+/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream, so that a following NCCL all-reduce is ordered
+ * after the kernels).  The handle's own stream is drained and destroyed; the caller keeps ownership of the new one. */
+int b200mc_set_stream(b200mc_handle *h, uint64_t stream);
+int b200mc_synchronize(b200mc_handle *h);
+
+/* ---- a1: deterministic "given normals" mode ------------------------------------------------------------
+ * Drop-in for _simulate_svj_paths_numba(S0, v0, r, q, T, kappa, theta, xi, rho, lambda_j, mu_j, sigma_j,
+ * Z1, Z2, Z_jump, Z_jump_size, num_steps, record_paths), engine/monte_carlo.py:189-243.
+ * Z* are C-contiguous float64 [n_paths, n_steps] HOST arrays; S_final, v_final float64 [n_paths];
+ * all_paths float64 [n_paths, n_steps + 1] (column 0 = S0) or NULL when record_paths == 0.  fp64 arithmetic,
+ * the reference's operation order (multiplicative S *= exp(..)); expect ~1e-13 relative agreement.
+ * Arrays the parameters make irrelevant are not read (nor copied to the device): Z2 when xi == 0, and Z_jump /
+ * Z_jump_size when lambda_j * dt <= 0 (Z_jump is a uniform in [0, 1), so the test at :233 cannot fire). */
+int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                  int64_t n_paths, int32_t n_steps,
+                                  const double *Z1, const double *Z2,
+                                  const double *Z_jump, const double *Z_jump_size,
+                                  int record_paths, double *S_final, double *v_final, double *all_paths);
+/* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the handle's stream. */
+int b200mc_simulate_given_normals_dev(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                      int64_t n_paths, int32_t n_steps,
+                                      const double *Z1, const double *Z2,
+                                      const double *Z_jump, const double *Z_jump_size,
+                                      int record_paths, double *S_final, double *v_final, double *all_paths);
+
+/* ---- a2+a1+a3/a4/a6-a9 fused: Philox draws in registers, payoff and Greek sums reduced on chip ----------
+ * Replaces the RNG front end + both kernel runs + the NumPy reductions of MonteCarloEngine.price
+ * (engine/monte_carlo.py:273-375), .price_batch (:377-450) and GreeksEngine.delta/vega/gamma
+ * (engine/greeks.py:53-203) for the pseudo-random case.  Simulates global paths
+ * [path_offset, path_offset + n_paths) for n_steps steps of dt = T / n_steps (the caller applies the
+ * reference's steps rule, monte_carlo.py:287) and writes one b200mc_sums per strike into out[n_strikes]
+ * (host memory).  `bumps` may be NULL unless B200MC_GREEKS is set.  is_call: 1 call, 0 put.
+ * No path matrix touches HBM.  Sums of disjoint path ranges add (multi-GPU: all-reduce the structs). */
+int b200mc_price_european(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                          int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                          const double *strikes, int32_t n_strikes, int is_call, uint32_t flags,
+                          const b200mc_bumps *bumps, b200mc_sums *out);
+/* Asynchronous form: launches on the handle's stream, results land in out_dev (DEVICE, n_strikes structs). */
+int b200mc_price_european_async(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                                const double *strikes, int32_t n_strikes, int is_call, uint32_t flags,
+                                const b200mc_bumps *bumps, b200mc_sums *out_dev);
+
+/* Terminal values of the fused simulation (deterministic-mode parity of the fused kernels, and the terminal
+ * P&L vector for compute_risk_metrics, engine/risk.py:117).  S_T / S_T_anti / v_T are [n_paths] of `dtype`
+ * (B200MC_F32 / B200MC_F64); any may be NULL.  on_device != 0: pointers are device memory. */
+int b200mc_simulate_terminal(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                             int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                             uint32_t flags, int dtype, int on_device,
+                             void *S_T, void *S_T_anti, void *v_T);
+
+/* ---- a5 / path-storing mode ------------------------------------------------------------------------------
+ * MonteCarloEngine.get_sample_paths (engine/monte_carlo.py:452-471) at scale: the full path matrix
+ * [n_paths, n_steps + 1], row-major with leading dimension ld >= n_steps + 1 (elements), column 0 = S0
+ * (:216-217,241).  Tiles are staged through shared memory and written with coalesced 128-bit stores. */
+int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                          int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                          uint32_t flags, int dtype, int on_device, void *out, int64_t ld);
+
+/* ---- a10: tail metrics -----------------------------------------------------------------------------------
+ * compute_risk_metrics(returns, confidence), engine/risk.py:117-155 (+ _hill_estimator :158-173), with the
+ * same index conventions (cutoff = int(n (1 - c)), var = -sorted[cutoff], cvar = -mean(sorted[:cutoff])).
+ * out[8] = { var, cvar, skewness, kurtosis, excess_kurtosis, tail_index, mean, std }.  Order statistics are
+ * found by radix select (exact, no sort). */
+int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device,
+                        double confidence, double out[8]);
+
+/* ---- draws, for feeding the reference the identical numbers ----------------------------------------------
+ * out is float64 [n_paths, n_steps] on the host; `stream` one of B200MC_STREAM_*; `which` one of B200MC_Z*.
+ * Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0). */
+int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
+                        int32_t n_steps, uint32_t stream, int which, double *out);
+/* Raw Philox words uint32 [n_paths, n_blocks, 4] (host), for the bit-exact check against the oracle. */
+int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
+                       int32_t n_blocks, uint32_t stream, uint32_t *out);
+
+/* ---- device memory helpers for callers without a CUDA runtime of their own (ctypes) ---------------------- */
+int b200mc_malloc(b200mc_handle *h, size_t bytes, void **dev_ptr);
+int b200mc_free(b200mc_handle *h, void *dev_ptr);
+int b200mc_memcpy_h2d(b200mc_handle *h, void *dst_dev, const void *src_host, size_t bytes);
+int b200mc_memcpy_d2h(b200mc_handle *h, void *dst_host, const void *src_dev, size_t bytes);
+int b200mc_malloc_host(b200mc_handle *h, size_t bytes, void **host_ptr); /* pinned */
+int b200mc_free_host(b200mc_handle *h, void *host_ptr);
+/* CUDA-event timing on the handle's stream: call begin, enqueue work, call end -> elapsed ms */
+int b200mc_timer_begin(b200mc_handle *h);
+int b200mc_timer_end(b200mc_handle *h, float *elapsed_ms);
+
+/* ---- issue-rate probes: the denominators of the fused kernel's instruction roofline --------------------------
+ * which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox call + two
+ * Box-Muller pairs, 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 pairs.  *ops_per_s: thread-level operations per
+ * second over the whole device (CUDA events, best of 3 after a warm-up launch). */
+int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MC_H */

@@ -1,0 +1,321 @@
+"""ctypes binding of libb200mc.so (C ABI in include/b200mc.h).
+
+This is the only place the shared library is loaded.  There is no CPU fallback: if the library is missing
+(`python __graft_entry__.py build` / `make -C monte_carlo_option_simulator_b200/csrc` builds it) or no sm_100
+device is visible, every compute entry point raises -- it never silently routes anywhere else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200mc.so")
+
+OK, EINVAL, ENODEVICE, ECUDA, ENOMEM = 0, 1, 2, 3, 4
+ANTITHETIC, GREEKS, FP64, FORCE_SVJ = 0x1, 0x2, 0x4, 0x8
+STREAM_GBM, STREAM_HESTON, STREAM_SVJ = 0, 1, 2
+Z1, Z2, ZJUMP_U, ZJUMP_SIZE = 0, 1, 2, 3
+F32, F64 = 0, 1
+
+
+class B200MCError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (callers of the reference catch Exception broadly:
+    engine/calibration.py:84-89, engine/app.py:139-140)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb200mc error {code}: {msg}")
+        self.code = code
+
+
+class SvjParams(C.Structure):
+    """b200mc_svj_params -- field set of SVJParams, engine/models.py:31-44."""
+    _fields_ = [(n, C.c_double) for n in
+                ("v0", "r", "q", "kappa", "theta", "xi", "rho", "lambda_j", "mu_j", "sigma_j")]
+
+
+class Bumps(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("spot_bump", "v0_up", "v0_dn", "r_up", "r_dn")]
+
+
+SUMS_FIELDS = ("n", "sum_a", "sum_b", "sum_aa", "sum_bb", "sum_ab", "sum_s", "sum_ss", "sum_ps",
+               "sum_pw_delta", "sum_spot_up", "sum_spot_dn", "sum_v0_up", "sum_v0_dn", "sum_r_up", "sum_r_dn",
+               "sum_pw_vega")
+NSUMS = len(SUMS_FIELDS)
+
+
+class Sums(C.Structure):
+    _fields_ = [(n, C.c_double) for n in SUMS_FIELDS]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_i32, _i64, _u32, _u64, _dbl, _vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double, C.c_void_p
+_dp = C.POINTER(C.c_double)
+_PROTOS = {
+    # name: (restype, argtypes)
+    "b200mc_version": (C.c_int, []),
+    "b200mc_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "b200mc_destroy": (C.c_int, [_vp]),
+    "b200mc_last_error": (C.c_char_p, [_vp]),
+    "b200mc_device_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_u64), C.POINTER(C.c_int)]),
+    "b200mc_launch_count": (_i64, [_vp]),
+    "b200mc_stream": (_u64, [_vp]),
+    "b200mc_set_stream": (C.c_int, [_vp, _u64]),
+    "b200mc_synchronize": (C.c_int, [_vp]),
+    "b200mc_simulate_given_normals": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i64, _i32,
+                                                 _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "b200mc_simulate_given_normals_dev": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i64, _i32,
+                                                     _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "b200mc_price_european": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
+                                         _vp, _i32, C.c_int, _u32, C.POINTER(Bumps), _vp]),
+    "b200mc_price_european_async": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
+                                               _vp, _i32, C.c_int, _u32, C.POINTER(Bumps), _vp]),
+    "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
+                                            _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
+                                         _u32, C.c_int, C.c_int, _vp, _i64]),
+    "b200mc_risk_metrics": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dbl, _dp]),
+    "b200mc_dump_normals": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, C.c_int, _vp]),
+    "b200mc_dump_philox": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, _vp]),
+    "b200mc_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "b200mc_free": (C.c_int, [_vp, _vp]),
+    "b200mc_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "b200mc_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "b200mc_malloc_host": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "b200mc_free_host": (C.c_int, [_vp, _vp]),
+    "b200mc_timer_begin": (C.c_int, [_vp]),
+    "b200mc_timer_end": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "b200mc_microbench": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+}
+EXPORTS = tuple(_PROTOS)
+
+
+def load() -> C.CDLL:
+    """Load libb200mc.so and set the prototypes.  Raises (never falls back) when the library is absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B200MCError(ENODEVICE, f"{LIB_PATH} is not built (run `python __graft_entry__.py build`); "
+                                         "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def to_params(p) -> SvjParams:
+    """Accepts the reference's SVJParams, ours, or anything with the ten fields (duck-typed)."""
+    return SvjParams(*(float(getattr(p, n)) for n, _ in SvjParams._fields_))
+
+
+def _ptr(a) -> Optional[int]:
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+class Handle:
+    """One b200mc_handle: one device, one stream, scratch.  Not thread-safe (one call in flight)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.b200mc_create(int(device), C.byref(h))
+        if rc != OK:
+            raise B200MCError(rc, (self.lib.b200mc_last_error(None) or b"").decode())
+        self.h = h
+        self.device = int(device)
+
+    # -- plumbing ------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != OK:
+            raise B200MCError(rc, (self.lib.b200mc_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200mc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self):
+        sm, khz, cc, hbm = C.c_int(), C.c_int(), C.c_int(), _u64()
+        self._check(self.lib.b200mc_device_info(self.h, C.byref(sm), C.byref(khz), C.byref(hbm), C.byref(cc)))
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "hbm_bytes": hbm.value, "cc": cc.value}
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.b200mc_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.b200mc_stream(self.h))
+
+    def set_stream(self, stream: int):
+        self._check(self.lib.b200mc_set_stream(self.h, int(stream)))
+
+    def synchronize(self):
+        self._check(self.lib.b200mc_synchronize(self.h))
+
+    def timer_begin(self):
+        self._check(self.lib.b200mc_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.b200mc_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def microbench(self, which: int, iters: int = 4096) -> float:
+        v = C.c_double()
+        self._check(self.lib.b200mc_microbench(self.h, int(which), int(iters), C.byref(v)))
+        return float(v.value)
+
+    def malloc(self, nbytes: int) -> int:
+        p = _vp()
+        self._check(self.lib.b200mc_malloc(self.h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def free(self, ptr: int):
+        self._check(self.lib.b200mc_free(self.h, _vp(ptr)))
+
+    def h2d(self, dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._check(self.lib.b200mc_memcpy_h2d(self.h, _vp(dst), src.ctypes.data, src.nbytes))
+
+    def d2h(self, dst: np.ndarray, src: int):
+        assert dst.flags["C_CONTIGUOUS"]
+        self._check(self.lib.b200mc_memcpy_d2h(self.h, dst.ctypes.data, _vp(src), dst.nbytes))
+
+    # -- a1: deterministic mode ------------------------------------------------------------------------
+    def simulate_given_normals(self, params, S0, T, Z1, Z2, Z_jump, Z_jump_size, n_steps, record_paths=False):
+        arrs = [np.ascontiguousarray(z, dtype=np.float64) for z in (Z1, Z2, Z_jump, Z_jump_size)]
+        n = arrs[0].shape[0] if arrs[0].ndim else 0
+        for z in arrs:
+            if z.ndim != 2 or z.shape[0] != n or z.shape[1] < n_steps:
+                raise B200MCError(EINVAL, "Z arrays must be [n_paths, >= n_steps] with a common n_paths")
+        if any(z.shape[1] != n_steps for z in arrs):      # the reference indexes Z[i, step] for step < num_steps
+            arrs = [np.ascontiguousarray(z[:, :n_steps]) for z in arrs]
+        S = np.empty(n, dtype=np.float64)
+        v = np.empty(n, dtype=np.float64)
+        paths = np.empty((n, n_steps + 1), dtype=np.float64) if record_paths else None
+        sp = to_params(params)
+        self._check(self.lib.b200mc_simulate_given_normals(
+            self.h, C.byref(sp), float(S0), float(T), n, int(n_steps), _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+            _ptr(arrs[3]), int(bool(record_paths)), _ptr(S), _ptr(v), _ptr(paths)))
+        return S, v, paths
+
+    # -- fused European --------------------------------------------------------------------------------
+    def price_european(self, params, S0, T, n_steps, n_paths, seed, strikes, is_call=True, flags=0,
+                       bumps: Optional[Bumps] = None, path_offset=0, out_dev: Optional[int] = None):
+        """Returns a float64 array [n_strikes, NSUMS] (columns = SUMS_FIELDS), or None when `out_dev`
+        (device pointer to n_strikes b200mc_sums) is given: then the launch is asynchronous."""
+        strikes = np.ascontiguousarray(np.atleast_1d(strikes), dtype=np.float64)
+        sp = to_params(params)
+        bp = C.byref(bumps) if bumps is not None else None
+        args = (self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & (2 ** 64 - 1),
+                int(path_offset), strikes.ctypes.data, int(strikes.size), int(bool(is_call)), int(flags), bp)
+        if out_dev is not None:
+            self._check(self.lib.b200mc_price_european_async(*args, _vp(out_dev)))
+            return None
+        out = np.empty((strikes.size, NSUMS), dtype=np.float64)
+        self._check(self.lib.b200mc_price_european(*args, out.ctypes.data))
+        return out
+
+    def simulate_terminal(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,
+                          want_anti=False, want_v=False, dev_ptrs=None):
+        dt = np.dtype(dtype)
+        code = F64 if dt == np.float64 else F32
+        sp = to_params(params)
+        if dev_ptrs is not None:
+            S, A, V = dev_ptrs
+            self._check(self.lib.b200mc_simulate_terminal(
+                self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & (2 ** 64 - 1),
+                int(path_offset), int(flags), code, 1, _vp(S) if S else None, _vp(A) if A else None,
+                _vp(V) if V else None))
+            return None
+        S = np.empty(n_paths, dtype=dt)
+        A = np.empty(n_paths, dtype=dt) if want_anti else None
+        V = np.empty(n_paths, dtype=dt) if want_v else None
+        self._check(self.lib.b200mc_simulate_terminal(
+            self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & (2 ** 64 - 1),
+            int(path_offset), int(flags), code, 0, _ptr(S), _ptr(A), _ptr(V)))
+        return S, A, V
+
+    def generate_paths(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,
+                       ld: Optional[int] = None, out_dev: Optional[int] = None):
+        dt = np.dtype(dtype)
+        code = F64 if dt == np.float64 else F32
+        ld = int(ld) if ld is not None else int(n_steps) + 1
+        sp = to_params(params)
+        if out_dev is not None:
+            self._check(self.lib.b200mc_generate_paths(
+                self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & (2 ** 64 - 1),
+                int(path_offset), int(flags), code, 1, _vp(out_dev), ld))
+            return None
+        out = np.empty((n_paths, ld), dtype=dt)
+        self._check(self.lib.b200mc_generate_paths(
+            self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & (2 ** 64 - 1),
+            int(path_offset), int(flags), code, 0, out.ctypes.data, ld))
+        return out[:, :n_steps + 1] if ld != n_steps + 1 else out
+
+    def risk_metrics(self, pnl, confidence=0.99, n: Optional[int] = None, dtype=None) -> np.ndarray:
+        """pnl: NumPy array (host) or an int device pointer (then n and dtype are required)."""
+        out = np.empty(8, dtype=np.float64)
+        if isinstance(pnl, int):
+            code = F64 if np.dtype(dtype) == np.float64 else F32
+            self._check(self.lib.b200mc_risk_metrics(self.h, _vp(pnl), int(n), code, 1, float(confidence),
+                                                      out.ctypes.data_as(_dp)))
+            return out
+        a = np.asarray(pnl)
+        if a.dtype != np.float32:
+            a = a.astype(np.float64, copy=False)
+        a = np.ascontiguousarray(a).ravel()
+        code = F64 if a.dtype == np.float64 else F32
+        self._check(self.lib.b200mc_risk_metrics(self.h, a.ctypes.data, a.size, code, 0, float(confidence),
+                                                  out.ctypes.data_as(_dp)))
+        return out
+
+    def dump_normals(self, seed, n_paths, n_steps, stream, which, path_offset=0) -> np.ndarray:
+        out = np.empty((n_paths, n_steps), dtype=np.float64)
+        self._check(self.lib.b200mc_dump_normals(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths),
+                                                  int(n_steps), int(stream), int(which), out.ctypes.data))
+        return out
+
+    def dump_philox(self, seed, n_paths, n_blocks, stream, path_offset=0) -> np.ndarray:
+        out = np.empty((n_paths, n_blocks, 4), dtype=np.uint32)
+        self._check(self.lib.b200mc_dump_philox(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths),
+                                                 int(n_blocks), int(stream), out.ctypes.data))
+        return out
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_handle(device: Optional[int] = None) -> Handle:
+    """Process-wide handle per device (LOCAL_RANK picks the device under torchrun)."""
+    if device is None:
+        device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        h = _default.get(device)
+        if h is None or h.h is None:
+            h = Handle(device)
+            _default[device] = h
+        return h

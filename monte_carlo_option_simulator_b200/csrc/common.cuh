@@ -1,0 +1,124 @@
+// common.cuh -- handle, error plumbing and reduction helpers shared by the kernels of libb200mc.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200mc.h"
+#include "philox.cuh"
+
+struct b200mc_handle {
+    int device;
+    int sm_count;
+    int sm_clock_khz;
+    int cc;
+    uint64_t hbm_bytes;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int64_t launches;
+    // scratch (grown on demand, never shrunk)
+    void *d_scratch;        size_t scratch_bytes;      // block partials, weights, device-side results
+    void *d_stage;          size_t stage_bytes;        // staging for host<->device array arguments
+    void *h_pinned;         size_t pinned_bytes;       // pinned bounce buffer for small arguments
+    void *d_result;         size_t result_bytes;       // device-side results of the synchronous entry points
+    bool own_stream;                                   // false after b200mc_set_stream
+    unsigned int *d_counter;                           // "last block reduces" ticket
+    char err[512];
+};
+
+namespace b200mc {
+
+extern thread_local char g_create_err[512];
+
+inline int fail(b200mc_handle *h, int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    char *dst = h ? h->err : g_create_err;
+    snprintf(dst, 512, fmt, a, b);
+    return code;
+}
+
+#define B200MC_CUDA(h, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? B200MC_ENOMEM : B200MC_ECUDA;    \
+            return b200mc::fail((h), code__, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+        }                                                                                      \
+    } while (0)
+
+#define B200MC_TRY(expr)            \
+    do {                            \
+        int rc__ = (expr);          \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pinned = false)
+{
+    if (*have >= want) return 0;
+    if (*p) {
+        if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    size_t sz = want + want / 4 + 4096;
+    cudaError_t e = pinned ? cudaMallocHost(p, sz) : cudaMalloc(p, sz);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, B200MC_ENOMEM, "%s of scratch failed: %s", pinned ? "cudaMallocHost" : "cudaMalloc",
+                    cudaGetErrorString(e));
+    }
+    *have = sz;
+    return 0;
+}
+
+// ---- warp / block reduction of NV doubles, deterministic "last block sums the partials" finish ---------
+template <int NV>
+__device__ __forceinline__ void warp_reduce(double (&v)[NV])
+{
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+}
+
+// Block partial -> partials[blockIdx.x * NV + i]; the last block to arrive adds all partials in block
+// order (fixed order => bitwise reproducible for a given launch geometry) and writes out[i].
+// smem must hold (blockDim.x / 32) * NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_finish(double (&v)[NV], double *smem, double *partials,
+                                             unsigned int *counter, double *out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    warp_reduce<NV>(v);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) smem[warp * NV + i] = v[i];
+    }
+    __syncthreads();
+    __shared__ bool is_last;
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < nwarp; ++w) s += smem[w * NV + threadIdx.x];
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < NV) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NV + threadIdx.x];
+            out[threadIdx.x] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0u;   // re-arm for the next launch on this stream
+    }
+}
+
+} // namespace b200mc

@@ -1,0 +1,98 @@
+// dump.cu -- the draws of the fused kernels, exported so that the reference (or the oracle) can be fed the
+// IDENTICAL numbers ("deterministic mode" of the acceptance contract).  Not in the reference.
+//
+// b200mc_dump_normals returns, as float64 [n_paths, n_steps], exactly the values the fused kernels consume:
+//   Z1 / Z2        BM_SCALE * (double)raw   with raw the fp32 Box-Muller output of philox.cuh
+//   Z_jump         (w + 0.5) / 2^32                                   (SVJ stream; 1.0 = "never jumps" elsewhere)
+//   Z_jump_size    (double)normcdfinvf(((w >> 8) + 0.5) / 2^24)       (SVJ stream; 0 elsewhere)
+// Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0).
+#include "common.cuh"
+
+namespace b200mc {
+
+__global__ void k_dump_philox(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_blocks, uint32_t stream,
+                              uint32_t *__restrict__ out)
+{
+    const int64_t total = n_paths * n_blocks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t path = path0 + (uint64_t)(i / n_blocks);
+        const uint32_t blk = (uint32_t)(i % n_blocks);
+        const U4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk, stream, key);
+        reinterpret_cast<uint4 *>(out)[i] = make_uint4(w.x, w.y, w.z, w.w);
+    }
+}
+
+__global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_steps, uint32_t stream, int which,
+                               double *__restrict__ out)
+{
+    const int per = stream == B200MC_STREAM_GBM ? 4 : (stream == B200MC_STREAM_HESTON ? 2 : 1);
+    const int n_blocks = (n_steps + per - 1) / per;
+    const int64_t total = n_paths * n_blocks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pi = i / n_blocks;
+        const uint64_t path = path0 + (uint64_t)pi;
+        const int blk = (int)(i % n_blocks);
+        const U4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)blk, stream, key);
+        const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
+        double vals[4];
+        int nv = per;
+        if (stream == B200MC_STREAM_GBM) {
+            const float r[4] = {p.rc, p.rs, q.rc, q.rs};
+            for (int t = 0; t < 4; ++t)
+                vals[t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)r[t] : (which == B200MC_ZJUMP_U ? 1.0 : 0.0);
+        } else if (stream == B200MC_STREAM_HESTON) {
+            const float z1[2] = {p.rc, q.rc}, z2[2] = {p.rs, q.rs};
+            for (int t = 0; t < 2; ++t)
+                vals[t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)z1[t]
+                        : which == B200MC_Z2 ? B200MC_BM_SCALE * (double)z2[t]
+                        : which == B200MC_ZJUMP_U ? 1.0 : 0.0;
+        } else {
+            vals[0] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)p.rc
+                    : which == B200MC_Z2 ? B200MC_BM_SCALE * (double)p.rs
+                    : which == B200MC_ZJUMP_U ? jump_uniform(w.z) : (double)jump_size_normal(w.w);
+        }
+        for (int t = 0; t < nv; ++t) {
+            const int s = blk * per + t;
+            if (s < n_steps) out[(size_t)pi * n_steps + s] = vals[t];
+        }
+    }
+}
+
+} // namespace b200mc
+using namespace b200mc;
+
+extern "C" int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
+                                  int32_t n_blocks, uint32_t stream, uint32_t *out)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out || n_paths <= 0 || n_blocks <= 0) return fail(h, B200MC_EINVAL, "bad argument");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)n_paths * n_blocks * 16;
+    B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, bytes));
+    k_dump_philox<<<h->sm_count * 4, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_blocks, stream,
+                                                          (uint32_t *)h->d_stage);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
+                                   int32_t n_steps, uint32_t stream, int which, double *out)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out || n_paths <= 0 || n_steps <= 0) return fail(h, B200MC_EINVAL, "bad argument");
+    if (stream > B200MC_STREAM_SVJ) return fail(h, B200MC_EINVAL, "unknown stream");
+    if (which < B200MC_Z1 || which > B200MC_ZJUMP_SIZE) return fail(h, B200MC_EINVAL, "unknown array selector");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)n_paths * n_steps * 8;
+    B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, bytes));
+    k_dump_normals<<<h->sm_count * 4, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_steps, stream,
+                                                           which, (double *)h->d_stage);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}

@@ -1,0 +1,269 @@
+// european.cu -- the fused European kernel: Philox draws in registers, log-Euler evolution, payoff and Greek
+// sums reduced on chip.  Replaces, for the pseudo-random case, the RNG front end + both kernel runs + the NumPy
+// reductions of MonteCarloEngine.price / price_batch (engine/monte_carlo.py:273-450) and the three re-simulations
+// each of GreeksEngine.delta / vega / gamma (engine/greeks.py:53-203).  No path matrix touches HBM: the only
+// global traffic is one 128-byte-per-strike partial per block and the final b200mc_sums.
+//
+// Block = 256 threads.  Phase A: every thread simulates one path (sim.cuh) and parks S_T of each state in
+// shared memory.  Phase B: thread t owns strike (t % n_strikes) and path slice (t / n_strikes) of the batch
+// and adds the payoff terms of that strike into fp64 register accumulators (for one strike this degenerates
+// to "every thread finishes its own path").  After the last batch the slices are folded through shared
+// memory, one partial per (block, strike) goes to scratch and the last block to arrive adds the partials in
+// block order, so a given launch geometry is bitwise reproducible.
+#include "prep.cuh"
+
+namespace b200mc {
+
+constexpr int EU_THREADS = 256;
+constexpr int NACC = 16;   // doubles per strike after b200mc_sums.n
+
+struct EuroArgs {
+    ModelArgs m;
+    PhiloxKey key;
+    uint64_t path0;
+    int64_t n_paths;
+    int32_t n_steps;
+    int32_t n_strikes;
+    int32_t is_call;
+    int32_t wld;
+    double up_mul, dn_mul, rup_mul, rdn_mul;   // S_T multipliers of the spot and rate bumps
+    double sigmaT;                             // sqrt(v0) T        (pathwise vega, GBM only)
+    double w_scale;                            // sqrt(dt) BM_SCALE (W_T = w_scale * sum raw z)
+};
+
+template <typename R> __device__ __forceinline__ R payoff(R s, R k, bool call)
+{
+    return call ? rmax(s - k, (R)0) : rmax(k - s, (R)0);
+}
+
+template <int MODE, bool ANTI, bool GREEKS, typename R>
+__global__ void __launch_bounds__(EU_THREADS)
+k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strikes_g,
+           const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
+           double *__restrict__ out)
+{
+    using L = StateLayout<ANTI, GREEKS>;
+    constexpr int NS = L::NS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *red = reinterpret_cast<double *>(smem_raw);                   // [256]
+    double *strikes = red + EU_THREADS;                                   // [n_strikes]
+    R *sT = reinterpret_cast<R *>(strikes + a.n_strikes);                 // [NS][256]
+    R *sW = sT + NS * EU_THREADS;                                         // [256]  sum of raw z
+    R *wtab = sW + EU_THREADS;                                            // [3][wld] (DETVAR)
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < a.n_strikes; i += EU_THREADS) strikes[i] = strikes_g[i];
+    if constexpr (MODE == MODE_DETVAR)
+        for (int i = tid; i < 3 * a.wld; i += EU_THREADS) wtab[i] = (R)wtab_g[i];
+    __syncthreads();
+
+    const int ks = a.n_strikes;
+    const int nslices = EU_THREADS / ks;
+    const int my_k = tid % ks, my_slice = tid / ks;
+    const bool worker = my_slice < nslices;
+    const bool call = a.is_call != 0;
+    const R K = (R)strikes[my_k];
+    const R S0 = (R)a.m.S0;
+
+    double acc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
+
+    for (int64_t base = (int64_t)blockIdx.x * EU_THREADS; base < a.n_paths; base += (int64_t)gridDim.x * EU_THREADS) {
+        // ---- phase A: one path per thread ---------------------------------------------------------------
+        const int64_t i = base + tid;
+        if (i < a.n_paths) {
+            R xT[NS], vT[NS], sumz;
+            simulate_path<MODE, ANTI, GREEKS, R>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT, vT,
+                                                 sumz, NoRec());
+#pragma unroll
+            for (int k = 0; k < NS; ++k) sT[k * EU_THREADS + tid] = S0 * rexp(xT[k]);
+            if constexpr (GREEKS && MODE == MODE_GBM) sW[tid] = sumz;
+        }
+        __syncthreads();
+        // ---- phase B: strike-major payoff sums -----------------------------------------------------------
+        const int64_t left = a.n_paths - base;
+        const int nvalid = left < EU_THREADS ? (int)left : EU_THREADS;
+        if (worker) {
+            for (int p = my_slice; p < nvalid; p += nslices) {
+                const R sa = sT[p];
+                const double da = (double)payoff<R>(sa, K, call);
+                double db = 0.0, s_avg = (double)sa, pay = da;
+                if constexpr (ANTI) {
+                    const R sb = sT[EU_THREADS + p];
+                    db = (double)payoff<R>(sb, K, call);
+                    s_avg = 0.5 * ((double)sa + (double)sb);
+                    pay = 0.5 * (da + db);
+                }
+                acc[0] += da;
+                acc[1] += db;
+                acc[2] = fma(da, da, acc[2]);
+                acc[3] = fma(db, db, acc[3]);
+                acc[4] = fma(da, db, acc[4]);
+                acc[5] += s_avg;
+                acc[6] = fma(s_avg, s_avg, acc[6]);
+                acc[7] = fma(pay, s_avg, acc[7]);
+                if constexpr (GREEKS) {
+                    const bool itm = call ? (sa > K) : (sa < K);                       // greeks.py:72,75
+                    if (itm) acc[8] += (double)(sa / S0);
+                    acc[9] += (double)payoff<R>(sa * (R)a.up_mul, K, call);
+                    acc[10] += (double)payoff<R>(sa * (R)a.dn_mul, K, call);
+                    acc[11] += (double)payoff<R>(sT[L::UP_IDX * EU_THREADS + p], K, call);
+                    acc[12] += (double)payoff<R>(sT[L::DN_IDX * EU_THREADS + p], K, call);
+                    acc[13] += (double)payoff<R>(sa * (R)a.rup_mul, K, call);
+                    acc[14] += (double)payoff<R>(sa * (R)a.rdn_mul, K, call);
+                    if constexpr (MODE == MODE_GBM) {
+                        if (itm) acc[15] += (double)sa * ((double)sW[p] * a.w_scale - a.sigmaT);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- fold slices -> one partial per (block, strike) ---------------------------------------------------
+    __shared__ bool is_last;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) {
+        red[tid] = acc[j];
+        __syncthreads();
+        if (tid < ks) {
+            double s = 0.0;
+            for (int sl = 0; sl < nslices; ++sl) s += red[sl * ks + tid];
+            partials[((size_t)blockIdx.x * ks + tid) * NACC + j] = s;
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const int items = ks * NACC;
+        for (int it = tid; it < items; it += EU_THREADS) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * items + it];
+            const int k = it / NACC, j = it % NACC;
+            out[(size_t)k * (NACC + 1) + 1 + j] = s;
+            if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
+        }
+        if (tid == 0) *counter = 0u;   // re-arm for the next launch on this stream
+    }
+}
+
+using EuroKernel = void (*)(const EuroArgs, const double *, const double *, double *, unsigned int *, double *);
+
+template <int MODE, typename R> static EuroKernel pick2(bool anti, bool greeks)
+{
+    if (anti) return greeks ? k_european<MODE, true, true, R> : k_european<MODE, true, false, R>;
+    return greeks ? k_european<MODE, false, true, R> : k_european<MODE, false, false, R>;
+}
+template <typename R> static EuroKernel pick1(int mode, bool anti, bool greeks)
+{
+    switch (mode) {
+    case MODE_GBM: return pick2<MODE_GBM, R>(anti, greeks);
+    case MODE_DETVAR: return pick2<MODE_DETVAR, R>(anti, greeks);
+    case MODE_HESTON: return pick2<MODE_HESTON, R>(anti, greeks);
+    default: return pick2<MODE_SVJ, R>(anti, greeks);
+    }
+}
+
+static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T, int32_t n_steps,
+                           int64_t n_paths, uint64_t seed, uint64_t path_offset, const double *strikes,
+                           int32_t n_strikes, int is_call, uint32_t flags, const b200mc_bumps *bumps,
+                           double *out_dev /* [n_strikes][17] */)
+{
+    Prep pr;
+    B200MC_TRY(prepare(h, p, S0, T, n_steps, n_paths, seed, flags, bumps, pr));
+    if (!strikes || n_strikes <= 0) return fail(h, B200MC_EINVAL, "strikes must hold at least one strike");
+    if (n_strikes > EU_THREADS) return fail(h, B200MC_EINVAL, "at most 256 strikes per launch");
+    if (!out_dev) return fail(h, B200MC_EINVAL, "out is NULL");
+
+    const bool anti = flags & B200MC_ANTITHETIC, greeks = flags & B200MC_GREEKS, fp64 = flags & B200MC_FP64;
+    EuroArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = pr.m;
+    a.key = pr.key;
+    a.path0 = path_offset;
+    a.n_paths = n_paths;
+    a.n_steps = n_steps;
+    a.n_strikes = n_strikes;
+    a.is_call = is_call ? 1 : 0;
+    a.wld = pr.wld;
+    if (greeks) {
+        a.up_mul = 1.0 + bumps->spot_bump;
+        a.dn_mul = 1.0 - bumps->spot_bump;
+        a.rup_mul = exp((bumps->r_up - p->r) * T);
+        a.rdn_mul = exp((bumps->r_dn - p->r) * T);
+    }
+    a.sigmaT = sqrt(p->v0 > 0.0 ? p->v0 : 0.0) * T;
+    a.w_scale = pr.m.sqrt_dt_s;
+
+    EuroKernel kern = fp64 ? pick1<double>(pr.mode, anti, greeks) : pick1<float>(pr.mode, anti, greeks);
+    const int ns = 1 + (anti ? 1 : 0) + (greeks ? 2 : 0);
+    const size_t rsz = fp64 ? 8 : 4;
+    size_t smem = (size_t)(EU_THREADS + n_strikes) * 8 + (size_t)(ns + 1) * EU_THREADS * rsz;
+    if (pr.mode == MODE_DETVAR) smem += (size_t)3 * pr.wld * rsz;
+    if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
+    B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, EU_THREADS, smem));
+    if (occ < 1) return fail(h, B200MC_ECUDA, "fused kernel does not fit on an SM");
+    const int64_t need = (n_paths + EU_THREADS - 1) / EU_THREADS;
+    int64_t grid = (int64_t)h->sm_count * occ;
+    if (grid > need) grid = need;
+
+    // scratch: [strikes n_strikes][wtab 3*wld][partials grid*n_strikes*NACC]
+    const size_t off_w = (size_t)n_strikes * 8;
+    const size_t off_p = off_w + pr.wtab.size() * 8;
+    const size_t total = off_p + (size_t)grid * n_strikes * NACC * 8;
+    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, total));
+    const size_t hbytes = off_p;
+    B200MC_TRY(ensure(h, &h->h_pinned, &h->pinned_bytes, hbytes > 4096 ? hbytes : 4096, true));
+    // the pinned bounce buffer may still feed the previous launch's copy
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->h_pinned, strikes, (size_t)n_strikes * 8);
+    if (!pr.wtab.empty()) memcpy((char *)h->h_pinned + off_w, pr.wtab.data(), pr.wtab.size() * 8);
+    B200MC_CUDA(h, cudaMemcpyAsync(h->d_scratch, h->h_pinned, hbytes, cudaMemcpyHostToDevice, h->stream));
+    char *sc = (char *)h->d_scratch;
+    kern<<<(unsigned)grid, EU_THREADS, smem, h->stream>>>(a, (const double *)sc, (const double *)(sc + off_w),
+                                                          (double *)(sc + off_p), h->d_counter, out_dev);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+} // namespace b200mc
+
+using namespace b200mc;
+
+extern "C" int b200mc_price_european_async(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                           int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                                           const double *strikes, int32_t n_strikes, int is_call, uint32_t flags,
+                                           const b200mc_bumps *bumps, b200mc_sums *out_dev)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    static_assert(sizeof(b200mc_sums) == (NACC + 1) * sizeof(double), "b200mc_sums layout");
+    return launch_european(h, p, S0, T, n_steps, n_paths, seed, path_offset, strikes, n_strikes, is_call, flags,
+                           bumps, reinterpret_cast<double *>(out_dev));
+}
+
+extern "C" int b200mc_price_european(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                     int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
+                                     const double *strikes, int32_t n_strikes, int is_call, uint32_t flags,
+                                     const b200mc_bumps *bumps, b200mc_sums *out)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out) return fail(h, B200MC_EINVAL, "out is NULL");
+    if (n_strikes <= 0 || n_strikes > EU_THREADS) return fail(h, B200MC_EINVAL, "n_strikes must be in [1, 256]");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)n_strikes * sizeof(b200mc_sums);
+    B200MC_TRY(ensure(h, &h->d_result, &h->result_bytes, bytes));
+    B200MC_TRY(launch_european(h, p, S0, T, n_steps, n_paths, seed, path_offset, strikes, n_strikes, is_call, flags,
+                               bumps, reinterpret_cast<double *>(h->d_result)));
+    B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}

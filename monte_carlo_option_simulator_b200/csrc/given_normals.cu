@@ -1,0 +1,225 @@
+// given_normals.cu -- deterministic mode: the SVJ recurrence on caller-supplied draws.
+//
+// Drop-in for _simulate_svj_paths_numba (engine/monte_carlo.py:189-243): same inputs (four C-contiguous float64
+// [n_paths, n_steps] arrays), same outputs, fp64, and the reference's own operation order -- every product and
+// sum below is a separately rounded IEEE operation (__dmul_rn / __dadd_rn, no FMA contraction), S is updated
+// multiplicatively with one exp per step (:236).  Per-path results therefore differ from the reference only by
+// the last-bit behaviour of exp().
+//
+// The arrays are path-major, so "one thread per path" would read with a stride of n_steps*8 bytes.  Each warp
+// instead owns 32 consecutive paths and walks the time axis in tiles of 16 steps: a half-warp loads one path's
+// 16 consecutive doubles (one full 128-byte line), the tile is parked in shared memory with a padded pitch, and
+// each lane then reads its own row.  The optional path record goes the other way through the same kind of tile.
+// Arrays the parameters make irrelevant (Z2 when xi == 0, the jump arrays when lambda_j <= 0) are never read.
+#include "common.cuh"
+
+namespace b200mc {
+
+constexpr int GN_WARPS = 4;
+constexpr int GN_TS = 16;                 // steps per tile
+constexpr int GN_PITCH = GN_TS + 1;
+
+struct GivenArgs {
+    double S0, v0, dt, sqrt_dt, drift_comp, kappa, theta, xi, rho, sq1mr2, jump_thr, mu_j, sigma_j;
+    int64_t n_paths;
+    int32_t n_steps;
+    int32_t need_z2, need_jump, record;
+};
+
+__device__ __forceinline__ void load_tile(double *tile, const double *__restrict__ src, int64_t path0, int64_t n_paths,
+                                          int n_steps, int s0, int lane)
+{
+    const int col = lane & 15, half = lane >> 4;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+        const int row = 2 * it + half;
+        const int64_t p = path0 + row;
+        double val = 0.0;
+        if (p < n_paths && s0 + col < n_steps) val = __ldg(src + (size_t)p * n_steps + s0 + col);
+        tile[row * GN_PITCH + col] = val;
+    }
+}
+
+__global__ void __launch_bounds__(GN_WARPS * 32)
+k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ Z1, const double *__restrict__ Z2,
+                const double *__restrict__ Zj, const double *__restrict__ Zjs, double *__restrict__ S_final,
+                double *__restrict__ v_final, double *__restrict__ all_paths)
+{
+    extern __shared__ __align__(16) double gn_tiles[];          // [GN_WARPS][5][32 * GN_PITCH]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TILE = 32 * GN_PITCH;
+    double *t1 = gn_tiles + (size_t)warp * 5 * TILE, *t2 = t1 + TILE, *tj = t2 + TILE, *tjs = tj + TILE,
+           *tout = tjs + TILE;
+    const int64_t n_groups = (a.n_paths + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * GN_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * GN_WARPS) {
+        const int64_t path0 = g * 32, me = path0 + lane;
+        double S = a.S0, v = a.v0;                                              // :212-213
+        if (a.record) {
+            if (me < a.n_paths) all_paths[(size_t)me * (a.n_steps + 1)] = a.S0;  // :217
+        }
+        for (int s0 = 0; s0 < a.n_steps; s0 += GN_TS) {
+            __syncwarp();
+            load_tile(t1, Z1, path0, a.n_paths, a.n_steps, s0, lane);
+            if (a.need_z2) load_tile(t2, Z2, path0, a.n_paths, a.n_steps, s0, lane);
+            if (a.need_jump) {
+                load_tile(tj, Zj, path0, a.n_paths, a.n_steps, s0, lane);
+                load_tile(tjs, Zjs, path0, a.n_paths, a.n_steps, s0, lane);
+            }
+            __syncwarp();
+            const int ns = min(GN_TS, a.n_steps - s0);
+            for (int t = 0; t < ns; ++t) {
+                const double z1 = t1[lane * GN_PITCH + t];
+                const double v_pos = fmax(v, 0.0);                               // :223
+                const double sqrt_v = sqrt(v_pos);                               // :224
+                const double dW1 = __dmul_rn(z1, a.sqrt_dt);                     // :226
+                double dW2 = __dmul_rn(__dmul_rn(a.rho, z1), a.sqrt_dt);         // :227
+                if (a.need_z2)
+                    dW2 = __dadd_rn(dW2, __dmul_rn(__dmul_rn(a.sq1mr2, t2[lane * GN_PITCH + t]), a.sqrt_dt));
+                const double log_drift = __dmul_rn(__dadd_rn(a.drift_comp, -__dmul_rn(0.5, v_pos)), a.dt);   // :229
+                const double log_diff = __dmul_rn(sqrt_v, dW1);                  // :230
+                double jump = 0.0;                                               // :232
+                if (a.need_jump) {
+                    if (tj[lane * GN_PITCH + t] < a.jump_thr)                    // :233
+                        jump = __dadd_rn(a.mu_j, __dmul_rn(a.sigma_j, tjs[lane * GN_PITCH + t]));   // :234
+                }
+                S = __dmul_rn(S, exp(__dadd_rn(__dadd_rn(log_drift, log_diff), jump)));              // :236
+                const double mr = __dmul_rn(__dmul_rn(a.kappa, __dadd_rn(a.theta, -v_pos)), a.dt);
+                const double vv = __dmul_rn(__dmul_rn(a.xi, sqrt_v), dW2);
+                v = fmax(__dadd_rn(__dadd_rn(v_pos, mr), vv), 0.0);              // :237-238
+                if (a.record) tout[lane * GN_PITCH + t] = S;
+            }
+            if (a.record) {                                                      // :241, coalesced by rows
+                __syncwarp();
+                const int col = lane & 15, half = lane >> 4;
+                for (int it = 0; it < 16; ++it) {
+                    const int row = 2 * it + half;
+                    const int64_t p = path0 + row;
+                    if (p < a.n_paths && col < ns)
+                        all_paths[(size_t)p * (a.n_steps + 1) + 1 + s0 + col] = tout[row * GN_PITCH + col];
+                }
+            }
+        }
+        if (me < a.n_paths) {
+            S_final[me] = S;
+            v_final[me] = v;
+        }
+    }
+}
+
+static int check_given(b200mc_handle *h, const b200mc_svj_params *p, int64_t n_paths, int32_t n_steps, double T,
+                       const double *Z1, const double *Z2, const double *Zj, const double *Zjs, int record,
+                       double *S_final, double *v_final, double *all_paths)
+{
+    if (!p) return fail(h, B200MC_EINVAL, "params is NULL");
+    if (n_paths < 0 || n_steps <= 0) return fail(h, B200MC_EINVAL, "n_paths must be >= 0 and n_steps > 0");
+    if (!(T == T)) return fail(h, B200MC_EINVAL, "T is NaN");
+    if (n_paths > 0 && (!Z1 || !Z2 || !Zj || !Zjs || !S_final || !v_final))
+        return fail(h, B200MC_EINVAL, "NULL array argument");
+    if (record && n_paths > 0 && !all_paths) return fail(h, B200MC_EINVAL, "record_paths set but all_paths is NULL");
+    return 0;
+}
+
+static GivenArgs make_args(const b200mc_svj_params *p, double S0, double T, int64_t n_paths, int32_t n_steps, int record)
+{
+    GivenArgs a;
+    a.S0 = S0;
+    a.v0 = p->v0;
+    a.dt = T / (double)n_steps;                                              // :206
+    a.sqrt_dt = sqrt(a.dt);                                                  // :207
+    const double k = exp(p->mu_j + 0.5 * (p->sigma_j * p->sigma_j)) - 1.0;   // :209
+    a.drift_comp = p->r - p->q - p->lambda_j * k;                            // :210
+    a.kappa = p->kappa; a.theta = p->theta; a.xi = p->xi; a.rho = p->rho;
+    a.sq1mr2 = sqrt(1.0 - p->rho * p->rho);
+    a.jump_thr = p->lambda_j * a.dt;
+    a.mu_j = p->mu_j; a.sigma_j = p->sigma_j;
+    a.n_paths = n_paths; a.n_steps = n_steps;
+    a.need_z2 = (p->xi != 0.0) ? 1 : 0;
+    // Z_jump is a uniform in [0, 1): with lambda_j dt <= 0 the test :233 can never fire
+    a.need_jump = (a.jump_thr > 0.0) ? 1 : 0;
+    a.record = record ? 1 : 0;
+    return a;
+}
+
+static int launch_given(b200mc_handle *h, const GivenArgs &a, const double *Z1, const double *Z2, const double *Zj,
+                        const double *Zjs, double *S_final, double *v_final, double *all_paths)
+{
+    if (a.n_paths == 0) return 0;
+    const int64_t groups = (a.n_paths + 31) / 32;
+    int64_t grid = (groups + GN_WARPS - 1) / GN_WARPS;
+    const int64_t cap = (int64_t)h->sm_count * 8;
+    if (grid > cap) grid = cap;
+    const size_t smem = (size_t)GN_WARPS * 5 * 32 * GN_PITCH * sizeof(double);
+    B200MC_CUDA(h, cudaFuncSetAttribute((const void *)k_given_normals, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    k_given_normals<<<(unsigned)grid, GN_WARPS * 32, smem, h->stream>>>(a, Z1, Z2, Zj, Zjs, S_final, v_final,
+                                                                         all_paths);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+} // namespace b200mc
+using namespace b200mc;
+
+extern "C" int b200mc_simulate_given_normals_dev(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                                 int64_t n_paths, int32_t n_steps, const double *Z1, const double *Z2,
+                                                 const double *Z_jump, const double *Z_jump_size, int record_paths,
+                                                 double *S_final, double *v_final, double *all_paths)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    B200MC_TRY(check_given(h, p, n_paths, n_steps, T, Z1, Z2, Z_jump, Z_jump_size, record_paths, S_final, v_final,
+                           all_paths));
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    return launch_given(h, make_args(p, S0, T, n_paths, n_steps, record_paths), Z1, Z2, Z_jump, Z_jump_size, S_final,
+                        v_final, all_paths);
+}
+
+extern "C" int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
+                                             int64_t n_paths, int32_t n_steps, const double *Z1, const double *Z2,
+                                             const double *Z_jump, const double *Z_jump_size, int record_paths,
+                                             double *S_final, double *v_final, double *all_paths)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    B200MC_TRY(check_given(h, p, n_paths, n_steps, T, Z1, Z2, Z_jump, Z_jump_size, record_paths, S_final, v_final,
+                           all_paths));
+    if (n_paths == 0) return 0;
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    GivenArgs a = make_args(p, S0, T, n_paths, n_steps, record_paths);
+    const int narr = 1 + a.need_z2 + 2 * a.need_jump;
+    // stage at most ~2 GiB of inputs + outputs per chunk of paths
+    const size_t in_row = (size_t)n_steps * 8, out_row = 16 + (record_paths ? (size_t)(n_steps + 1) * 8 : 0);
+    const size_t per_path = (size_t)narr * in_row + out_row;
+    int64_t chunk = (int64_t)(((size_t)2 << 30) / per_path);
+    chunk = chunk < 32 ? 32 : (chunk & ~(int64_t)31);
+    if (chunk > n_paths) chunk = n_paths;
+    B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, (size_t)chunk * per_path + 1024));
+    char *base = (char *)h->d_stage;
+    double *dZ[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t off = 0;
+    const int use[4] = {1, a.need_z2, a.need_jump, a.need_jump};
+    for (int i = 0; i < 4; ++i) {
+        if (use[i]) { dZ[i] = (double *)(base + off); off += (size_t)chunk * in_row; }
+    }
+    double *dS = (double *)(base + off); off += (size_t)chunk * 8;
+    double *dv = (double *)(base + off); off += (size_t)chunk * 8;
+    double *dP = record_paths ? (double *)(base + off) : nullptr;
+    const double *src[4] = {Z1, Z2, Z_jump, Z_jump_size};
+    for (int64_t p0 = 0; p0 < n_paths; p0 += chunk) {
+        const int64_t np = (n_paths - p0 < chunk) ? (n_paths - p0) : chunk;
+        for (int i = 0; i < 4; ++i) {
+            if (use[i])
+                B200MC_CUDA(h, cudaMemcpyAsync(dZ[i], src[i] + (size_t)p0 * n_steps, (size_t)np * in_row,
+                                               cudaMemcpyHostToDevice, h->stream));
+        }
+        a.n_paths = np;
+        B200MC_TRY(launch_given(h, a, dZ[0], dZ[1] ? dZ[1] : dZ[0], dZ[2] ? dZ[2] : dZ[0], dZ[3] ? dZ[3] : dZ[0], dS, dv,
+                                dP));
+        B200MC_CUDA(h, cudaMemcpyAsync(S_final + p0, dS, (size_t)np * 8, cudaMemcpyDeviceToHost, h->stream));
+        B200MC_CUDA(h, cudaMemcpyAsync(v_final + p0, dv, (size_t)np * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (record_paths)
+            B200MC_CUDA(h, cudaMemcpyAsync(all_paths + (size_t)p0 * (n_steps + 1), dP, (size_t)np * (n_steps + 1) * 8,
+                                           cudaMemcpyDeviceToHost, h->stream));
+        B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}

@@ -1,0 +1,164 @@
+// microbench.cu -- issue-rate probes for the pipes the fused kernel lives on.  The roofline of a kernel that moves
+// no data is an instruction-throughput roofline; its denominators (FP32 FMA, 32x32->64 integer multiply, 3-input
+// logic, MUFU) are not in MEASURED_PEAKS.json, so bench.py measures them on the same device, in the same run,
+// with these kernels ("the builder must microbenchmark FFMA, IMAD.WIDE, LOP3, MUFU").
+// Each thread runs 8 independent dependency chains of one instruction type; with 2048 threads per SM resident the
+// pipe, not latency, is the limit.
+#include "common.cuh"
+
+namespace b200mc {
+
+enum { MB_FFMA = 0, MB_IMAD_WIDE = 1, MB_LOP3 = 2, MB_MUFU_EX2 = 3, MB_MUFU_SIN = 4, MB_IADD3 = 5, MB_PHILOX = 6,
+       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_COUNT = 12 };
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, const __grid_constant__ PhiloxKey key,
+                                                    uint32_t *sink)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (WHICH == MB_FFMA || WHICH == MB_FMUL) {
+        float a[8];
+        const float b = __uint_as_float(0x3f800001u + (seed & 1)), c = __uint_as_float(0x33800000u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (float)(t + k);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (WHICH == MB_FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[k]) : "f"(b), "f"(c));
+                else asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(a[k]) : "f"(b));
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += a[k];
+        if (s == 123.456f) sink[0] = t;
+    } else if constexpr (WHICH == MB_IMAD_WIDE) {
+        uint32_t a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = t * 8u + k + seed;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint64_t p;
+                asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(p) : "r"(a[k]));
+                a[k] = (uint32_t)(p >> 32);       // hi word feeds the next multiply (a register move at most)
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s ^= a[k];
+        if (s == 0x12345u) sink[0] = t;
+    } else if constexpr (WHICH == MB_LOP3 || WHICH == MB_IADD3) {
+        uint32_t a[8];
+        const uint32_t b = seed * 2654435761u, c = ~seed;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = t * 8u + k;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (WHICH == MB_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b + i), "r"(c));
+                else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s ^= a[k];
+        if (s == 0x12345u) sink[0] = t;
+    } else if constexpr (WHICH == MB_MUFU_EX2 || WHICH == MB_MUFU_SIN || WHICH == MB_MUFU_LG2 || WHICH == MB_MUFU_SQRT) {
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = 0.5f + 1e-3f * (float)((t + k) & 255);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (WHICH == MB_MUFU_EX2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+                else if constexpr (WHICH == MB_MUFU_SIN) asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+                else if constexpr (WHICH == MB_MUFU_LG2) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+                else asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += a[k];
+        if (s == 123.456f) sink[0] = t;
+    } else if constexpr (WHICH == MB_MIX_FFMA_LOP3) {
+        float a[4];
+        uint32_t u[4];
+        const float b = __uint_as_float(0x3f800001u + (seed & 1)), c = __uint_as_float(0x33800000u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[k] = (float)(t + k); u[k] = t * 4u + k; }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[k]) : "f"(b), "f"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[k]) : "r"(seed + i), "r"(~seed));
+            }
+        }
+        float s = 0.f;
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s += a[k]; x ^= u[k]; }
+        if (s == 123.456f && x == 77u) sink[0] = t;
+    } else {   // MB_PHILOX, MB_PHILOX_BM: iters Philox4x32-10 calls (+ two Box-Muller pairs) per thread
+        float s = 0.f;
+        uint32_t x = 0;
+        for (int i = 0; i < iters; ++i) {
+            const U4 w = philox4x32_10(t, seed, (uint32_t)i, 0u, key);
+            if constexpr (WHICH == MB_PHILOX) x ^= w.x ^ w.y ^ w.z ^ w.w;
+            else {
+                const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
+                s += p.rc; s += p.rs; s += q.rc; s += q.rs;
+            }
+        }
+        if (s == 123.456f || x == 0x12345u) sink[0] = t;
+    }
+}
+
+template <int W> static void mb_launch(int grid, int iters, uint32_t seed, const PhiloxKey &key, uint32_t *sink, cudaStream_t st)
+{
+    k_microbench<W><<<grid, 256, 0, st>>>(iters, seed, key, sink);
+}
+
+} // namespace b200mc
+using namespace b200mc;
+
+// which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox + 2 Box-Muller
+// pairs (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs).
+// *ops_per_s = thread-level operations per second over the whole device (kernel time by CUDA events, best of 3).
+extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s)
+{
+    if (!h || !ops_per_s) return fail(h, B200MC_EINVAL, "NULL argument");
+    if (which < 0 || which >= MB_COUNT || iters <= 0) return fail(h, B200MC_EINVAL, "bad microbench selector");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const int grid = h->sm_count * 8;
+    const PhiloxKey key = philox_make_key(0x9E3779B97F4A7C15ull);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        B200MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        switch (which) {
+        case 0: mb_launch<0>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 1: mb_launch<1>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 2: mb_launch<2>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 3: mb_launch<3>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 4: mb_launch<4>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 5: mb_launch<5>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 6: mb_launch<6>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 7: mb_launch<7>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 8: mb_launch<8>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 9: mb_launch<9>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 10: mb_launch<10>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        default: mb_launch<11>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        }
+        B200MC_CUDA(h, cudaGetLastError());
+        B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        B200MC_CUDA(h, cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        B200MC_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0 && ms < best) best = ms;
+        h->launches += 1;
+    }
+    const double per_thread = (which == MB_PHILOX || which == MB_PHILOX_BM) ? (double)iters
+                            : (which == MB_MIX_FFMA_LOP3 ? 4.0 * iters : 8.0 * iters);
+    *ops_per_s = (double)grid * 256.0 * per_thread / ((double)best * 1e-3);
+    return 0;
+}

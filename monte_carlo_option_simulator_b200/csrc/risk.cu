@@ -1,0 +1,208 @@
+// risk.cu -- tail metrics of a P&L vector on the device.
+//
+// Restates compute_risk_metrics (engine/risk.py:117-155) and _hill_estimator (:158-173) without the full sort:
+//   sorted[cutoff]            -> exact order statistic by most-significant-digit radix select over the order-preserving
+//                                64-bit image of the doubles (8 passes of 8 bits; the vector stays L2 resident)
+//   mean(sorted[:cutoff])     -> sum of the elements below the threshold + (cutoff - count_below) copies of it (ties)
+//   Hill sum over the k largest losses -> same construction with the k-th order statistic
+//   mean / std / skew / kurt  -> two passes (mean first, central moments second) like np.mean / np.std (:137-144)
+// Index conventions are the reference's: cutoff = int(n (1 - confidence)) (:128), var = -sorted[cutoff] (:129),
+// cvar = -mean(sorted[:cutoff]) (:130), k = max(int(sqrt(m)), 10) clipped to m - 1 over the m strictly negative
+// returns, tail index only when m > 20 (:147-150,162-173).
+#include "common.cuh"
+
+namespace b200mc {
+
+constexpr int RK_THREADS = 256;
+
+struct SelectState {
+    unsigned long long prefix[2];
+    long long rank[2];
+    unsigned long long hist[2][256];
+    double thr[2];
+};
+
+__device__ __forceinline__ unsigned long long key_of(double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(unsigned long long k)
+{
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RK_THREADS)
+k_risk_pass1(const T *__restrict__ x, int64_t n, unsigned long long *__restrict__ keys, double *partials,
+             unsigned int *counter, double *out /* [2]: sum, count of x < 0 */)
+{
+    __shared__ double smem[(RK_THREADS / 32) * 2];
+    double v[2] = {0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RK_THREADS) {
+        const double d = (double)x[i];
+        keys[i] = key_of(d);
+        v[0] += d;
+        if (d < 0.0) v[1] += 1.0;
+    }
+    block_finish<2>(v, smem, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(RK_THREADS)
+k_risk_hist(const unsigned long long *__restrict__ keys, int64_t n, int pass, int nsel, SelectState *st)
+{
+    __shared__ unsigned int h[2][256];
+    for (int i = threadIdx.x; i < 512; i += RK_THREADS) (&h[0][0])[i] = 0u;
+    __syncthreads();
+    const int shift = 8 * pass;
+    const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
+    for (int64_t i = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RK_THREADS) {
+        const unsigned long long k = keys[i];
+        const unsigned long long hi = (pass == 7) ? 0ull : (k >> (shift + 8));
+        const unsigned int digit = (unsigned int)(k >> shift) & 255u;
+        if (pass == 7 || hi == (p0 >> (shift + 8))) atomicAdd(&h[0][digit], 1u);
+        if (nsel > 1 && (pass == 7 || hi == (p1 >> (shift + 8)))) atomicAdd(&h[1][digit], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * nsel; i += RK_THREADS) {
+        const unsigned int c = (&h[0][0])[i];
+        if (c) atomicAdd(&st->hist[0][0] + i, (unsigned long long)c);
+    }
+}
+
+__global__ void k_risk_pick(int pass, int nsel, SelectState *st)
+{
+    const int s = threadIdx.x;
+    if (s >= nsel) return;
+    long long r = st->rank[s];
+    unsigned long long cum = 0;
+    int bin = 255;
+    for (int b = 0; b < 256; ++b) {
+        const unsigned long long c = st->hist[s][b];
+        if ((long long)(cum + c) > r) { bin = b; break; }
+        cum += c;
+    }
+    st->rank[s] = r - (long long)cum;
+    st->prefix[s] |= (unsigned long long)bin << (8 * pass);
+    for (int b = 0; b < 256; ++b) st->hist[s][b] = 0ull;
+    if (pass == 0) st->thr[s] = value_of(st->prefix[s]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RK_THREADS)
+k_risk_pass2(const T *__restrict__ x, int64_t n, double mean, int nsel, const SelectState *st, double *partials,
+             unsigned int *counter, double *out /* [6] */)
+{
+    __shared__ double smem[(RK_THREADS / 32) * 6];
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double tc = st->thr[0], tk = nsel > 1 ? st->thr[1] : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RK_THREADS) {
+        const double d = (double)x[i];
+        const double c = d - mean, c2 = c * c;
+        v[0] += c2;
+        v[1] += c2 * c;
+        v[2] += c2 * c2;
+        if (d < tc) { v[3] += 1.0; v[4] += d; }
+        if (nsel > 1 && d < tk) v[5] += log(d / tk);       // both negative: loss_i / loss_k   (:170)
+    }
+    block_finish<6>(v, smem, partials, counter, out);
+}
+
+template <typename T>
+static int risk_run(b200mc_handle *h, const T *x_dev, int64_t n, double confidence, double out[8])
+{
+    int64_t grid = (n + RK_THREADS - 1) / RK_THREADS;
+    const int64_t cap = (int64_t)h->sm_count * 8;
+    if (grid > cap) grid = cap;
+    // scratch: [keys n*8][SelectState][partials grid*6*8][results 8*8]
+    const size_t off_st = ((size_t)n * 8 + 255) & ~(size_t)255;
+    const size_t off_pa = off_st + ((sizeof(SelectState) + 255) & ~(size_t)255);
+    const size_t off_re = off_pa + (size_t)grid * 6 * 8;
+    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, off_re + 64));
+    char *sc = (char *)h->d_scratch;
+    unsigned long long *keys = (unsigned long long *)sc;
+    SelectState *st = (SelectState *)(sc + off_st);
+    double *partials = (double *)(sc + off_pa), *res = (double *)(sc + off_re);
+
+    k_risk_pass1<T><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(x_dev, n, keys, partials, h->d_counter, res);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    double r1[2];
+    B200MC_CUDA(h, cudaMemcpyAsync(r1, res, 16, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    const double mean = r1[0] / (double)n;                                   // :137
+    const int64_t m = (int64_t)r1[1];                                        // len(losses), :147
+
+    int64_t cutoff = (int64_t)((double)n * (1.0 - confidence));              // :128
+    if (cutoff < 0) cutoff = 0;
+    const int64_t rank_c = cutoff < n ? cutoff : 0;                          // :129
+    int64_t k = 0;
+    const bool want_hill = m > 20;                                           // :150
+    if (want_hill) {
+        k = (int64_t)sqrt((double)m);                                        // :165
+        if (k < 10) k = 10;
+        if (k > m - 1) k = m - 1;                                            // :166
+    }
+    const int nsel = want_hill ? 2 : 1;
+    SelectState init;
+    memset(&init, 0, sizeof(init));
+    init.rank[0] = rank_c;
+    init.rank[1] = k;
+    B200MC_TRY(ensure(h, &h->h_pinned, &h->pinned_bytes, sizeof(SelectState) > 4096 ? sizeof(SelectState) : 4096, true));
+    memcpy(h->h_pinned, &init, sizeof(init));
+    B200MC_CUDA(h, cudaMemcpyAsync(st, h->h_pinned, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    for (int pass = 7; pass >= 0; --pass) {
+        k_risk_hist<<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(keys, n, pass, nsel, st);
+        k_risk_pick<<<1, 32, 0, h->stream>>>(pass, nsel, st);
+        h->launches += 2;
+    }
+    B200MC_CUDA(h, cudaGetLastError());
+    k_risk_pass2<T><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(x_dev, n, mean, nsel, st, partials, h->d_counter, res);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    double r2[6], thr[2];
+    B200MC_CUDA(h, cudaMemcpyAsync(r2, res, 48, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaMemcpyAsync(thr, &st->thr[0], 16, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+
+    const double nn = (double)n;
+    const double var_pop = r2[0] / nn;
+    const double sd = sqrt(var_pop);                                         // :138 (np.std, ddof = 0)
+    const double sdc = sd > 1e-10 ? sd : 1e-10;                              // :141
+    const double skew = (r2[1] / nn) / (sdc * sdc * sdc);                    // :143
+    const double kurt = (r2[2] / nn) / (sdc * sdc * sdc * sdc);              // :144
+    const double var = -thr[0];                                              // :129
+    double cvar;
+    if (cutoff <= 0) cvar = -thr[0];                                         // :130, else-branch (-sorted[0])
+    else if (cutoff >= n) cvar = -mean;                                      // slice covers everything
+    else cvar = -(r2[4] + ((double)cutoff - r2[3]) * thr[0]) / (double)cutoff;
+    double tail = NAN;
+    if (want_hill && thr[1] < 0.0 && r2[5] > 0.0) tail = (double)k / r2[5];  // :168-173
+    out[0] = var; out[1] = cvar; out[2] = skew; out[3] = kurt; out[4] = kurt - 3.0; out[5] = tail;
+    out[6] = mean; out[7] = sd;
+    return 0;
+}
+
+} // namespace b200mc
+using namespace b200mc;
+
+extern "C" int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device,
+                                   double confidence, double out[8])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!pnl || !out) return fail(h, B200MC_EINVAL, "NULL argument");
+    if (n <= 0) return fail(h, B200MC_EINVAL, "returns must not be empty");
+    if (dtype != B200MC_F32 && dtype != B200MC_F64) return fail(h, B200MC_EINVAL, "dtype must be B200MC_F32 or B200MC_F64");
+    if (!(confidence == confidence)) return fail(h, B200MC_EINVAL, "confidence is NaN");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t esz = dtype == B200MC_F64 ? 8 : 4;
+    const void *x = pnl;
+    if (!on_device) {
+        B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, (size_t)n * esz + 256));
+        B200MC_CUDA(h, cudaMemcpyAsync(h->d_stage, pnl, (size_t)n * esz, cudaMemcpyHostToDevice, h->stream));
+        x = h->d_stage;
+    }
+    if (dtype == B200MC_F64) return risk_run<double>(h, (const double *)x, n, confidence, out);
+    return risk_run<float>(h, (const float *)x, n, confidence, out);
+}

@@ -1,0 +1,220 @@
+// sim.cuh -- the per-path simulator shared by the fused kernels (sums, terminal values, path store).
+//
+// Restates the recurrence of _simulate_svj_paths_numba (engine/monte_carlo.py:205-241) in log space with
+// the draws produced in registers by Philox4x32-10 (philox.cuh) instead of read from four host arrays:
+//     v+ = max(v, 0)                                   :223
+//     x += (r - q - lambda k - v+/2) dt + sqrt(v+) sqrt(dt) Z1 + jump      :226-236   (S = S0 exp(x))
+//     v  = max(v+ + kappa (theta - v+) dt + xi sqrt(v+) sqrt(dt) (rho Z1 + sqrt(1-rho^2) Z2), 0)   :227,237-238
+// One thread owns one path and carries NS "states" over the SAME draws (common random numbers):
+//     state 0            the primary path
+//     state 1 (ANTI)     its antithetic twin (-Z1, -Z2, U, -Zjs), monte_carlo.py:318-324
+//     next two (GREEKS)  the path started from v0_up / v0_dn, greeks.py:124-147
+// Four modes, picked by the host from the parameters:
+//     GBM     xi = 0, lambda = 0, variance constant: x_T = drift + w * sum(z); only sum(z) is carried
+//     DETVAR  xi = 0, lambda = 0, variance deterministic but moving (kappa != 0, theta != v0): per-step
+//             weights w_s = sqrt(v_s dt) come from a table in shared memory (built on the host in fp64)
+//     HESTON  lambda = 0: two normals per step, two steps per Philox call
+//     SVJ     everything: one Philox call per step (Z1, Z2, U_jump, Z_jump_size)
+// R is the type of the path state (float or double); the draws are float in both cases.
+#pragma once
+#include "common.cuh"
+
+namespace b200mc {
+
+enum { MODE_GBM = 0, MODE_DETVAR = 1, MODE_HESTON = 2, MODE_SVJ = 3 };
+
+struct ModelArgs {
+    double S0, T, dt;
+    double drift_dt;        // (r - q - lambda_j k) dt                       :210,229
+    double half_dt;         // dt / 2
+    double sqrt_dt_s;       // sqrt(dt) * BM_SCALE  (the draws are unscaled, see philox.cuh)
+    double kappa_dt, theta;
+    double xi_sqrt_dt_s;    // xi sqrt(dt) BM_SCALE
+    double rho, crho;       // crho = sqrt(1 - rho^2)                        :227
+    double mu_j, sigma_j;
+    uint64_t jump_thr;      // jump iff w2 < jump_thr  <=>  (w2 + 0.5) / 2^32 < lambda_j dt    :233
+    double v0[3];           // base, up, down
+    double x_drift[3];      // GBM / DETVAR: total drift of x over [0, T] for the three variance starts
+    double x_w[3];          // GBM: x_T = x_drift + x_w * sum(raw z);  x_w = sqrt(v0 dt) BM_SCALE
+    double step_drift[3];   // GBM: per-step drift (path store)
+};
+
+template <typename R> struct Consts {
+    R drift_dt, half_dt, sqrt_dt_s, kappa_dt, theta, xi_sqrt_dt_s, rho, crho, mu_j, sigma_j;
+    __device__ __forceinline__ explicit Consts(const ModelArgs &m)
+        : drift_dt((R)m.drift_dt), half_dt((R)m.half_dt), sqrt_dt_s((R)m.sqrt_dt_s), kappa_dt((R)m.kappa_dt),
+          theta((R)m.theta), xi_sqrt_dt_s((R)m.xi_sqrt_dt_s), rho((R)m.rho), crho((R)m.crho),
+          mu_j((R)m.mu_j), sigma_j((R)m.sigma_j) {}
+};
+
+__device__ __forceinline__ float  rsqrt_of(float x)  { return sqrt_approx(x); }
+__device__ __forceinline__ double rsqrt_of(double x) { return sqrt(x); }
+__device__ __forceinline__ float  rmax(float a, float b)   { return fmaxf(a, b); }
+__device__ __forceinline__ double rmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float  rexp(float x)  { return expf(x); }
+__device__ __forceinline__ double rexp(double x) { return exp(x); }
+
+template <bool ANTI, bool GREEKS> struct StateLayout {
+    static constexpr int NS = 1 + (ANTI ? 1 : 0) + (GREEKS ? 2 : 0);
+    static constexpr int ANTI_IDX = 1;
+    static constexpr int UP_IDX = 1 + (ANTI ? 1 : 0);
+    static constexpr int DN_IDX = UP_IDX + 1;
+};
+
+// One stochastic-variance step for all states.  z1, z2 are UNSCALED draws (scale folded in the constants).
+template <typename R, bool ANTI, bool GREEKS>
+__device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R (&v)[StateLayout<ANTI, GREEKS>::NS],
+                                        const Consts<R> &c, R z1, R zc, R jmu, R jsz)
+{
+    constexpr int NS = StateLayout<ANTI, GREEKS>::NS;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const bool neg = ANTI && k == 1;
+        const R vp = rmax(v[k], (R)0);
+        const R sv = rsqrt_of(vp);
+        const R a = sv * c.sqrt_dt_s;                    // sqrt(v+) sqrt(dt)
+        const R d = c.drift_dt - c.half_dt * vp;         // :229
+        const R b = sv * c.xi_sqrt_dt_s;
+        const R mr = vp + c.kappa_dt * (c.theta - vp);   // :237
+        if (neg) {
+            x[k] = x[k] + (d - a * z1 + (jmu - jsz));      // twin: -Z1, -Z2, same U, -Zjs  (:323)
+            v[k] = rmax(mr - b * zc, (R)0);
+        } else {
+            x[k] = x[k] + (d + a * z1 + (jmu + jsz));
+            v[k] = rmax(mr + b * zc, (R)0);
+        }
+    }
+}
+
+// Simulates global path `path` to T.  On return xT[k] = log(S_T / S0) of state k and vT[k] its variance
+// (GBM / DETVAR: vT is left untouched); sumz_out = sum of the raw draws (GBM only; feeds the pathwise vega).
+// wtab: DETVAR weights, wtab[k * wld + s] = sqrt(v_s^{(k)} dt) * BM_SCALE in shared memory.
+// REC: after every step s call rec(s, x0) with the primary state's log return (path store).
+template <int MODE, bool ANTI, bool GREEKS, typename R, typename Rec>
+__device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKey &key, uint64_t path, int n_steps,
+                                              const R *wtab, int wld,
+                                              R (&xT)[StateLayout<ANTI, GREEKS>::NS],
+                                              R (&vT)[StateLayout<ANTI, GREEKS>::NS], R &sumz_out, Rec rec)
+{
+    using L = StateLayout<ANTI, GREEKS>;
+    constexpr int NS = L::NS;
+    const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
+
+    if constexpr (MODE == MODE_GBM && Rec::enabled) {
+        // path store: the log return itself is carried so that every step can be recorded
+        const R w = (R)m.x_w[0], d = (R)m.step_drift[0];
+        R x = (R)0;
+        const int nblk = (n_steps + 3) >> 2;
+        for (int j = 0; j < nblk; ++j) {
+            const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+            const BM2 p = box_muller_raw(u.x, u.y), q = box_muller_raw(u.z, u.w);
+            const R z[4] = {(R)p.rc, (R)p.rs, (R)q.rc, (R)q.rs};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (4 * j + t < n_steps) {
+                    x += w * z[t] + d;
+                    rec(4 * j + t, x);
+                }
+            }
+        }
+        sumz_out = (R)0;
+        xT[0] = x;
+    } else if constexpr (MODE == MODE_GBM) {
+        R sumz = (R)0;
+        const int nblk = n_steps >> 2;
+#pragma unroll 2
+        for (int j = 0; j < nblk; ++j) {
+            const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+            const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
+            sumz += (R)p.rc; sumz += (R)p.rs; sumz += (R)q.rc; sumz += (R)q.rs;
+        }
+        const int rem = n_steps & 3;
+        if (rem) {
+            const U4 w = philox4x32_10(c0, c1, (uint32_t)nblk, B200MC_STREAM_GBM, key);
+            const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
+            sumz += (R)p.rc;
+            if (rem > 1) sumz += (R)p.rs;
+            if (rem > 2) sumz += (R)q.rc;
+        }
+        sumz_out = sumz;
+        xT[0] = (R)m.x_drift[0] + (R)m.x_w[0] * sumz;
+        if constexpr (ANTI) xT[1] = (R)m.x_drift[0] - (R)m.x_w[0] * sumz;
+        if constexpr (GREEKS) {
+            xT[L::UP_IDX] = (R)m.x_drift[1] + (R)m.x_w[1] * sumz;
+            xT[L::DN_IDX] = (R)m.x_drift[2] + (R)m.x_w[2] * sumz;
+        }
+    } else if constexpr (MODE == MODE_DETVAR) {
+        R acc[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) acc[k] = (R)0;
+        // weight row of state k: ANTI twin shares row 0 with a minus sign
+        auto row = [&](int k) -> int { return (ANTI && k == 1) ? 0 : (k == 0 ? 0 : k - (ANTI ? 1 : 0)); };
+        const int nblk = (n_steps + 3) >> 2;     // the table is zero-padded to a multiple of 4
+        for (int j = 0; j < nblk; ++j) {
+            const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+            const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
+            const R z[4] = {(R)p.rc, (R)p.rs, (R)q.rc, (R)q.rs};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    if (ANTI && k == 1) continue;
+                    acc[k] += wtab[row(k) * wld + 4 * j + t] * z[t];
+                }
+                if constexpr (Rec::enabled) { if (4 * j + t < n_steps) rec(4 * j + t, acc[0]); }
+            }
+        }
+        sumz_out = (R)0;
+        xT[0] = (R)m.x_drift[0] + acc[0];
+        if constexpr (ANTI) xT[1] = (R)m.x_drift[0] - acc[0];
+        if constexpr (GREEKS) {
+            xT[L::UP_IDX] = (R)m.x_drift[1] + acc[L::UP_IDX];
+            xT[L::DN_IDX] = (R)m.x_drift[2] + acc[L::DN_IDX];
+        }
+    } else {
+        const Consts<R> c(m);
+        R x[NS], v[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { x[k] = (R)0; v[k] = (R)m.v0[0]; }
+        if constexpr (GREEKS) { v[L::UP_IDX] = (R)m.v0[1]; v[L::DN_IDX] = (R)m.v0[2]; }
+        if constexpr (MODE == MODE_HESTON) {
+            const int nblk = n_steps >> 1;
+            for (int j = 0; j < nblk; ++j) {
+                const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_HESTON, key);
+                const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
+                sv_step<R, ANTI, GREEKS>(x, v, c, (R)p.rc, c.rho * (R)p.rc + c.crho * (R)p.rs, (R)0, (R)0);
+                if constexpr (Rec::enabled) rec(2 * j, x[0]);
+                sv_step<R, ANTI, GREEKS>(x, v, c, (R)q.rc, c.rho * (R)q.rc + c.crho * (R)q.rs, (R)0, (R)0);
+                if constexpr (Rec::enabled) rec(2 * j + 1, x[0]);
+            }
+            if (n_steps & 1) {
+                const U4 w = philox4x32_10(c0, c1, (uint32_t)nblk, B200MC_STREAM_HESTON, key);
+                const BM2 p = box_muller_raw(w.x, w.y);
+                sv_step<R, ANTI, GREEKS>(x, v, c, (R)p.rc, c.rho * (R)p.rc + c.crho * (R)p.rs, (R)0, (R)0);
+                if constexpr (Rec::enabled) rec(n_steps - 1, x[0]);
+            }
+        } else {
+            for (int j = 0; j < n_steps; ++j) {
+                const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_SVJ, key);
+                const BM2 p = box_muller_raw(w.x, w.y);
+                R jmu = (R)0, jsz = (R)0;
+                if ((uint64_t)w.z < m.jump_thr) {                                    // :233-234
+                    jmu = c.mu_j;
+                    jsz = c.sigma_j * (R)jump_size_normal(w.w);
+                }
+                sv_step<R, ANTI, GREEKS>(x, v, c, (R)p.rc, c.rho * (R)p.rc + c.crho * (R)p.rs, jmu, jsz);
+                if constexpr (Rec::enabled) rec(j, x[0]);
+            }
+        }
+        sumz_out = (R)0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { xT[k] = x[k]; vT[k] = v[k]; }
+    }
+}
+
+struct NoRec {
+    static constexpr bool enabled = false;
+    template <typename R> __device__ __forceinline__ void operator()(int, R) const {}
+};
+
+} // namespace b200mc

@@ -1,0 +1,60 @@
+"""Multi-GPU sharding of the fused pricer: one process per GPU, paths split into contiguous ranges of the GLOBAL
+path index (Philox counters are derived from that index, so 1/2/4/8-GPU runs draw identical numbers), and ONE
+all-reduce of the per-strike sum vectors (17 doubles per strike).  Nothing in the reference corresponds to this
+(it is single-process); SURVEY.md section 8(e)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from ._lib import NSUMS
+
+
+def shard_range(n_paths: int, rank: int, world: int):
+    """[lo, hi) of the global path index owned by `rank`: contiguous, sizes differ by at most one."""
+    base, rem = divmod(int(n_paths), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Comm:
+    """Minimal communicator interface: rank, world, allreduce_sum(np.float64 array) -> np.float64 array."""
+    rank = 0
+    world = 1
+
+    def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
+        return a
+
+
+class TorchComm(Comm):
+    """torch.distributed communicator.  With the NCCL backend the sums are reduced on the device."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+
+    def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        if self.backend == "nccl":
+            t = t.cuda()
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+
+def sharded_sums(handle, comm: Comm, params, spot, T, steps, n_paths, seed, strikes, is_call, flags,
+                 bumps=None) -> np.ndarray:
+    """Each rank simulates its path range; returns the all-reduced [n_strikes, NSUMS] sums on every rank."""
+    lo, hi = shard_range(n_paths, comm.rank, comm.world)
+    ks = np.atleast_1d(np.asarray(strikes, dtype=np.float64))
+    if hi > lo:
+        local = handle.price_european(params, spot, T, steps, hi - lo, seed, ks, is_call, flags, bumps,
+                                      path_offset=lo)
+    else:
+        local = np.zeros((ks.size, NSUMS))
+    return comm.allreduce_sum(local).reshape(ks.size, NSUMS)

@@ -1,0 +1,378 @@
+"""Host mirror of engine/monte_carlo.py on top of libb200mc (CUDA, sm_100a).
+
+Same names, argument meaning, result dictionaries and error behaviour as the reference module, so its callers
+(engine/app.py:142-149,219-223, engine/greeks.py, engine/risk.py:37-93, engine/calibration.py:78-85, verify.py:31-51)
+run unchanged after ``patch_reference()``:
+
+    bs_price, bs_delta                     monte_carlo.py:28-55      closed forms (scalar, host)
+    _simulate_svj_paths_numba              monte_carlo.py:189-243    -> b200mc_simulate_given_normals
+    MonteCarloEngine.price                 monte_carlo.py:273-375    -> b200mc_price_european (fused)
+    MonteCarloEngine.price_batch           monte_carlo.py:377-450    -> b200mc_price_european, all strikes in one launch
+    MonteCarloEngine.get_sample_paths      monte_carlo.py:452-471    -> b200mc_generate_paths
+
+Random numbers.  ``rng="philox"`` (default) draws on the device (Philox4x32-10 in registers, nothing materialised);
+results agree with the reference statistically (within 3 standard errors), not draw for draw.  ``rng="reference"``
+reproduces the reference's own host draws -- PCG64 or scrambled Sobol + its Brownian-bridge re-ordering
+(monte_carlo.py:61-183,290-308) -- and runs the recurrence on the GPU over those arrays; results then agree with the
+reference to ~1e-12.  That mode exists for parity and is as slow as the reference's RNG front end.
+The environment variable B200MC_RNG overrides the default.
+
+Documented divergences: an ``int`` spot is cast to float (the reference silently truncates every step to int64,
+SURVEY.md section 0 quirk 3); the reference's degenerate Sobol/Brownian-bridge path and its pseudo control variate
+(quirks 1, 2) are reproduced as they are, and a genuine control-variate estimate is returned under NEW keys
+(``price_cv_spot``, ``std_error_cv_spot``) by the philox mode only.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import ANTITHETIC, FP64, SUMS_FIELDS
+
+DEFAULT_NUM_PATHS = 500_000      # engine/config.py:23
+DEFAULT_NUM_STEPS = 252          # engine/config.py:24
+
+_COL = {n: i for i, n in enumerate(SUMS_FIELDS)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# closed forms (engine/monte_carlo.py:28-55)
+# --------------------------------------------------------------------------------------------------------
+def _ncdf(x: float) -> float:
+    return 0.5 * math.erfc(-x / math.sqrt(2.0))
+
+
+def bs_price(S: float, K: float, T: float, r: float, q: float, sigma: float, is_call: bool = True) -> float:
+    """Analytical Black-Scholes price (monte_carlo.py:28-42)."""
+    if T <= 0:
+        return max(S - K, 0.0) if is_call else max(K - S, 0.0)
+    sT = sigma * math.sqrt(T)
+    d1 = (math.log(S / K) + (r - q + 0.5 * sigma ** 2) * T) / sT
+    d2 = d1 - sT
+    if is_call:
+        return S * math.exp(-q * T) * _ncdf(d1) - K * math.exp(-r * T) * _ncdf(d2)
+    return K * math.exp(-r * T) * _ncdf(-d2) - S * math.exp(-q * T) * _ncdf(-d1)
+
+
+def bs_delta(S: float, K: float, T: float, r: float, q: float, sigma: float, is_call: bool = True) -> float:
+    """Analytical Black-Scholes delta (monte_carlo.py:45-55)."""
+    if T <= 0:
+        if is_call:
+            return 1.0 if S > K else 0.0
+        return -1.0 if S < K else 0.0
+    d1 = (math.log(S / K) + (r - q + 0.5 * sigma ** 2) * T) / (sigma * math.sqrt(T))
+    if is_call:
+        return math.exp(-q * T) * _ncdf(d1)
+    return math.exp(-q * T) * (_ncdf(d1) - 1.0)
+
+
+# --------------------------------------------------------------------------------------------------------
+# the reference's host RNG front end, kept on the host for rng="reference" (SURVEY.md 8a, rows a2 / a2')
+# --------------------------------------------------------------------------------------------------------
+def generate_sobol_normals(num_paths: int, num_dims: int, seed: int = 0) -> np.ndarray:
+    """Scrambled Sobol points -> clip -> inverse normal CDF (monte_carlo.py:61-85)."""
+    from scipy.stats import norm
+    from scipy.stats.qmc import Sobol
+    m = int(np.ceil(np.log2(max(num_paths, 2))))
+    pts = Sobol(d=num_dims, scramble=True, seed=seed).random(2 ** m)
+    return norm.ppf(np.clip(pts, 1e-10, 1 - 1e-10))[:num_paths]
+
+
+def _bb_ordering(n: int) -> List[int]:
+    """Visit order of the bridge: endpoint, then interval midpoints breadth first (monte_carlo.py:148-169)."""
+    if n <= 0:
+        return []
+    done = np.zeros(n, dtype=bool)
+    order = [n - 1]
+    done[n - 1] = True
+    work, head = [(0, n - 1)], 0
+    while head < len(work) and len(order) < n:
+        a, b = work[head]
+        head += 1
+        if b - a <= 1:
+            if not done[a]:
+                order.append(a)
+                done[a] = True
+            continue
+        mid = (a + b) // 2
+        if not done[mid]:
+            order.append(mid)
+            done[mid] = True
+        work += [(a, mid), (mid, b)]
+    order += [i for i in range(n) if not done[i]]
+    return order[:n]
+
+
+def brownian_bridge_reorder(normals: np.ndarray, num_steps: int) -> np.ndarray:
+    """The reference's Brownian-bridge construction, monte_carlo.py:88-145 with the neighbour search of :172-183,
+    reproduced INCLUDING its degeneracy (the first point placed is the endpoint itself, so its conditional variance
+    is 0 and W_T == 0 on every path).  Kept for API parity only."""
+    n_paths = normals.shape[0]
+    dt = 1.0 / num_steps
+    W = np.zeros((n_paths, num_steps + 1))
+    known = np.zeros(num_steps + 2, dtype=bool)
+    for dim, tidx in enumerate(_bb_ordering(num_steps)):
+        if dim >= normals.shape[1]:
+            break
+        j = tidx + 1
+        lo = np.flatnonzero(known[1:j + 1])
+        hi = np.flatnonzero(known[j:num_steps])
+        left = int(lo[-1]) + 1 if lo.size else 0
+        right = int(hi[0]) + j if hi.size else num_steps
+        t, tl, tr = j * dt, left * dt, right * dt
+        if right > left:
+            mean = W[:, left] + (W[:, right] - W[:, left]) * (t - tl) / (tr - tl)
+            var = (t - tl) * (tr - t) / (tr - tl)
+        else:
+            mean = W[:, left]
+            var = t - tl
+        W[:, j] = mean + math.sqrt(max(var, 0)) * normals[:, dim]
+        known[j] = True
+    return np.diff(W, axis=1)
+
+
+def _reference_draws(seed: int, n: int, steps: int, use_sobol: bool):
+    """(Z1, Z2, Z_jump, Z_jump_size) exactly as MonteCarloEngine.price draws them (monte_carlo.py:290-308)."""
+    if use_sobol:
+        raw = generate_sobol_normals(n, 3 * steps, seed=seed)
+        Z1 = brownian_bridge_reorder(raw[:, :steps], steps)
+        Z2 = brownian_bridge_reorder(raw[:, steps:2 * steps], steps)
+        Zjs = np.ascontiguousarray(raw[:, 2 * steps:3 * steps])
+    else:
+        g = np.random.default_rng(seed)
+        Z1 = g.standard_normal((n, steps))
+        Z2 = g.standard_normal((n, steps))
+        Zjs = g.standard_normal((n, steps))
+    Zj = np.random.default_rng(seed + 1).random((n, steps))
+    return Z1, Z2, Zj, Zjs
+
+
+# --------------------------------------------------------------------------------------------------------
+# a1: drop-in for the Numba kernel
+# --------------------------------------------------------------------------------------------------------
+def _simulate_svj_paths_numba(S0, v0, r, q, T, kappa, theta, xi, rho, lambda_j, mu_j, sigma_j,
+                              Z1, Z2, Z_jump, Z_jump_size, num_steps, record_paths=False):
+    """Same signature and return triple as the reference kernel (monte_carlo.py:189-243); runs on the GPU."""
+    class _P:
+        pass
+    p = _P()
+    p.v0, p.r, p.q, p.kappa, p.theta, p.xi, p.rho = v0, r, q, kappa, theta, xi, rho
+    p.lambda_j, p.mu_j, p.sigma_j = lambda_j, mu_j, sigma_j
+    S, v, paths = _lib.default_handle().simulate_given_normals(p, float(S0), T, Z1, Z2, Z_jump, Z_jump_size,
+                                                               int(num_steps), bool(record_paths))
+    return S, v, (paths if record_paths else np.zeros((0, 0)))
+
+
+def steps_for(num_steps: int, T: float, floor: int = 10) -> int:
+    """monte_carlo.py:287 (floor 10) and :455 (floor 50)."""
+    return max(int(num_steps * T), floor)
+
+
+def _default_rng() -> str:
+    return os.environ.get("B200MC_RNG", "philox")
+
+
+# --------------------------------------------------------------------------------------------------------
+# a3 / a4 / a5
+# --------------------------------------------------------------------------------------------------------
+class MonteCarloEngine:
+    """Mirror of the reference's MonteCarloEngine (monte_carlo.py:249-471).
+
+    Extra keyword-only arguments (not in the reference): ``rng`` ("philox" | "reference"), ``precision``
+    ("fp32" | "fp64": arithmetic of the path state in the fused kernels), ``handle`` (a ``_lib.Handle``),
+    ``comm`` (a ``dist.Comm``: paths are sharded over its ranks and the sums all-reduced).
+    """
+
+    def __init__(self, params, num_paths: int = DEFAULT_NUM_PATHS, num_steps: int = DEFAULT_NUM_STEPS,
+                 seed: int = 42, use_sobol: bool = True, use_antithetic: bool = True,
+                 use_control_variate: bool = True, *, rng: Optional[str] = None, precision: str = "fp32",
+                 handle=None, comm=None):
+        self.params = params
+        self.num_paths = num_paths
+        self.num_steps = num_steps
+        self.seed = seed
+        self.use_sobol = use_sobol
+        self.use_antithetic = use_antithetic
+        self.use_control_variate = use_control_variate
+        self.rng = rng or _default_rng()
+        if self.rng not in ("philox", "reference"):
+            raise ValueError("rng must be 'philox' or 'reference'")
+        if precision not in ("fp32", "fp64"):
+            raise ValueError("precision must be 'fp32' or 'fp64'")
+        self.precision = precision
+        self._handle = handle
+        self.comm = comm
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            self._handle = _lib.default_handle()
+        return self._handle
+
+    # ---- fused path -------------------------------------------------------------------------------------
+    def _flags(self) -> int:
+        return (ANTITHETIC if self.use_antithetic else 0) | (FP64 if self.precision == "fp64" else 0)
+
+    def _sums(self, spot, strikes, T, is_call, steps, flags=None, bumps=None) -> np.ndarray:
+        flags = self._flags() if flags is None else flags
+        n = int(self.num_paths)
+        if self.comm is not None and self.comm.world > 1:
+            from .dist import sharded_sums
+            return sharded_sums(self.handle, self.comm, self.params, float(spot), float(T), steps, n, self.seed,
+                                strikes, is_call, flags, bumps)
+        return self.handle.price_european(self.params, float(spot), float(T), steps, n, self.seed, strikes,
+                                          is_call, flags, bumps)
+
+    @staticmethod
+    def _moments(row: np.ndarray, anti: bool):
+        """mean and population variance of the combined payoff, mean of the primary payoff, variance of
+        (combined - primary): everything price()/price_batch() need, from the five sums."""
+        n = row[_COL["n"]]
+        sa, sb, saa, sbb, sab = (row[_COL[k]] for k in ("sum_a", "sum_b", "sum_aa", "sum_bb", "sum_ab"))
+        mean_a = sa / n
+        if anti:
+            mean = 0.5 * (sa + sb) / n
+            var = max(0.25 * (saa + 2.0 * sab + sbb) / n - mean * mean, 0.0)
+            dmean = 0.5 * (sb - sa) / n
+            dvar = max(0.25 * (saa - 2.0 * sab + sbb) / n - dmean * dmean, 0.0)
+        else:
+            mean, var = mean_a, max(saa / n - mean_a * mean_a, 0.0)
+            dvar = 0.0
+        return n, mean, var, mean_a, dvar
+
+    def price(self, spot: float, strike: float, T: float, is_call: bool = True) -> Dict[str, float]:
+        """Price a European option; same keys as monte_carlo.py:345-373."""
+        if self.rng == "reference":
+            return self._price_reference(spot, strike, T, is_call)
+        p = self.params
+        steps = steps_for(self.num_steps, T)                                   # :287
+        row = self._sums(spot, [float(strike)], T, is_call, steps)[0]
+        n, mean, var, mean_a, dvar = self._moments(row, self.use_antithetic)
+        discount = math.exp(-p.r * T)                                          # :327
+        raw_price = discount * mean                                            # :342
+        result = {"price": raw_price, "std_error": discount * math.sqrt(var) / math.sqrt(n),   # :343
+                  "num_paths_used": self.num_paths, "num_steps": steps}
+        if self.use_control_variate:                                           # :353-373 (pseudo-CV, quirk 2)
+            bs_ref = bs_price(float(spot), strike, T, p.r, p.q, math.sqrt(p.v0), is_call)
+            bs_mc = discount * mean_a
+            result["price"] = raw_price - (bs_mc - bs_ref)
+            result["bs_cv_adjustment"] = bs_mc - bs_ref
+            result["bs_ref"] = bs_ref
+            result["raw_mc_price"] = raw_price
+            result["std_error"] = discount * math.sqrt(dvar) / math.sqrt(n)
+        result.update(self._spot_cv(row, spot, T, discount))
+        return result
+
+    def _spot_cv(self, row, spot, T, discount) -> Dict[str, float]:
+        """NEW keys: regression control variate on S_T, whose mean S0 e^{(r-q)T} is known for every SVJ
+        parameter set (the jump drift is compensated, monte_carlo.py:209-210)."""
+        p = self.params
+        n = row[_COL["n"]]
+        anti = self.use_antithetic
+        pay_mean = (0.5 * (row[_COL["sum_a"]] + row[_COL["sum_b"]]) if anti else row[_COL["sum_a"]]) / n
+        if anti:
+            pay_sq = 0.25 * (row[_COL["sum_aa"]] + 2 * row[_COL["sum_ab"]] + row[_COL["sum_bb"]]) / n
+        else:
+            pay_sq = row[_COL["sum_aa"]] / n
+        s_mean, s_sq, ps = row[_COL["sum_s"]] / n, row[_COL["sum_ss"]] / n, row[_COL["sum_ps"]] / n
+        var_s = s_sq - s_mean * s_mean
+        if not var_s > 0:
+            return {}
+        cov = ps - pay_mean * s_mean
+        beta = cov / var_s
+        target = float(spot) * math.exp((p.r - p.q) * T)
+        var_cv = max(pay_sq - pay_mean * pay_mean - cov * cov / var_s, 0.0)
+        return {"price_cv_spot": discount * (pay_mean - beta * (s_mean - target)),
+                "std_error_cv_spot": discount * math.sqrt(var_cv) / math.sqrt(n)}
+
+    def price_batch(self, spot: float, strikes, T: float, is_call: bool = True) -> list:
+        """Price multiple strikes with shared path simulation (monte_carlo.py:377-450)."""
+        if self.rng == "reference":
+            return self._price_batch_reference(spot, strikes, T, is_call)
+        p = self.params
+        steps = steps_for(self.num_steps, T)
+        ks = np.asarray(strikes, dtype=np.float64).ravel()
+        discount = math.exp(-p.r * T)
+        sigma_bs = math.sqrt(p.v0)
+        results = []
+        for lo in range(0, ks.size, 256):                                      # at most 256 strikes per launch
+            rows = self._sums(spot, ks[lo:lo + 256], T, is_call, steps)
+            for K, row in zip(list(strikes)[lo:lo + 256], rows):
+                n, mean, var, mean_a, _ = self._moments(row, self.use_antithetic)
+                raw = discount * mean
+                res = {"strike": K, "price": raw, "std_error": discount * math.sqrt(var) / math.sqrt(n)}   # :438-441
+                if self.use_control_variate:                                   # :443-448
+                    bs_ref = bs_price(float(spot), float(K), T, p.r, p.q, sigma_bs, is_call)
+                    res["price"] = raw - (discount * mean_a - bs_ref)
+                    res["bs_ref"] = bs_ref
+                results.append(res)
+        return results
+
+    def get_sample_paths(self, spot: float, T: float, num_samples: int = 50) -> np.ndarray:
+        """[num_samples, steps + 1] float64, column 0 = spot (monte_carlo.py:452-471)."""
+        steps = steps_for(self.num_steps, T, floor=50)                         # :455
+        if self.rng == "reference":
+            g = np.random.default_rng(self.seed + 999)                         # :458-462
+            Z1 = g.standard_normal((num_samples, steps))
+            Z2 = g.standard_normal((num_samples, steps))
+            Zjs = g.standard_normal((num_samples, steps))
+            Zj = g.random((num_samples, steps))
+            return self.handle.simulate_given_normals(self.params, float(spot), T, Z1, Z2, Zj, Zjs, steps, True)[2]
+        return self.handle.generate_paths(self.params, float(spot), T, steps, int(num_samples), self.seed + 999,
+                                          FP64, np.float64)
+
+    # ---- rng="reference": the reference's own draws, recurrence on the GPU ------------------------------
+    def _terminal_reference(self, spot, T):
+        p = self.params
+        n = int(self.num_paths)
+        steps = steps_for(self.num_steps, T)
+        Z1, Z2, Zj, Zjs = _reference_draws(self.seed, n, steps, self.use_sobol)
+        h = self.handle
+        S = h.simulate_given_normals(p, float(spot), T, Z1, Z2, Zj, Zjs, steps)[0]
+        S_anti = None
+        if self.use_antithetic:                                                # :318-324
+            S_anti = h.simulate_given_normals(p, float(spot), T, -Z1, -Z2, Zj, -Zjs, steps)[0]
+        return steps, S, S_anti
+
+    def _price_reference(self, spot, strike, T, is_call):
+        p, n = self.params, self.num_paths
+        steps, S, S_anti = self._terminal_reference(spot, T)
+        discount = np.exp(-p.r * T)
+        pay = (lambda s: np.maximum(s - strike, 0.0)) if is_call else (lambda s: np.maximum(strike - s, 0.0))
+        a = pay(S)
+        payoffs = 0.5 * (a + pay(S_anti)) if self.use_antithetic else a
+        raw_price = discount * np.mean(payoffs)
+        result = {"price": raw_price, "std_error": discount * np.std(payoffs) / np.sqrt(n),
+                  "num_paths_used": n, "num_steps": steps}
+        if self.use_control_variate:
+            bs_ref = bs_price(float(spot), strike, T, p.r, p.q, np.sqrt(p.v0), is_call)
+            bs_mc = discount * np.mean(a)
+            result["price"] = raw_price - (bs_mc - bs_ref)
+            result["bs_cv_adjustment"] = bs_mc - bs_ref
+            result["bs_ref"] = bs_ref
+            result["raw_mc_price"] = raw_price
+            result["std_error"] = discount * np.std(payoffs - (a - bs_ref / discount)) / np.sqrt(n)
+        return result
+
+    def _price_batch_reference(self, spot, strikes, T, is_call):
+        p, n = self.params, self.num_paths
+        _, S, S_anti = self._terminal_reference(spot, T)
+        discount = np.exp(-p.r * T)
+        sigma_bs = np.sqrt(p.v0)
+        results = []
+        for K in strikes:
+            pay = (lambda s: np.maximum(s - K, 0.0)) if is_call else (lambda s: np.maximum(K - s, 0.0))
+            a = pay(S)
+            payoffs = 0.5 * (a + pay(S_anti)) if self.use_antithetic else a
+            raw = discount * np.mean(payoffs)
+            res = {"strike": K, "price": raw, "std_error": discount * np.std(payoffs) / np.sqrt(n)}
+            if self.use_control_variate:
+                bs_ref = bs_price(float(spot), float(K), T, p.r, p.q, sigma_bs, is_call)
+                res["price"] = raw - (discount * np.mean(a) - bs_ref)
+                res["bs_ref"] = bs_ref
+            results.append(res)
+        return results

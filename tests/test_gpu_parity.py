@@ -1,0 +1,519 @@
+"""GPU parity tests: every CUDA entry point of libb200mc (through its C ABI / ctypes) against the CPU oracle, the
+golden fixtures written by the reference, and size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star):
+  deterministic mode (identical draws)   <= 1e-6 relative in fp64, <= 1e-4 in fp32   (we assert far tighter in fp64)
+  production mode                        within 3 standard errors of the reference, within 1e-3 (relative) of
+                                         closed-form Black-Scholes in the GBM limit
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import unnan
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-11      # fp64 kernels vs oracle on identical inputs (north_star bound: 1e-6)
+RTOL32 = 1e-4       # fp32 path state vs the fp64 oracle on identical draws (north_star bound)
+
+
+@pytest.fixture(scope="module")
+def H():
+    from monte_carlo_option_simulator_b200 import _lib
+    h = _lib.Handle(0)
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="module")
+def L():
+    from monte_carlo_option_simulator_b200 import _lib
+    return _lib
+
+
+def P(golden, name):
+    return O.Params(**golden["params"][name])
+
+
+PNAMES = ["svj_default", "gbm_cfg1", "heston", "jumpy"]
+
+
+# ---------------------------------------------------------------------------------------------- device + RNG
+def test_device_is_b200(H):
+    info = H.device_info()
+    assert info["cc"] // 10 == 10 and info["sm_count"] >= 100
+
+
+def test_philox_words_bit_exact(H, L):
+    for seed, off, stream in [(42, 0, 0), (0x1234567890ABCDEF, (1 << 32) - 3, 1), (2 ** 64 - 1, 2 ** 40 + 5, 2)]:
+        got = H.dump_philox(seed, 37, 9, stream, path_offset=off)
+        np.testing.assert_array_equal(got, O.philox_block_words(seed, off, 37, 9, stream))
+
+
+def test_philox_kat_on_device(H, golden):
+    # ctr = (path_lo, path_hi, block, stream), key = seed: reproduce the Random123 vectors through the dump
+    kat = golden["cases"]["philox_kat"][0]
+    assert all(int(x, 16) == 0 for x in kat["ctr"] + kat["key"])
+    got = H.dump_philox(0, 1, 1, 0)[0, 0]
+    np.testing.assert_array_equal(got, np.array([int(x, 16) for x in kat["out"]], dtype=np.uint32))
+
+
+def test_normals_are_standard(H, L):
+    z = H.dump_normals(7, 20000, 64, L.STREAM_GBM, L.Z1)
+    assert abs(z.mean()) < 4 / math.sqrt(z.size) and abs(z.var() - 1) < 5 * math.sqrt(2 / z.size)
+    assert abs((z ** 3).mean()) < 5 * math.sqrt(15 / z.size) and abs((z ** 4).mean() - 3) < 5 * math.sqrt(96 / z.size)
+    z1 = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.Z1)
+    z2 = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.Z2)
+    u = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_U)
+    zj = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_SIZE)
+    assert abs(np.corrcoef(z1.ravel(), z2.ravel())[0, 1]) < 5 / math.sqrt(z1.size)
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 5 / math.sqrt(12 * u.size)
+    assert abs(zj.mean()) < 5 / math.sqrt(zj.size) and abs(zj.var() - 1) < 5 * math.sqrt(2 / zj.size)
+
+
+# ---------------------------------------------------------------------------------------------- a1: given normals
+@pytest.mark.parametrize("name", PNAMES)
+def test_given_normals_golden(H, golden, garr, name):
+    p = P(golden, name)
+    S, v, paths = H.simulate_given_normals(p, 22500.0, 0.25, garr["k_small_Z1"], garr["k_small_Z2"], garr["k_small_Zj"],
+                                           garr["k_small_Zjs"], 40, True)
+    np.testing.assert_allclose(S, garr[f"k_small_{name}_S"], rtol=RTOL64)
+    np.testing.assert_allclose(v, garr[f"k_small_{name}_v"], rtol=RTOL64, atol=1e-17)
+    np.testing.assert_allclose(paths, garr[f"k_small_{name}_paths"], rtol=RTOL64)
+    assert np.all(paths[:, 0] == 22500.0)
+
+
+def test_given_normals_pcg64_4096(H, golden, garr):
+    c = golden["cases"]["k_4096"]
+    p = P(golden, c["params"])
+    Z1, Z2, Zj, Zjs = O.draw_pcg64(c["seed"], c["n"], c["steps"])
+    S, v, none = H.simulate_given_normals(p, c["spot"], c["T"], Z1, Z2, Zj, Zjs, c["steps"])
+    assert none is None
+    np.testing.assert_allclose(S, garr["k_4096_S"], rtol=RTOL64)
+    np.testing.assert_allclose(v, garr["k_4096_v"], rtol=RTOL64, atol=1e-17)
+    Sa = H.simulate_given_normals(p, c["spot"], c["T"], -Z1, -Z2, Zj, -Zjs, c["steps"])[0]
+    np.testing.assert_allclose(Sa, garr["k_4096_S_anti"], rtol=RTOL64)
+    Su = H.simulate_given_normals(p.replace(v0=p.v0 + 0.01), c["spot"], c["T"], Z1, Z2, Zj, Zjs, c["steps"])[0]
+    np.testing.assert_allclose(Su, garr["k_4096_S_v0up"], rtol=RTOL64)
+
+
+@pytest.mark.parametrize("n,steps", [(1, 1), (31, 7), (33, 16), (100, 17), (257, 50)])
+def test_given_normals_ragged(H, golden, n, steps):
+    p = P(golden, "svj_default")
+    g = np.random.default_rng(n * 1000 + steps)
+    Z1, Z2, Zjs = (g.standard_normal((n, steps)) for _ in range(3))
+    Zj = g.random((n, steps))
+    S, v, paths = H.simulate_given_normals(p, 100.0, 0.5, Z1, Z2, Zj, Zjs, steps, True)
+    So, vo, po = O.simulate_svj(100.0, p.v0, p.r, p.q, 0.5, p.kappa, p.theta, p.xi, p.rho, p.lambda_j, p.mu_j, p.sigma_j,
+                                Z1, Z2, Zj, Zjs, steps, True)
+    np.testing.assert_allclose(S, So, rtol=RTOL64)
+    np.testing.assert_allclose(v, vo, rtol=RTOL64, atol=1e-17)
+    np.testing.assert_allclose(paths, po, rtol=RTOL64)
+
+
+def test_given_normals_empty_and_errors(H, L, golden):
+    p = P(golden, "svj_default")
+    e = np.zeros((0, 5))
+    S, v, _ = H.simulate_given_normals(p, 100.0, 0.5, e, e, e, e, 5)
+    assert S.shape == (0,) and v.shape == (0,)
+    with pytest.raises(L.B200MCError):
+        H.simulate_given_normals(p, 100.0, 0.5, np.zeros((4, 5)), np.zeros((3, 5)), np.zeros((4, 5)), np.zeros((4, 5)), 5)
+    with pytest.raises(L.B200MCError):
+        H.price_european(p, 100.0, 0.5, 0, 10, 1, [100.0])
+    with pytest.raises(L.B200MCError):
+        H.price_european(p, 100.0, -1.0, 10, 10, 1, [100.0])
+
+
+def test_drop_in_kernel_function(golden, garr):
+    from monte_carlo_option_simulator_b200 import _simulate_svj_paths_numba as f
+    p = P(golden, "jumpy")
+    S, v, paths = f(22500.0, p.v0, p.r, p.q, 0.25, p.kappa, p.theta, p.xi, p.rho, p.lambda_j, p.mu_j, p.sigma_j,
+                    garr["k_small_Z1"], garr["k_small_Z2"], garr["k_small_Zj"], garr["k_small_Zjs"], 40)
+    assert paths.shape == (0, 0)
+    np.testing.assert_allclose(S, garr["k_small_jumpy_S"], rtol=RTOL64)
+
+
+# ---------------------------------------------------------------------------------------------- fused: deterministic mode
+def _mode_params(golden, mode):
+    if mode == "gbm":
+        return P(golden, "gbm_cfg1").replace(kappa=0.0), 0
+    if mode == "detvar":
+        return P(golden, "gbm_cfg1").replace(kappa=3.0, theta=0.05), 0
+    if mode == "heston":
+        return P(golden, "heston"), 1
+    return P(golden, "svj_default"), 2
+
+
+def _draws(H, L, seed, n, steps, stream, off=0):
+    return [H.dump_normals(seed, n, steps, stream, w, path_offset=off) for w in (L.Z1, L.Z2, L.ZJUMP_U, L.ZJUMP_SIZE)]
+
+
+@pytest.mark.parametrize("mode", ["gbm", "detvar", "heston", "svj"])
+@pytest.mark.parametrize("steps", [250, 63, 10, 7])
+def test_fused_terminal_identical_draws(H, L, golden, mode, steps):
+    """north_star deterministic mode: the reference recurrence (oracle) fed the IDENTICAL draws."""
+    p, stream = _mode_params(golden, mode)
+    n, seed, off, T, S0 = 1500, 99, 12345, 0.8, 2500.0
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, stream, off)
+    So, vo, _ = O._sim(p, S0, T, Z1, Z2, Zj, Zjs, steps)
+    Sao = O._sim(p, S0, T, -Z1, -Z2, Zj, -Zjs, steps)[0]
+    S, A, V = H.simulate_terminal(p, S0, T, steps, n, seed, L.ANTITHETIC | L.FP64, np.float64, off, True, True)
+    np.testing.assert_allclose(S, So, rtol=1e-10)
+    np.testing.assert_allclose(A, Sao, rtol=1e-10)
+    np.testing.assert_allclose(V, vo, rtol=1e-9, atol=1e-15)
+    S32, A32, V32 = H.simulate_terminal(p, S0, T, steps, n, seed, L.ANTITHETIC, np.float32, off, True, True)
+    assert S32.dtype == np.float32
+    np.testing.assert_allclose(S32, So, rtol=RTOL32)
+    np.testing.assert_allclose(A32, Sao, rtol=RTOL32)
+    np.testing.assert_allclose(V32, vo, rtol=2e-3, atol=2e-6)   # variance near the zero boundary amplifies fp32 rounding
+
+
+def test_fused_jumps_fire_like_reference(H, L, golden):
+    """A jump-heavy parameter set: the integer jump test in the kernel must equal the reference's float compare."""
+    p = P(golden, "jumpy")
+    n, steps, seed = 4000, 40, 5
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, 2)
+    assert (Zj < p.lambda_j * 0.5 / steps).sum() > 100
+    So = O._sim(p, 100.0, 0.5, Z1, Z2, Zj, Zjs, steps)[0]
+    S = H.simulate_terminal(p, 100.0, 0.5, steps, n, seed, L.FP64, np.float64)[0]
+    np.testing.assert_allclose(S, So, rtol=1e-10)
+
+
+def test_force_svj_on_gbm_params(H, L, golden):
+    p, _ = _mode_params(golden, "gbm")
+    n, steps, seed = 512, 30, 3
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, 2)
+    So = O._sim(p, 2500.0, 1.0, Z1, Z2, Zj, Zjs, steps)[0]
+    S = H.simulate_terminal(p, 2500.0, 1.0, steps, n, seed, L.FP64 | L.FORCE_SVJ, np.float64)[0]
+    np.testing.assert_allclose(S, So, rtol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------- fused: sums
+def _np_sums(L, S, A, K, is_call, S0, extra=None):
+    pay = (lambda s: np.maximum(s - K, 0.0)) if is_call else (lambda s: np.maximum(K - s, 0.0))
+    a = pay(S)
+    b = pay(A) if A is not None else np.zeros_like(a)
+    s_avg = 0.5 * (S + A) if A is not None else S
+    payc = 0.5 * (a + b) if A is not None else a
+    d = dict(n=len(S), sum_a=a.sum(), sum_b=b.sum(), sum_aa=(a * a).sum(), sum_bb=(b * b).sum(), sum_ab=(a * b).sum(),
+             sum_s=s_avg.sum(), sum_ss=(s_avg ** 2).sum(), sum_ps=(payc * s_avg).sum())
+    return d
+
+
+@pytest.mark.parametrize("mode", ["gbm", "detvar", "heston", "svj"])
+@pytest.mark.parametrize("anti", [False, True])
+@pytest.mark.parametrize("is_call", [True, False])
+def test_fused_sums_match_terminal_values(H, L, golden, mode, anti, is_call):
+    """The on-chip reduction equals NumPy sums over the terminal values of the same paths (fp64 state), for a
+    ragged path count, a path offset and several strike counts (1, 3, 21, 64)."""
+    p, _ = _mode_params(golden, mode)
+    n, steps, seed, off, S0, T = 3001, 50, 11, 777, 2500.0, 1.0
+    fl = L.FP64 | (L.ANTITHETIC if anti else 0)
+    S, A, _ = H.simulate_terminal(p, S0, T, steps, n, seed, fl, np.float64, off, anti, False)
+    for ks in ([2500.0], [2000.0, 2500.0, 3100.0], list(np.linspace(0.7, 1.3, 21) * S0), list(np.linspace(0.7, 1.3, 64) * S0)):
+        rows = H.price_european(p, S0, T, steps, n, seed, ks, is_call, fl, None, path_offset=off)
+        assert rows.shape == (len(ks), L.NSUMS)
+        for K, row in zip(ks, rows):
+            want = _np_sums(L, S, A if anti else None, K, is_call, S0)
+            for k, w in want.items():
+                assert row[L.SUMS_FIELDS.index(k)] == pytest.approx(w, rel=1e-11, abs=1e-6), (k, K)
+
+
+@pytest.mark.parametrize("mode", ["gbm", "detvar", "heston", "svj"])
+@pytest.mark.parametrize("is_call", [True, False])
+def test_fused_greek_sums_vs_oracle(H, L, golden, mode, is_call):
+    """Bump accumulators of the fused launch == re-simulating with the oracle on the identical draws (the
+    reference's CRN construction, greeks.py:65-80,:124-147)."""
+    p, stream = _mode_params(golden, mode)
+    n, steps, seed, S0, T, K, b = 2000, 40, 21, 2500.0, 0.5, 2450.0, 0.01
+    Z = _draws(H, L, seed, n, steps, stream)
+    bumps = L.Bumps(b, p.v0 + 0.01, max(p.v0 - 0.01, 0.001), p.r + 1e-4, max(p.r - 1e-4, 0))
+    row = H.price_european(p, S0, T, steps, n, seed, [K], is_call, L.FP64 | L.GREEKS, bumps)[0]
+    col = {k: row[i] for i, k in enumerate(L.SUMS_FIELDS)}
+    pay = (lambda s: np.maximum(s - K, 0.0)) if is_call else (lambda s: np.maximum(K - s, 0.0))
+    S = O._sim(p, S0, T, *Z, steps)[0]
+    itm = (S > K) if is_call else (S < K)
+    want = {
+        "sum_a": pay(S).sum(),
+        "sum_pw_delta": (itm * S / S0).sum(),
+        "sum_spot_up": pay(O._sim(p, S0 * (1 + b), T, *Z, steps)[0]).sum(),
+        "sum_spot_dn": pay(O._sim(p, S0 * (1 - b), T, *Z, steps)[0]).sum(),
+        "sum_v0_up": pay(O._sim(p, S0, T, *Z, steps, v0=bumps.v0_up)[0]).sum(),
+        "sum_v0_dn": pay(O._sim(p, S0, T, *Z, steps, v0=bumps.v0_dn)[0]).sum(),
+        "sum_r_up": pay(O._sim(p.replace(r=bumps.r_up), S0, T, *Z, steps)[0]).sum(),
+        "sum_r_dn": pay(O._sim(p.replace(r=bumps.r_dn), S0, T, *Z, steps)[0]).sum(),
+    }
+    for k, w in want.items():
+        assert col[k] == pytest.approx(w, rel=1e-9), k
+
+
+def test_fused_fp32_sums_close_to_fp64(H, L, golden):
+    p, _ = _mode_params(golden, "gbm")
+    ks = list(np.linspace(0.8, 1.2, 5) * 2500.0)
+    r64 = H.price_european(p, 2500.0, 1.0, 250, 200_000, 42, ks, True, L.FP64 | L.ANTITHETIC)
+    r32 = H.price_european(p, 2500.0, 1.0, 250, 200_000, 42, ks, True, L.ANTITHETIC)
+    np.testing.assert_allclose(r32[:, :9], r64[:, :9], rtol=2e-5)
+
+
+def test_fused_launch_is_reproducible_and_offsets_add(H, L, golden):
+    p, _ = _mode_params(golden, "svj")
+    a = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, [95.0, 105.0], True, L.ANTITHETIC)
+    b = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, [95.0, 105.0], True, L.ANTITHETIC)
+    np.testing.assert_array_equal(a, b)
+    lo = H.price_european(p, 100.0, 0.5, 20, 3_333, 9, [95.0, 105.0], True, L.ANTITHETIC)
+    hi = H.price_european(p, 100.0, 0.5, 20, 6_667, 9, [95.0, 105.0], True, L.ANTITHETIC, path_offset=3_333)
+    np.testing.assert_allclose(lo + hi, a, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- production mode
+def test_production_gbm_vs_black_scholes_and_reference(golden):
+    """BASELINE config 1 market, 2e7 paths x 250 steps, plain MC (no antithetic, no CV): |MC - BS| <= 1e-3 * BS
+    (SE ~ 575 / sqrt(n) = 0.13 => 1e-3 relative is ~2.9 sigma; we also assert the 3-sigma band itself) and within
+    3 combined standard errors of the reference's own 50k-path value (golden)."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    p = SVJParams(**golden["params"]["gbm_cfg1"])
+    ref = [c for c in golden["cases"]["price"] if c["n"] == 50_000 and c["is_call"] and not c["sobol"]
+           and not c["anti"] and not c["cv"]][0]["result"]
+    bs = golden["cases"]["bs"]["cfg1_call"]
+    for prec in ("fp32", "fp64"):
+        eng = MonteCarloEngine(p, 20_000_000, 250, seed=42, use_sobol=False, use_antithetic=False,
+                               use_control_variate=False, rng="philox", precision=prec)
+        r = eng.price(2500.0, 2500.0, 1.0, True)
+        assert r["num_steps"] == 250 and r["num_paths_used"] == 20_000_000
+        assert abs(r["price"] - bs) <= 3 * r["std_error"]
+        assert abs(r["price"] - bs) <= 1e-3 * bs
+        assert abs(r["price"] - ref["price"]) <= 3 * math.hypot(r["std_error"], ref["std_error"])
+        assert r["std_error"] == pytest.approx(ref["std_error"] * math.sqrt(50_000 / 20_000_000), rel=0.02)
+        # the genuine control variate (new key) is far tighter and still unbiased
+        assert abs(r["price_cv_spot"] - bs) <= 4 * r["std_error_cv_spot"]
+        assert r["std_error_cv_spot"] < 0.5 * r["std_error"]
+
+
+def test_production_put_call_parity_and_antithetic(golden):
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    p = SVJParams(**golden["params"]["gbm_cfg1"])
+    eng = MonteCarloEngine(p, 4_000_000, 250, seed=7, use_sobol=False, use_antithetic=True, use_control_variate=False,
+                           rng="philox")
+    c = eng.price(2500.0, 2400.0, 1.0, True)
+    q = eng.price(2500.0, 2400.0, 1.0, False)
+    fwd = 2500.0 * math.exp(-p.q) - 2400.0 * math.exp(-p.r)
+    assert abs((c["price"] - q["price"]) - fwd) <= 4 * math.hypot(c["std_error"], q["std_error"])
+    assert abs(c["price"] - O.bs_price(2500.0, 2400.0, 1.0, p.r, p.q, 0.3, True)) <= 4 * c["std_error"]
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_production_svj_within_3se_of_reference(golden, case):
+    """Default SVJ parameters (stochastic vol + jumps): fused Philox engine vs the reference's golden prices at
+    4096 paths (pseudo-random, no CV), using many more paths on our side."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    cases = [c for c in golden["cases"]["price"] if c["params"] == "svj_default" and not c["sobol"] and not c["cv"]]
+    c = cases[case % len(cases)]
+    p = SVJParams(**golden["params"][c["params"]])
+    eng = MonteCarloEngine(p, 2_000_000, c["num_steps"], seed=1, use_sobol=False, use_antithetic=c["anti"],
+                           use_control_variate=False, rng="philox")
+    r = eng.price(c["spot"], c["strike"], c["T"], c["is_call"])
+    assert r["num_steps"] == c["result"]["num_steps"]
+    assert abs(r["price"] - c["result"]["price"]) <= 3 * math.hypot(r["std_error"], c["result"]["std_error"])
+
+
+def test_pseudo_cv_formula_reproduced(golden):
+    """Quirk 2: with antithetic off the reference's 'control variate' returns exactly bs_ref with SE 0; with it
+    on, price = bs_ref + D*mean((b - a)/2).  Same dictionary keys as the reference."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    p = SVJParams(**golden["params"]["gbm_cfg1"])
+    want = [c for c in golden["cases"]["price"] if c["n"] == 50_000 and c["is_call"] and not c["sobol"] and c["cv"]]
+    for c in want:
+        eng = MonteCarloEngine(p, 50_000, 250, seed=42, use_sobol=False, use_antithetic=c["anti"],
+                               use_control_variate=True, rng="philox")
+        r = eng.price(2500.0, 2500.0, 1.0, True)
+        assert set(c["result"]) <= set(r)
+        assert r["bs_ref"] == pytest.approx(c["result"]["bs_ref"], rel=1e-13)
+        if not c["anti"]:
+            assert r["price"] == pytest.approx(r["bs_ref"], rel=1e-12) and r["std_error"] < 1e-9
+        else:
+            assert abs(r["price"] - c["result"]["price"]) <= 3 * math.hypot(r["std_error"], c["result"]["std_error"])
+            assert r["std_error"] == pytest.approx(c["result"]["std_error"], rel=0.05)
+
+
+# ---------------------------------------------------------------------------------------------- rng="reference" (bit parity)
+def test_reference_rng_matches_golden_prices(golden):
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    cases = [c for c in golden["cases"]["price"] if c["n"] <= 5000]
+    assert len(cases) >= 24
+    for c in cases:
+        eng = MonteCarloEngine(SVJParams(**golden["params"][c["params"]]), c["n"], c["num_steps"], c["seed"],
+                               c["sobol"], c["anti"], c["cv"], rng="reference")
+        got = eng.price(c["spot"], c["strike"], c["T"], c["is_call"])
+        assert set(got) == set(c["result"])
+        for k, w in c["result"].items():
+            assert got[k] == pytest.approx(w, rel=1e-9, abs=1e-8), (k, c)
+
+
+def test_reference_rng_price_batch_and_sample_paths(golden, garr):
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    for c in golden["cases"]["price_batch"]:
+        eng = MonteCarloEngine(SVJParams(**golden["params"][c["params"]]), c["n"], c["num_steps"], c["seed"], False,
+                               c["anti"], c["cv"], rng="reference")
+        got = eng.price_batch(c["spot"], np.array(c["strikes"]), c["T"], c["is_call"])
+        for g, w in zip(got, c["result"]):
+            assert set(g) == set(w)
+            for k in w:
+                assert g[k] == pytest.approx(w[k], rel=1e-9, abs=1e-8)
+    eng = MonteCarloEngine(SVJParams(**golden["params"]["svj_default"]), 1000, seed=42, rng="reference")
+    got = eng.get_sample_paths(22500.0, 0.1, 8)
+    np.testing.assert_allclose(got, garr["sample_paths_svj"], rtol=RTOL64)
+
+
+def test_philox_price_batch_keys_and_consistency(golden):
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    c = golden["cases"]["price_batch"][0]
+    p = SVJParams(**golden["params"][c["params"]])
+    eng = MonteCarloEngine(p, 500_000, c["num_steps"], c["seed"], False, c["anti"], c["cv"], rng="philox")
+    got = eng.price_batch(c["spot"], np.array(c["strikes"]), c["T"], c["is_call"])
+    assert len(got) == len(c["result"])
+    for g, w in zip(got, c["result"]):
+        assert set(g) == set(w) and g["strike"] == w["strike"]
+        # raw std errors: 4096 paths in the golden, 500k here
+        assert abs(g["price"] - w["price"]) <= 4 * math.hypot(g["std_error"], w["std_error"]) + 1e-9
+        single = eng.price(c["spot"], w["strike"], c["T"], c["is_call"])
+        assert single["price"] == pytest.approx(g["price"], rel=1e-9)      # same paths whatever the strike count
+
+
+# ---------------------------------------------------------------------------------------------- Greeks
+def test_greeks_engine_reference_rng_matches_golden(golden):
+    from monte_carlo_option_simulator_b200 import GreeksEngine, SVJParams
+    c = [g for g in golden["cases"]["greeks"] if g["n"] <= 4096][0]
+    g = GreeksEngine(SVJParams(**golden["params"][c["params"]]), c["n"], c["num_steps"], c["seed"], rng="reference")
+    args = (c["spot"], c["strike"], c["T"], c["is_call"])
+    for name in ("delta", "vega", "gamma"):
+        got = getattr(g, name)(*args)
+        assert set(got) == set(c[name])
+        for k, w in c[name].items():
+            assert got[k] == pytest.approx(w, rel=1e-7, abs=1e-9), (name, k)
+
+
+def test_greeks_engine_philox_vs_black_scholes(golden):
+    """cfg2: European call/put + all Greeks from ONE fused launch (GBM, kappa = 0), against closed forms."""
+    from monte_carlo_option_simulator_b200 import GreeksEngine, SVJParams
+    from scipy.stats import norm
+    S0 = K = 2500.0
+    T, r, sig = 1.0, 0.065, 0.3
+    p = SVJParams.gbm(sig, r=r, q=0.0)
+    d1 = (math.log(S0 / K) + (r + 0.5 * sig * sig) * T) / (sig * math.sqrt(T))
+    d2 = d1 - sig * math.sqrt(T)
+    bs_gamma = norm.pdf(d1) / (S0 * sig * math.sqrt(T))
+    bs_vega = S0 * norm.pdf(d1) * math.sqrt(T)
+    for is_call in (True, False):
+        g = GreeksEngine(p, 10_000_000, 250, seed=42, rng="philox")
+        d = g.delta(S0, K, T, is_call)
+        bs_d = norm.cdf(d1) if is_call else norm.cdf(d1) - 1
+        assert d["pathwise"] == pytest.approx(bs_d, abs=2e-3) and d["finite_diff"] == pytest.approx(bs_d, abs=2e-3)
+        assert d["diff_pct"] < 0.5
+        assert g.gamma(S0, K, T, is_call)["gamma"] == pytest.approx(bs_gamma, rel=0.03)
+        v = g.vega(S0, K, T, is_call)
+        assert v["vega_per_vol_point"] == pytest.approx(bs_vega, rel=0.01)
+        assert v["pathwise_vega_sigma"] == pytest.approx(bs_vega, rel=0.01)
+        bs_rho = K * T * math.exp(-r * T) * (norm.cdf(d2) if is_call else -norm.cdf(-d2))
+        assert g.rho(S0, K, T, is_call)["rho_crn"] == pytest.approx(bs_rho, rel=0.01)
+
+
+# ---------------------------------------------------------------------------------------------- path store
+@pytest.mark.parametrize("mode", ["gbm", "detvar", "heston", "svj"])
+@pytest.mark.parametrize("n,steps", [(70, 250), (33, 31), (5, 50), (64, 96)])
+def test_generate_paths_identical_draws(H, L, golden, mode, n, steps):
+    p, stream = _mode_params(golden, mode)
+    seed, off, S0, T = 4, 1000, 2500.0, 1.0
+    Z = _draws(H, L, seed, n, steps, stream, off)
+    want = O._sim(p, S0, T, *Z, steps, record=True)[2]
+    got = H.generate_paths(p, S0, T, steps, n, seed, L.FP64, np.float64, off)
+    assert got.shape == (n, steps + 1) and np.all(got[:, 0] == S0)
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    got32 = H.generate_paths(p, S0, T, steps, n, seed, 0, np.float32, off)
+    assert got32.dtype == np.float32
+    np.testing.assert_allclose(got32, want, rtol=RTOL32)
+    padded = H.generate_paths(p, S0, T, steps, n, seed, L.FP64, np.float64, off, ld=steps + 4)
+    np.testing.assert_array_equal(padded, got)
+
+
+def test_generate_paths_terminal_column_equals_terminal_mode(H, L, golden):
+    p, _ = _mode_params(golden, "svj")
+    paths = H.generate_paths(p, 100.0, 0.5, 77, 1000, 3, L.FP64, np.float64)
+    S = H.simulate_terminal(p, 100.0, 0.5, 77, 1000, 3, L.FP64, np.float64)[0]
+    np.testing.assert_allclose(paths[:, -1], S, rtol=1e-13)
+
+
+def test_sample_paths_philox_shape(golden):
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    eng = MonteCarloEngine(SVJParams(**golden["params"]["svj_default"]), 1000, seed=42, rng="philox")
+    sp = eng.get_sample_paths(22500.0, 0.1, 8)
+    assert sp.shape == (8, 51) and sp.dtype == np.float64 and np.all(sp[:, 0] == 22500.0) and np.all(sp > 0)
+
+
+# ---------------------------------------------------------------------------------------------- a10: risk metrics
+def test_risk_metrics_golden(H, golden, garr):
+    from monte_carlo_option_simulator_b200 import compute_risk_metrics
+    for c in golden["cases"]["risk"]:
+        got = compute_risk_metrics(garr[f"risk_{c['name']}"], c["confidence"], handle=H)
+        want = unnan(c["result"])
+        assert set(got) == set(want)
+        for k, w in want.items():
+            if np.isnan(w):
+                assert np.isnan(got[k]), (c["name"], k)
+            else:
+                assert got[k] == pytest.approx(w, rel=1e-11, abs=1e-13), (c["name"], k)
+
+
+def test_risk_metrics_large_and_fp32(H):
+    g = np.random.default_rng(0)
+    x = g.standard_t(4, size=4_000_000) * 0.01
+    got = H.risk_metrics(x, 0.99)
+    want = O.risk_metrics(x, 0.99)
+    for k, v in zip(("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std"), got):
+        assert v == pytest.approx(want[k], rel=1e-9, abs=1e-12), k
+    x32 = x.astype(np.float32)
+    got32 = H.risk_metrics(x32, 0.95)
+    want32 = O.risk_metrics(x32.astype(np.float64), 0.95)
+    assert got32[0] == pytest.approx(want32["var"], rel=1e-12) and got32[1] == pytest.approx(want32["cvar"], rel=1e-9)
+
+
+def test_risk_metrics_edge_cases(H, L):
+    from monte_carlo_option_simulator_b200 import compute_risk_metrics
+    with pytest.raises(IndexError):
+        compute_risk_metrics(np.array([]))
+    one = compute_risk_metrics(np.array([-0.5]), handle=H)
+    assert one["var"] == 0.5 and one["cvar"] == 0.5 and math.isnan(one["tail_index"]) and one["std"] == 0.0
+    same = compute_risk_metrics(np.full(1000, -1.0), handle=H)
+    want = O.risk_metrics(np.full(1000, -1.0))
+    assert same["var"] == want["var"] and same["cvar"] == pytest.approx(want["cvar"]) and math.isnan(same["tail_index"])
+
+
+def test_cfg4_terminal_pnl_var(H, L, golden):
+    """BASELINE config 4 reduced: terminal P&L of a short-dated option, device select vs oracle sort."""
+    p, _ = _mode_params(golden, "gbm")
+    S = H.simulate_terminal(p, 2500.0, 1.0, 250, 300_000, 42, 0, np.float64)[0]
+    pnl = math.exp(-p.r) * np.maximum(S - 2500.0, 0.0) - 374.07
+    got = H.risk_metrics(pnl, 0.99)
+    want = O.risk_metrics(pnl, 0.99)
+    for k, v in zip(("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std"), got):
+        if math.isnan(want[k]):
+            assert math.isnan(v)
+        else:
+            assert v == pytest.approx(want[k], rel=1e-9, abs=1e-9), k
+
+
+# ---------------------------------------------------------------------------------------------- patched reference callers
+def test_full_size_linearity_property(H, L, golden):
+    """BASELINE config 2 size (1e7 x 250): sums over two halves of the path range add up to the whole-range sums
+    (the property multi-GPU sharding relies on), and sum_s/n hits the forward within 4 standard errors."""
+    p, _ = _mode_params(golden, "gbm")
+    n = 10_000_000
+    whole = H.price_european(p, 2500.0, 1.0, 250, n, 42, [2500.0], True, 0)[0]
+    a = H.price_european(p, 2500.0, 1.0, 250, n // 2, 42, [2500.0], True, 0)[0]
+    b = H.price_european(p, 2500.0, 1.0, 250, n - n // 2, 42, [2500.0], True, 0, path_offset=n // 2)[0]
+    np.testing.assert_allclose(a + b, whole, rtol=1e-11)
+    mean_s = whole[L.SUMS_FIELDS.index("sum_s")] / n
+    sd_s = math.sqrt(whole[L.SUMS_FIELDS.index("sum_ss")] / n - mean_s ** 2)
+    assert abs(mean_s - 2500.0 * math.exp(p.r - p.q)) <= 4 * sd_s / math.sqrt(n)
