@@ -42,8 +42,8 @@ T = 1.0
 WORKLOAD = ("BASELINE cfg2: European call + Delta/Gamma/Vega/Rho accumulators, one fused launch, "
             "S0=K=2500 r=6.5% sigma=30% T=1y, 250 steps, 10M paths per GPU")
 
-# fallback instruction mix per 8 path-steps of k_european<GBM, no anti, greeks, fp32> (tools/sass_mix.py)
-FALLBACK_MIX = {"heavy": 36, "alu": 54, "fp32": 20, "xu": 16, "uni": 7, "lsu": 2, "ctl": 1, "total": 136, "philox_calls": 2}
+# fallback instruction mix per Philox call (8 path-steps) of k_european<GBM, no anti, greeks, fp32> (tools/sass_mix.py)
+FALLBACK_MIX = {"heavy": 18, "alu": 33, "fp32": 20, "xu": 16, "uni": 2, "lsu": 2, "ctl": 1, "total": 92, "imad_wide": 17, "philox_calls": 1}
 
 
 def gbm_params():
@@ -151,36 +151,47 @@ def instruction_roofline(h, achieved_path_steps_per_gpu, sm_mhz):
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import sass_mix
-        mixes = sass_mix.mix("k_europeanILi0ELb0ELb1Ef")
+        mixes = sass_mix.mix("k_europeanILi0ELb0ELb1EfLb1E")
         mix = list(mixes.values())[0]
         src = "cuobjdump -sass of libb200mc.so (tools/sass_mix.py)"
         if not mix.get("xu"):
             raise RuntimeError("empty mix")
     except Exception as e:  # noqa: BLE001
         mix, src = dict(FALLBACK_MIX), f"fallback constants ({type(e).__name__})"
-    steps_per_iter = 4.0 * mix.get("philox_calls", 2)
-    per_step = {k: mix.get(k, 0) / steps_per_iter for k in ("heavy", "alu", "fp32", "xu", "uni", "lsu", "ctl", "total")}
+    steps_per_iter = 8.0 * mix.get("philox_calls", 1)
+    per_step = {k: mix.get(k, 0) / steps_per_iter for k in ("heavy", "alu", "fp32", "xu", "uni", "lsu", "ctl", "total", "imad_wide")}
     rates = {"ffma": h.microbench(0), "imad_wide": h.microbench(1), "lop3": h.microbench(2),
              "mufu_ex2": h.microbench(3), "mufu_sin": h.microbench(4), "mufu_lg2": h.microbench(9),
              "mufu_sqrt": h.microbench(10), "ffma_lop3_pairs": h.microbench(11),
              "philox_calls": h.microbench(6), "philox_bm_calls": h.microbench(7)}
-    issue = 2.0 * rates["ffma_lop3_pairs"]                 # thread-instructions/s with two pipes fed every cycle
     xu = min(rates["mufu_ex2"], rates["mufu_sin"], rates["mufu_lg2"], rates["mufu_sqrt"])
-    bounds = {
-        "xu": xu / per_step["xu"] if per_step["xu"] else float("inf"),
-        "alu": rates["lop3"] / per_step["alu"] if per_step["alu"] else float("inf"),
-        "fma_heavy": rates["imad_wide"] / per_step["heavy"] if per_step["heavy"] else float("inf"),
-        "issue": issue / per_step["total"] if per_step["total"] else float("inf"),
-    }
-    binding = min(bounds, key=bounds.get)
-    peak = bounds[binding]
+
+    def bounds_for(n_wide, n_other, n_alu, n_xu):
+        # serial-issue model measured by tools/pipe_probe.py: an IMAD.WIDE holds the sub-partition's issue port for
+        # 1/R_wide (4 cycles), every other instruction for one issue slot (1/R_ffma); XU and ALU work overlaps.
+        return {"issue": 1.0 / (n_wide / rates["imad_wide"] + n_other / rates["ffma"]),
+                "xu": xu / n_xu if n_xu else float("inf"),
+                "alu": rates["lop3"] / n_alu if n_alu else float("inf")}
+
+    # ALGORITHMIC cost per path-step: one Philox4x32-10 call per 8 steps with the first round's
+    # multiplies loop-invariant/uniform = 17 IMAD.WIDE + 20 LOP3; per Box-Muller pair 2 ALU + 3 FP32 + 4 MUFU + 2 FP32 to
+    # scale and accumulate; ~4 loop instructions per call.
+    algo = {"imad_wide": 17 / 8, "alu": (20 + 4 * 2) / 8, "fp32": 4 * 5 / 8, "xu": 2.0, "loop": 4 / 8}
+    algo_other = algo["alu"] + algo["fp32"] + algo["xu"] + algo["loop"]
+    b_algo = bounds_for(algo["imad_wide"], algo_other, algo["alu"], algo["xu"])
+    b_sass = bounds_for(per_step["imad_wide"], per_step["total"] - per_step["imad_wide"], per_step["alu"], per_step["xu"])
+    binding = min(b_algo, key=b_algo.get)
+    peak = b_algo[binding]
     return {"bound": binding, "achieved": achieved_path_steps_per_gpu, "peak": peak, "unit": UNIT,
             "frac": achieved_path_steps_per_gpu / peak, "traffic": None,
-            "kernel": "k_european<GBM, fp32, greeks>", "kind": "instruction roofline (kernel moves no data)",
-            "per_path_step_instructions": per_step, "mix_source": src,
-            "measured_rates_ops_per_s": rates, "pipe_bounds_path_steps_per_s": bounds,
+            "kernel": "k_european<GBM, fp32, greeks>", "kind": "instruction roofline (the kernel moves no data): "
+            "algorithmic instructions per path-step over issue rates measured in this run",
+            "algorithmic_per_path_step": algo, "pipe_bounds_algorithmic": b_algo,
+            "sass_per_path_step": per_step, "pipe_bounds_sass_mix": b_sass,
+            "frac_of_sass_mix_bound": achieved_path_steps_per_gpu / min(b_sass.values()), "mix_source": src,
+            "measured_rates_ops_per_s": rates,
             "peak_source": "b200mc_microbench on this device in this run (not in MEASURED_PEAKS.json)",
-            "rng_only_path_steps_per_s": 4.0 * rates["philox_bm_calls"]}
+            "rng_only_path_steps_per_s": 8.0 * rates["philox_bm_calls"]}
 
 
 def hbm_roofline(h, torch, n_paths=1_000_000, reps=3):

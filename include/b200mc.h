@@ -21,13 +21,17 @@
  *
  * Random numbers (fused modes): counter-based Philox4x32-10, key = (seed_lo, seed_hi),
  * counter = (path_lo, path_hi, block, stream) with `path` the GLOBAL path index (path_offset + i), so a
- * path draws the same numbers whatever the launch geometry or the number of GPUs.  Streams:
- *   B200MC_STREAM_GBM    block j -> 4 normals for steps 4j..4j+3: (z0,z1)=BM(w0,w1), (z2,z3)=BM(w2,w3)
- *   B200MC_STREAM_HESTON block j -> steps 2j, 2j+1: (Z1,Z2)=BM(w0,w1) for 2j, BM(w2,w3) for 2j+1
- *   B200MC_STREAM_SVJ    block j -> step j: (Z1,Z2)=BM(w0,w1), U_jump=(w2+0.5)/2^32, Z_jump_size=ICDF(w3)
- * BM(wa,wb): u1 = 2 - f(wa) in (0,1], f(w) = float with mantissa w & 0x7fffff in [1,2);  R = sqrt(-2 ln u1);
- * angle = 2 pi f(wb);  pair = (R cos, R sin).  b200mc_dump_normals returns exactly the values the fused
- * kernels use, so the reference (or the oracle) can be fed identical draws.
+ * path draws the same numbers whatever the launch geometry or the number of GPUs.  Every 32-bit output word w
+ * yields one Box-Muller pair BM(w) = (R cos a, R sin a):  u1 = 2 - f(w & 0x7fffff) in (0,1],  R = sqrt(-2 ln u1),
+ * a = 2 pi f(w >> 9) - 3 pi,  f(m) = the float in [1,2) with mantissa m  (fp32, MUFU lg2/sqrt/sin/cos).  Streams:
+ *   B200MC_STREAM_GBM    block j -> steps 8j..8j+7: word i gives the normals of steps 8j+2i and 8j+2i+1
+ *   B200MC_STREAM_HESTON block j -> steps 4j..4j+3: word i gives (Z1, Z2) of step 4j+i
+ *   B200MC_STREAM_SVJ    block j -> steps 2j, 2j+1: (w0 -> (Z1,Z2), w1 -> U_jump), (w2 -> (Z1,Z2), w3 -> U_jump);
+ *                        U_jump = (w + 0.5) / 2^32
+ *   B200MC_STREAM_JUMP   block s -> word 0 gives Z_jump_size of step s = normcdfinv(((w >> 8) + 0.5) / 2^24)
+ *                        (internal to the SVJ mode; drawn only when the jump fires)
+ * b200mc_dump_normals returns exactly the values the fused kernels use, so the reference (or the oracle) can be
+ * fed identical draws.
  */
 #ifndef B200MC_H
 #define B200MC_H
@@ -57,6 +61,7 @@ extern "C" {
 #define B200MC_STREAM_GBM    0u
 #define B200MC_STREAM_HESTON 1u
 #define B200MC_STREAM_SVJ    2u
+#define B200MC_STREAM_JUMP   3u
 
 /* which array b200mc_dump_normals returns */
 #define B200MC_Z1         0
@@ -210,6 +215,9 @@ int b200mc_timer_end(b200mc_handle *h, float *elapsed_ms);
  * Box-Muller pairs, 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 pairs.  *ops_per_s: thread-level operations per
  * second over the whole device (CUDA events, best of 3 after a warm-up launch). */
 int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s);
+/* Mixed probe: per thread-iteration counts[0] IMAD.WIDE + counts[1] LOP3 + counts[2] MUFU + counts[3] FFMA (a fixed
+ * table indexed by combo); *iters_per_s = thread-iterations per second.  Shows which pipes overlap. */
+int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, double *iters_per_s, int counts[4]);
 
 #ifdef __cplusplus
 }

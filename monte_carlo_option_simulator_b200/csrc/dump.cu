@@ -4,7 +4,8 @@
 // b200mc_dump_normals returns, as float64 [n_paths, n_steps], exactly the values the fused kernels consume:
 //   Z1 / Z2        BM_SCALE * (double)raw   with raw the fp32 Box-Muller output of philox.cuh
 //   Z_jump         (w + 0.5) / 2^32                                   (SVJ stream; 1.0 = "never jumps" elsewhere)
-//   Z_jump_size    (double)normcdfinvf(((w >> 8) + 0.5) / 2^24)       (SVJ stream; 0 elsewhere)
+//   Z_jump_size    (double)normcdfinvf(((w >> 8) + 0.5) / 2^24)       (SVJ stream, every step -- the fused kernel
+//                  draws it only when the jump fires, from the same counter; 0 elsewhere)
 // Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0).
 #include "common.cuh"
 
@@ -25,33 +26,43 @@ __global__ void k_dump_philox(PhiloxKey key, uint64_t path0, int64_t n_paths, in
 __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_steps, uint32_t stream, int which,
                                double *__restrict__ out)
 {
-    const int per = stream == B200MC_STREAM_GBM ? 4 : (stream == B200MC_STREAM_HESTON ? 2 : 1);
+    const int per = stream == B200MC_STREAM_GBM ? 8 : (stream == B200MC_STREAM_HESTON ? 4 : 2);
     const int n_blocks = (n_steps + per - 1) / per;
     const int64_t total = n_paths * n_blocks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pi = i / n_blocks;
         const uint64_t path = path0 + (uint64_t)pi;
+        const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
         const int blk = (int)(i % n_blocks);
-        const U4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)blk, stream, key);
-        const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
-        double vals[4];
-        int nv = per;
+        const U4 w = philox4x32_10(c0, c1, (uint32_t)blk, stream, key);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        const double neutral = which == B200MC_ZJUMP_U ? 1.0 : 0.0;
+        double vals[8];
         if (stream == B200MC_STREAM_GBM) {
-            const float r[4] = {p.rc, p.rs, q.rc, q.rs};
-            for (int t = 0; t < 4; ++t)
-                vals[t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)r[t] : (which == B200MC_ZJUMP_U ? 1.0 : 0.0);
+            for (int t = 0; t < 4; ++t) {
+                const BM2 b = box_muller_word(ww[t]);
+                vals[2 * t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rc : neutral;
+                vals[2 * t + 1] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rs : neutral;
+            }
         } else if (stream == B200MC_STREAM_HESTON) {
-            const float z1[2] = {p.rc, q.rc}, z2[2] = {p.rs, q.rs};
-            for (int t = 0; t < 2; ++t)
-                vals[t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)z1[t]
-                        : which == B200MC_Z2 ? B200MC_BM_SCALE * (double)z2[t]
-                        : which == B200MC_ZJUMP_U ? 1.0 : 0.0;
+            for (int t = 0; t < 4; ++t) {
+                const BM2 b = box_muller_word(ww[t]);
+                vals[t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rc
+                        : which == B200MC_Z2 ? B200MC_BM_SCALE * (double)b.rs : neutral;
+            }
         } else {
-            vals[0] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)p.rc
-                    : which == B200MC_Z2 ? B200MC_BM_SCALE * (double)p.rs
-                    : which == B200MC_ZJUMP_U ? jump_uniform(w.z) : (double)jump_size_normal(w.w);
+            for (int t = 0; t < 2; ++t) {
+                const BM2 b = box_muller_word(ww[2 * t]);
+                if (which == B200MC_Z1) vals[t] = B200MC_BM_SCALE * (double)b.rc;
+                else if (which == B200MC_Z2) vals[t] = B200MC_BM_SCALE * (double)b.rs;
+                else if (which == B200MC_ZJUMP_U) vals[t] = jump_uniform(ww[2 * t + 1]);
+                else {
+                    const U4 uj = philox4x32_10(c0, c1, (uint32_t)(blk * 2 + t), B200MC_STREAM_JUMP, key);
+                    vals[t] = (double)jump_size_normal(uj.x);
+                }
+            }
         }
-        for (int t = 0; t < nv; ++t) {
+        for (int t = 0; t < per; ++t) {
             const int s = blk * per + t;
             if (s < n_steps) out[(size_t)pi * n_steps + s] = vals[t];
         }

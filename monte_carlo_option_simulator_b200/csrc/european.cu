@@ -36,7 +36,44 @@ template <typename R> __device__ __forceinline__ R payoff(R s, R k, bool call)
     return call ? rmax(s - k, (R)0) : rmax(k - s, (R)0);
 }
 
+// Adds one path's payoff terms for strike K into the fp64 accumulators (order = b200mc_sums after .n).
 template <int MODE, bool ANTI, bool GREEKS, typename R>
+__device__ __forceinline__ void accumulate(double (&acc)[NACC], const EuroArgs &a, R K, R S0, bool call, R sa, R sb,
+                                           R s_up, R s_dn, R sumz)
+{
+    const double da = (double)payoff<R>(sa, K, call);
+    double db = 0.0, s_avg = (double)sa, pay = da;
+    if constexpr (ANTI) {
+        db = (double)payoff<R>(sb, K, call);
+        s_avg = 0.5 * ((double)sa + (double)sb);
+        pay = 0.5 * (da + db);
+    }
+    acc[0] += da;
+    acc[1] += db;
+    acc[2] = fma(da, da, acc[2]);
+    acc[3] = fma(db, db, acc[3]);
+    acc[4] = fma(da, db, acc[4]);
+    acc[5] += s_avg;
+    acc[6] = fma(s_avg, s_avg, acc[6]);
+    acc[7] = fma(pay, s_avg, acc[7]);
+    if constexpr (GREEKS) {
+        const bool itm = call ? (sa > K) : (sa < K);                       // greeks.py:72,75
+        if (itm) acc[8] += (double)(sa / S0);
+        acc[9] += (double)payoff<R>(sa * (R)a.up_mul, K, call);
+        acc[10] += (double)payoff<R>(sa * (R)a.dn_mul, K, call);
+        acc[11] += (double)payoff<R>(s_up, K, call);
+        acc[12] += (double)payoff<R>(s_dn, K, call);
+        acc[13] += (double)payoff<R>(sa * (R)a.rup_mul, K, call);
+        acc[14] += (double)payoff<R>(sa * (R)a.rdn_mul, K, call);
+        if constexpr (MODE == MODE_GBM) {
+            if (itm) acc[15] += (double)sa * ((double)sumz * a.w_scale - a.sigmaT);
+        }
+    }
+}
+
+// SINGLE = exactly one strike: every thread finishes its own paths, no shared-memory staging and no block barrier
+// inside the path loop.  Otherwise phase A / phase B as described at the top of the file.
+template <int MODE, bool ANTI, bool GREEKS, typename R, bool SINGLE>
 __global__ void __launch_bounds__(EU_THREADS)
 k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strikes_g,
            const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
@@ -47,9 +84,9 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *red = reinterpret_cast<double *>(smem_raw);                   // [256]
     double *strikes = red + EU_THREADS;                                   // [n_strikes]
-    R *sT = reinterpret_cast<R *>(strikes + a.n_strikes);                 // [NS][256]
-    R *sW = sT + NS * EU_THREADS;                                         // [256]  sum of raw z
-    R *wtab = sW + EU_THREADS;                                            // [3][wld] (DETVAR)
+    R *sT = reinterpret_cast<R *>(strikes + a.n_strikes);                 // [NS][256]   (not SINGLE)
+    R *sW = sT + (SINGLE ? 0 : NS * EU_THREADS);                          // [256]  sum of raw z (not SINGLE)
+    R *wtab = sW + (SINGLE ? 0 : EU_THREADS);                             // [3][wld] (DETVAR)
 
     const int tid = threadIdx.x;
     for (int i = tid; i < a.n_strikes; i += EU_THREADS) strikes[i] = strikes_g[i];
@@ -69,56 +106,45 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
 #pragma unroll
     for (int j = 0; j < NACC; ++j) acc[j] = 0.0;
 
-    for (int64_t base = (int64_t)blockIdx.x * EU_THREADS; base < a.n_paths; base += (int64_t)gridDim.x * EU_THREADS) {
-        // ---- phase A: one path per thread ---------------------------------------------------------------
-        const int64_t i = base + tid;
-        if (i < a.n_paths) {
+    if constexpr (SINGLE) {
+        for (int64_t i = (int64_t)blockIdx.x * EU_THREADS + tid; i < a.n_paths; i += (int64_t)gridDim.x * EU_THREADS) {
             R xT[NS], vT[NS], sumz;
             simulate_path<MODE, ANTI, GREEKS, R>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT, vT,
                                                  sumz, NoRec());
+            R sv[NS];
 #pragma unroll
-            for (int k = 0; k < NS; ++k) sT[k * EU_THREADS + tid] = S0 * rexp(xT[k]);
-            if constexpr (GREEKS && MODE == MODE_GBM) sW[tid] = sumz;
+            for (int k = 0; k < NS; ++k) sv[k] = S0 * rexp(xT[k]);
+            accumulate<MODE, ANTI, GREEKS, R>(acc, a, K, S0, call, sv[0], ANTI ? sv[NS > 1 ? 1 : 0] : (R)0,
+                                              GREEKS ? sv[L::UP_IDX < NS ? L::UP_IDX : 0] : (R)0,
+                                              GREEKS ? sv[L::DN_IDX < NS ? L::DN_IDX : 0] : (R)0, sumz);
         }
-        __syncthreads();
-        // ---- phase B: strike-major payoff sums -----------------------------------------------------------
-        const int64_t left = a.n_paths - base;
-        const int nvalid = left < EU_THREADS ? (int)left : EU_THREADS;
-        if (worker) {
-            for (int p = my_slice; p < nvalid; p += nslices) {
-                const R sa = sT[p];
-                const double da = (double)payoff<R>(sa, K, call);
-                double db = 0.0, s_avg = (double)sa, pay = da;
-                if constexpr (ANTI) {
-                    const R sb = sT[EU_THREADS + p];
-                    db = (double)payoff<R>(sb, K, call);
-                    s_avg = 0.5 * ((double)sa + (double)sb);
-                    pay = 0.5 * (da + db);
-                }
-                acc[0] += da;
-                acc[1] += db;
-                acc[2] = fma(da, da, acc[2]);
-                acc[3] = fma(db, db, acc[3]);
-                acc[4] = fma(da, db, acc[4]);
-                acc[5] += s_avg;
-                acc[6] = fma(s_avg, s_avg, acc[6]);
-                acc[7] = fma(pay, s_avg, acc[7]);
-                if constexpr (GREEKS) {
-                    const bool itm = call ? (sa > K) : (sa < K);                       // greeks.py:72,75
-                    if (itm) acc[8] += (double)(sa / S0);
-                    acc[9] += (double)payoff<R>(sa * (R)a.up_mul, K, call);
-                    acc[10] += (double)payoff<R>(sa * (R)a.dn_mul, K, call);
-                    acc[11] += (double)payoff<R>(sT[L::UP_IDX * EU_THREADS + p], K, call);
-                    acc[12] += (double)payoff<R>(sT[L::DN_IDX * EU_THREADS + p], K, call);
-                    acc[13] += (double)payoff<R>(sa * (R)a.rup_mul, K, call);
-                    acc[14] += (double)payoff<R>(sa * (R)a.rdn_mul, K, call);
-                    if constexpr (MODE == MODE_GBM) {
-                        if (itm) acc[15] += (double)sa * ((double)sW[p] * a.w_scale - a.sigmaT);
-                    }
+    } else {
+        for (int64_t base = (int64_t)blockIdx.x * EU_THREADS; base < a.n_paths;
+             base += (int64_t)gridDim.x * EU_THREADS) {
+            // ---- phase A: one path per thread ------------------------------------------------------------
+            const int64_t i = base + tid;
+            if (i < a.n_paths) {
+                R xT[NS], vT[NS], sumz;
+                simulate_path<MODE, ANTI, GREEKS, R>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT,
+                                                     vT, sumz, NoRec());
+#pragma unroll
+                for (int k = 0; k < NS; ++k) sT[k * EU_THREADS + tid] = S0 * rexp(xT[k]);
+                if constexpr (GREEKS && MODE == MODE_GBM) sW[tid] = sumz;
+            }
+            __syncthreads();
+            // ---- phase B: strike-major payoff sums --------------------------------------------------------
+            const int64_t left = a.n_paths - base;
+            const int nvalid = left < EU_THREADS ? (int)left : EU_THREADS;
+            if (worker) {
+                for (int p = my_slice; p < nvalid; p += nslices) {
+                    accumulate<MODE, ANTI, GREEKS, R>(acc, a, K, S0, call, sT[p], ANTI ? sT[EU_THREADS + p] : (R)0,
+                                                      GREEKS ? sT[L::UP_IDX * EU_THREADS + p] : (R)0,
+                                                      GREEKS ? sT[L::DN_IDX * EU_THREADS + p] : (R)0,
+                                                      (GREEKS && MODE == MODE_GBM) ? sW[p] : (R)0);
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- fold slices -> one partial per (block, strike) ---------------------------------------------------
@@ -154,18 +180,22 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
 
 using EuroKernel = void (*)(const EuroArgs, const double *, const double *, double *, unsigned int *, double *);
 
-template <int MODE, typename R> static EuroKernel pick2(bool anti, bool greeks)
+template <int MODE, typename R, bool SINGLE> static EuroKernel pick3(bool anti, bool greeks)
 {
-    if (anti) return greeks ? k_european<MODE, true, true, R> : k_european<MODE, true, false, R>;
-    return greeks ? k_european<MODE, false, true, R> : k_european<MODE, false, false, R>;
+    if (anti) return greeks ? k_european<MODE, true, true, R, SINGLE> : k_european<MODE, true, false, R, SINGLE>;
+    return greeks ? k_european<MODE, false, true, R, SINGLE> : k_european<MODE, false, false, R, SINGLE>;
 }
-template <typename R> static EuroKernel pick1(int mode, bool anti, bool greeks)
+template <int MODE, typename R> static EuroKernel pick2(bool anti, bool greeks, bool single)
+{
+    return single ? pick3<MODE, R, true>(anti, greeks) : pick3<MODE, R, false>(anti, greeks);
+}
+template <typename R> static EuroKernel pick1(int mode, bool anti, bool greeks, bool single)
 {
     switch (mode) {
-    case MODE_GBM: return pick2<MODE_GBM, R>(anti, greeks);
-    case MODE_DETVAR: return pick2<MODE_DETVAR, R>(anti, greeks);
-    case MODE_HESTON: return pick2<MODE_HESTON, R>(anti, greeks);
-    default: return pick2<MODE_SVJ, R>(anti, greeks);
+    case MODE_GBM: return pick2<MODE_GBM, R>(anti, greeks, single);
+    case MODE_DETVAR: return pick2<MODE_DETVAR, R>(anti, greeks, single);
+    case MODE_HESTON: return pick2<MODE_HESTON, R>(anti, greeks, single);
+    default: return pick2<MODE_SVJ, R>(anti, greeks, single);
     }
 }
 
@@ -200,10 +230,11 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
     a.sigmaT = sqrt(p->v0 > 0.0 ? p->v0 : 0.0) * T;
     a.w_scale = pr.m.sqrt_dt_s;
 
-    EuroKernel kern = fp64 ? pick1<double>(pr.mode, anti, greeks) : pick1<float>(pr.mode, anti, greeks);
+    const bool single = n_strikes == 1;
+    EuroKernel kern = fp64 ? pick1<double>(pr.mode, anti, greeks, single) : pick1<float>(pr.mode, anti, greeks, single);
     const int ns = 1 + (anti ? 1 : 0) + (greeks ? 2 : 0);
     const size_t rsz = fp64 ? 8 : 4;
-    size_t smem = (size_t)(EU_THREADS + n_strikes) * 8 + (size_t)(ns + 1) * EU_THREADS * rsz;
+    size_t smem = (size_t)(EU_THREADS + n_strikes) * 8 + (single ? 0 : (size_t)(ns + 1) * EU_THREADS * rsz);
     if (pr.mode == MODE_DETVAR) smem += (size_t)3 * pr.wld * rsz;
     if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
     B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -106,12 +106,41 @@ __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, co
             const U4 w = philox4x32_10(t, seed, (uint32_t)i, 0u, key);
             if constexpr (WHICH == MB_PHILOX) x ^= w.x ^ w.y ^ w.z ^ w.w;
             else {
-                const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
-                s += p.rc; s += p.rs; s += q.rc; s += q.rs;
+                const BM2 b0 = box_muller_word(w.x), b1 = box_muller_word(w.y), b2 = box_muller_word(w.z),
+                          b3 = box_muller_word(w.w);
+                s += b0.rc; s += b0.rs; s += b1.rc; s += b1.rs; s += b2.rc; s += b2.rs; s += b3.rc; s += b3.rs;
             }
         }
         if (s == 123.456f || x == 0x12345u) sink[0] = t;
     }
+}
+
+// Mixed probe: per iteration NW IMAD.WIDE + NL LOP3 + NM MUFU + NF FFMA over independent chains -- shows which pipes
+// overlap and which share a dispatch port (the fused kernel's hot loop is such a mix).
+template <int NW, int NL, int NM, int NF>
+__global__ void __launch_bounds__(256) k_mix(int iters, uint32_t seed, uint32_t *sink)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w[8], l[8];
+    float m[8], f[8];
+    const float b = __uint_as_float(0x3f800001u + (seed & 1)), c = __uint_as_float(0x33800000u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { w[k] = t * 8u + k + seed; l[k] = t + k; m[k] = 0.5f + 1e-3f * (float)((t + k) & 255); f[k] = (float)(t + k); }
+    for (int i = 0; i < iters; ++i) {
+        constexpr int NMAX = NW > NL ? (NW > NM ? (NW > NF ? NW : NF) : (NM > NF ? NM : NF)) : (NL > NM ? (NL > NF ? NL : NF) : (NM > NF ? NM : NF));
+#pragma unroll
+        for (int k = 0; k < NMAX; ++k) {
+            if (k < NW) { uint64_t p; asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(p) : "r"(w[k & 7])); w[k & 7] = (uint32_t)(p >> 32); }
+            if (k < NL) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(l[k & 7]) : "r"(seed + i), "r"(~seed));
+            if (k < NM) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(m[k & 7]));
+            if (k < NF) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[k & 7]) : "f"(b), "f"(c));
+        }
+    }
+    float s = 0.f;
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += m[k] + f[k]; x ^= w[k] ^ l[k]; }
+    if (s == 123.456f && x == 77u) sink[0] = t;
 }
 
 template <int W> static void mb_launch(int grid, int iters, uint32_t seed, const PhiloxKey &key, uint32_t *sink, cudaStream_t st)
@@ -122,8 +151,53 @@ template <int W> static void mb_launch(int grid, int iters, uint32_t seed, const
 } // namespace b200mc
 using namespace b200mc;
 
-// which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox + 2 Box-Muller
-// pairs (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs).
+// Mixed probe: combo selects (NW, NL, NM, NF) from a fixed table; *iters_per_s = thread-iterations per second.
+extern "C" int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, double *iters_per_s, int counts[4])
+{
+    if (!h || !iters_per_s || !counts) return fail(h, B200MC_EINVAL, "NULL argument");
+    if (iters <= 0) return fail(h, B200MC_EINVAL, "iters must be positive");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const int grid = h->sm_count * 8;
+    uint32_t *sink = (uint32_t *)h->d_counter + 4;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        B200MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+#define MIXCASE(id, a, b, c, d) case id: k_mix<a, b, c, d><<<grid, 256, 0, h->stream>>>(iters, rep, sink); counts[0] = a; counts[1] = b; counts[2] = c; counts[3] = d; break;
+        switch (combo) {
+        MIXCASE(0, 8, 0, 0, 0)
+        MIXCASE(1, 0, 8, 0, 0)
+        MIXCASE(2, 0, 0, 8, 0)
+        MIXCASE(3, 0, 0, 0, 8)
+        MIXCASE(4, 8, 0, 4, 0)
+        MIXCASE(5, 8, 12, 0, 0)
+        MIXCASE(6, 0, 12, 4, 0)
+        MIXCASE(7, 0, 0, 4, 8)
+        MIXCASE(8, 8, 0, 0, 8)
+        MIXCASE(9, 8, 12, 4, 4)
+        MIXCASE(10, 8, 12, 4, 0)
+        MIXCASE(11, 8, 0, 4, 4)
+        MIXCASE(12, 8, 12, 2, 4)
+        MIXCASE(13, 6, 12, 4, 4)
+        MIXCASE(14, 8, 16, 4, 8)
+        MIXCASE(15, 0, 16, 0, 16)
+        MIXCASE(16, 4, 8, 4, 4)
+        default: return fail(h, B200MC_EINVAL, "unknown mix combo");
+        }
+#undef MIXCASE
+        B200MC_CUDA(h, cudaGetLastError());
+        B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        B200MC_CUDA(h, cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        B200MC_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0 && ms < best) best = ms;
+        h->launches += 1;
+    }
+    *iters_per_s = (double)grid * 256.0 * (double)iters / ((double)best * 1e-3);
+    return 0;
+}
+
+// which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox + 4 Box-Muller
+// pairs = 8 normals (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs).
 // *ops_per_s = thread-level operations per second over the whole device (kernel time by CUDA events, best of 3).
 extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s)
 {

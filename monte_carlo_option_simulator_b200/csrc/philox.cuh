@@ -5,8 +5,10 @@
 // part of the ABI contract (include/b200mc.h, "Random numbers") because b200mc_dump_normals must return
 // the very same values so the reference can be fed identical draws.
 //
-// Cost model (SASS, sm_100a): one round = 2 IMAD.WIDE.U32 + 2 LOP3 (round keys are kernel parameters,
-// i.e. constant-bank operands of the LOP3), so one call = 40 integer ops for 4 words = 10 per draw.
+// Cost model (SASS, sm_100a, measured with csrc/microbench.cu): one round = 2 IMAD.WIDE.U32 + 2 LOP3 (round keys
+// are kernel parameters, i.e. uniform-register operands of the LOP3).  IMAD.WIDE holds the sub-partition's issue
+// port for 4 cycles, so the multiplies ARE the cost of a call (~68 of ~90 issue cycles): the streams below
+// therefore squeeze 8 normals out of every call (one Box-Muller pair per 32-bit word).
 #pragma once
 #include <stdint.h>
 
@@ -91,17 +93,23 @@ __device__ __forceinline__ float mant12(uint32_t w)
 // The fused kernels fold it into their per-step weight, b200mc_dump_normals multiplies it in (in double).
 #define B200MC_BM_SCALE 1.1774100225154747
 
-// Box-Muller on two words.  Returns the UNSCALED pair (rc, rs) = sqrt(-lg2 u1) * (cos, sin)(angle):
-// the standard normals are B200MC_BM_SCALE * rc and B200MC_BM_SCALE * rs.
-//   u1    = 2 - mant12(wa)            in (0, 1]           (so lg2 <= 0 and never -inf)
-//   angle = 2 pi (mant12(wb) - 1.5)   in [-pi, pi)        (best range of sin/cos.approx)
-// 4 MUFU (lg2, sqrt, sin, cos) per pair.
+// Box-Muller on ONE word: a 32-bit word yields a whole pair of normals.
+//   radius  u1    = 2 - mant12(w)                 in (0, 1]    low 23 bits of w  (lg2 <= 0 and never -inf)
+//           rad   = sqrt(-lg2 u1)                              max radius sqrt(2*23*ln 2) = 5.65 sigma
+//   angle   f2    = float with mantissa (w >> 9)  in [1, 2)    top 23 bits of w, one funnel shift
+//           ang   = 2 pi f2 - 3 pi                in [-pi, pi)  (best range of sin/cos.approx)
+// The two fields share bits 9..22.  That is harmless: for any fixed radius field the angle still runs over 512
+// equally spaced directions (bits 23..31) plus an offset, so E[g(rad) e^{ik ang}] = 0 for every k that is not
+// a multiple of 512 -- all joint moments of the pair up to order 511 are those of two independent normals,
+// exactly as for a continuous angle.  Returns the UNSCALED pair (rc, rs) = rad * (cos, sin)(ang): the standard
+// normals are B200MC_BM_SCALE * rc and B200MC_BM_SCALE * rs.  Cost: 2 ALU + 3 FP32 + 4 MUFU per pair.
 struct BM2 { float rc, rs; };
-__device__ __forceinline__ BM2 box_muller_raw(uint32_t wa, uint32_t wb)
+__device__ __forceinline__ BM2 box_muller_word(uint32_t w)
 {
-    const float u1 = 2.0f - mant12(wa);
+    const float u1 = 2.0f - mant12(w);
     const float rad = sqrt_approx(-lg2_approx(u1));
-    const float ang = fmaf(mant12(wb), 6.283185307179586f, -9.42477796076938f);
+    const float f2 = __uint_as_float(__funnelshift_r(w, 0x7Fu, 9));      // (w >> 9) | 0x3f800000
+    const float ang = fmaf(f2, 6.283185307179586f, -9.42477796076938f);
     BM2 o;
     o.rc = rad * cos_approx(ang);
     o.rs = rad * sin_approx(ang);

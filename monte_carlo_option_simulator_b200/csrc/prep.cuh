@@ -13,7 +13,7 @@ struct Prep {
     ModelArgs m;
     PhiloxKey key;
     int mode;
-    int wld;                       // row length of the DETVAR tables (n_steps rounded up to 4)
+    int wld;                       // row length of the DETVAR tables (n_steps rounded up to 8)
     std::vector<double> wtab;      // [3][wld]  sqrt(v_s dt) BM_SCALE, zero padded
     std::vector<double> dtab;      // [wld]     cumulative drift of the primary state after step s
 };
@@ -70,7 +70,7 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
     else if (n_steps <= B200MC_DETVAR_MAX_STEPS) o.mode = MODE_DETVAR;
     else o.mode = MODE_HESTON;
 
-    o.wld = (n_steps + 3) & ~3;
+    o.wld = (n_steps + 7) & ~7;
     if (o.mode == MODE_GBM) {
         for (int r = 0; r < 3; ++r) {
             m.step_drift[r] = (drift_comp - 0.5 * m.v0[r]) * dt;            // :229

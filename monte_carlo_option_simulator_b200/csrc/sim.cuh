@@ -86,10 +86,17 @@ __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R
     }
 }
 
+// Draw layout (part of the ABI, include/b200mc.h "Random numbers"): Philox counter = (path_lo, path_hi, block, stream),
+// every 32-bit output word w yields one Box-Muller pair (rc, rs) = box_muller_word(w):
+//   GBM / DETVAR  stream 0, block j -> steps 8j..8j+7: word i gives the normals of steps 8j+2i (rc) and 8j+2i+1 (rs)
+//   HESTON        stream 1, block j -> steps 4j..4j+3: word i gives (Z1, Z2) = (rc, rs) of step 4j+i
+//   SVJ           stream 2, block j -> steps 2j, 2j+1: (w0 -> (Z1, Z2), w1 -> U_jump) and (w2, w3) likewise;
+//                 stream 3, block s -> word 0 gives Z_jump_size of step s (drawn only when the jump fires)
+//
 // Simulates global path `path` to T.  On return xT[k] = log(S_T / S0) of state k and vT[k] its variance
 // (GBM / DETVAR: vT is left untouched); sumz_out = sum of the raw draws (GBM only; feeds the pathwise vega).
-// wtab: DETVAR weights, wtab[k * wld + s] = sqrt(v_s^{(k)} dt) * BM_SCALE in shared memory.
-// REC: after every step s call rec(s, x0) with the primary state's log return (path store).
+// wtab: DETVAR weights, wtab[k * wld + s] = sqrt(v_s^{(k)} dt) * BM_SCALE in shared memory (wld = steps rounded up to 8,
+// zero padded).  rec: after every step s, rec(s, x0) gets the primary state's log return (path store).
 template <int MODE, bool ANTI, bool GREEKS, typename R, typename Rec>
 __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKey &key, uint64_t path, int n_steps,
                                               const R *wtab, int wld,
@@ -104,37 +111,45 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         // path store: the log return itself is carried so that every step can be recorded
         const R w = (R)m.x_w[0], d = (R)m.step_drift[0];
         R x = (R)0;
-        const int nblk = (n_steps + 3) >> 2;
+        const int nblk = (n_steps + 7) >> 3;
         for (int j = 0; j < nblk; ++j) {
             const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
-            const BM2 p = box_muller_raw(u.x, u.y), q = box_muller_raw(u.z, u.w);
-            const R z[4] = {(R)p.rc, (R)p.rs, (R)q.rc, (R)q.rs};
+            const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
+                      b3 = box_muller_word(u.w);
+            const R z[8] = {(R)b0.rc, (R)b0.rs, (R)b1.rc, (R)b1.rs, (R)b2.rc, (R)b2.rs, (R)b3.rc, (R)b3.rs};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (4 * j + t < n_steps) {
+            for (int t = 0; t < 8; ++t) {
+                if (8 * j + t < n_steps) {
                     x += w * z[t] + d;
-                    rec(4 * j + t, x);
+                    rec(8 * j + t, x);
                 }
             }
         }
         sumz_out = (R)0;
         xT[0] = x;
     } else if constexpr (MODE == MODE_GBM) {
+        // Software-pipelined: the Philox rounds of block j+1 (IMAD.WIDE / LOP3) are issued in the same loop body as
+        // the Box-Muller transforms of block j (MUFU), so every warp feeds the XU pipe at an even rate instead of
+        // in bursts (ncu: mio_throttle was the top stall with the two phases back to back).
         R sumz = (R)0;
-        const int nblk = n_steps >> 2;
-#pragma unroll 2
-        for (int j = 0; j < nblk; ++j) {
-            const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
-            const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
-            sumz += (R)p.rc; sumz += (R)p.rs; sumz += (R)q.rc; sumz += (R)q.rs;
+        const int nb = (n_steps + 7) >> 3;                 // blocks, the last one possibly partial
+        U4 u = philox4x32_10(c0, c1, 0u, B200MC_STREAM_GBM, key);
+        for (int j = 1; j < nb; ++j) {
+            const U4 un = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+            const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
+                      b3 = box_muller_word(u.w);
+            sumz += (R)b0.rc; sumz += (R)b0.rs; sumz += (R)b1.rc; sumz += (R)b1.rs;
+            sumz += (R)b2.rc; sumz += (R)b2.rs; sumz += (R)b3.rc; sumz += (R)b3.rs;
+            u = un;
         }
-        const int rem = n_steps & 3;
-        if (rem) {
-            const U4 w = philox4x32_10(c0, c1, (uint32_t)nblk, B200MC_STREAM_GBM, key);
-            const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
-            sumz += (R)p.rc;
-            if (rem > 1) sumz += (R)p.rs;
-            if (rem > 2) sumz += (R)q.rc;
+        {
+            const int rem = n_steps - 8 * (nb - 1);        // 1..8 draws of the last block are used
+            const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
+                      b3 = box_muller_word(u.w);
+            const R z[8] = {(R)b0.rc, (R)b0.rs, (R)b1.rc, (R)b1.rs, (R)b2.rc, (R)b2.rs, (R)b3.rc, (R)b3.rs};
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (t < rem) sumz += z[t];
         }
         sumz_out = sumz;
         xT[0] = (R)m.x_drift[0] + (R)m.x_w[0] * sumz;
@@ -147,21 +162,22 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         R acc[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) acc[k] = (R)0;
-        // weight row of state k: ANTI twin shares row 0 with a minus sign
-        auto row = [&](int k) -> int { return (ANTI && k == 1) ? 0 : (k == 0 ? 0 : k - (ANTI ? 1 : 0)); };
-        const int nblk = (n_steps + 3) >> 2;     // the table is zero-padded to a multiple of 4
+        // weight row of state k (the ANTI twin shares row 0 with a minus sign and is not accumulated)
+        auto row = [&](int k) -> int { return k == 0 ? 0 : k - (ANTI ? 1 : 0); };
+        const int nblk = (n_steps + 7) >> 3;     // the table is zero-padded to a multiple of 8
         for (int j = 0; j < nblk; ++j) {
-            const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
-            const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
-            const R z[4] = {(R)p.rc, (R)p.rs, (R)q.rc, (R)q.rs};
+            const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+            const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
+                      b3 = box_muller_word(u.w);
+            const R z[8] = {(R)b0.rc, (R)b0.rs, (R)b1.rc, (R)b1.rs, (R)b2.rc, (R)b2.rs, (R)b3.rc, (R)b3.rs};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     if (ANTI && k == 1) continue;
-                    acc[k] += wtab[row(k) * wld + 4 * j + t] * z[t];
+                    acc[k] += wtab[row(k) * wld + 8 * j + t] * z[t];
                 }
-                if constexpr (Rec::enabled) { if (4 * j + t < n_steps) rec(4 * j + t, acc[0]); }
+                if constexpr (Rec::enabled) { if (8 * j + t < n_steps) rec(8 * j + t, acc[0]); }
             }
         }
         sumz_out = (R)0;
@@ -178,32 +194,39 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         for (int k = 0; k < NS; ++k) { x[k] = (R)0; v[k] = (R)m.v0[0]; }
         if constexpr (GREEKS) { v[L::UP_IDX] = (R)m.v0[1]; v[L::DN_IDX] = (R)m.v0[2]; }
         if constexpr (MODE == MODE_HESTON) {
-            const int nblk = n_steps >> 1;
+            const int nblk = (n_steps + 3) >> 2;
             for (int j = 0; j < nblk; ++j) {
-                const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_HESTON, key);
-                const BM2 p = box_muller_raw(w.x, w.y), q = box_muller_raw(w.z, w.w);
-                sv_step<R, ANTI, GREEKS>(x, v, c, (R)p.rc, c.rho * (R)p.rc + c.crho * (R)p.rs, (R)0, (R)0);
-                if constexpr (Rec::enabled) rec(2 * j, x[0]);
-                sv_step<R, ANTI, GREEKS>(x, v, c, (R)q.rc, c.rho * (R)q.rc + c.crho * (R)q.rs, (R)0, (R)0);
-                if constexpr (Rec::enabled) rec(2 * j + 1, x[0]);
-            }
-            if (n_steps & 1) {
-                const U4 w = philox4x32_10(c0, c1, (uint32_t)nblk, B200MC_STREAM_HESTON, key);
-                const BM2 p = box_muller_raw(w.x, w.y);
-                sv_step<R, ANTI, GREEKS>(x, v, c, (R)p.rc, c.rho * (R)p.rc + c.crho * (R)p.rs, (R)0, (R)0);
-                if constexpr (Rec::enabled) rec(n_steps - 1, x[0]);
+                const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_HESTON, key);
+                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t == 0 || 4 * j + t < n_steps) {
+                        const BM2 b = box_muller_word(ww[t]);
+                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs, (R)0, (R)0);
+                        if constexpr (Rec::enabled) rec(4 * j + t, x[0]);
+                    }
+                }
             }
         } else {
-            for (int j = 0; j < n_steps; ++j) {
-                const U4 w = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_SVJ, key);
-                const BM2 p = box_muller_raw(w.x, w.y);
-                R jmu = (R)0, jsz = (R)0;
-                if ((uint64_t)w.z < m.jump_thr) {                                    // :233-234
-                    jmu = c.mu_j;
-                    jsz = c.sigma_j * (R)jump_size_normal(w.w);
+            const int nblk = (n_steps + 1) >> 1;
+            for (int j = 0; j < nblk; ++j) {
+                const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_SVJ, key);
+                const uint32_t wz[2] = {u.x, u.z}, wu[2] = {u.y, u.w};
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int s = 2 * j + t;
+                    if (t == 0 || s < n_steps) {
+                        const BM2 b = box_muller_word(wz[t]);
+                        R jmu = (R)0, jsz = (R)0;
+                        if ((uint64_t)wu[t] < m.jump_thr) {                          // :233-234
+                            const U4 uj = philox4x32_10(c0, c1, (uint32_t)s, B200MC_STREAM_JUMP, key);
+                            jmu = c.mu_j;
+                            jsz = c.sigma_j * (R)jump_size_normal(uj.x);
+                        }
+                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs, jmu, jsz);
+                        if constexpr (Rec::enabled) rec(s, x[0]);
+                    }
                 }
-                sv_step<R, ANTI, GREEKS>(x, v, c, (R)p.rc, c.rho * (R)p.rc + c.crho * (R)p.rs, jmu, jsz);
-                if constexpr (Rec::enabled) rec(j, x[0]);
             }
         }
         sumz_out = (R)0;

@@ -82,8 +82,8 @@ def mix(substr, steps_per_iter=None):
             counts[c] = counts.get(c, 0) + 1
         counts["total"] = len(body)
         counts["imad_wide"] = sum(1 for i in body if i[1].startswith("IMAD.WIDE"))
-        if steps_per_iter is None:      # 4 path-steps per Philox call, 20 IMAD.WIDE per call (first round partly hoisted: 19)
-            calls = max(1, round(counts["imad_wide"] / 19.5))
+        if steps_per_iter is None:      # 8 path-steps per Philox call; 17-20 IMAD.WIDE per call (first round hoisted)
+            calls = max(1, round(counts["imad_wide"] / 18.0))
             counts["philox_calls"] = calls
         res[name] = counts
     return res
