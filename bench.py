@@ -194,8 +194,9 @@ def instruction_roofline(h, achieved_path_steps_per_gpu, sm_mhz):
             "rng_only_path_steps_per_s": 8.0 * rates["philox_bm_calls"]}
 
 
-def hbm_roofline(h, torch, n_paths=1_000_000, reps=3):
-    """Path-store kernel (4 bytes per path-step, written once) vs the measured copy bandwidth."""
+def hbm_roofline(h, torch, n_paths=4_000_000, reps=3):
+    """BASELINE cfg4: the path-store kernel (4M paths x 250 steps; 4 or 8 bytes per path-step, written once, output
+    far larger than L2) vs the measured copy bandwidth."""
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, read+write)"
@@ -203,8 +204,11 @@ def hbm_roofline(h, torch, n_paths=1_000_000, reps=3):
         peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     from monte_carlo_option_simulator_b200 import _lib
     out = {}
-    for name, dt_np, fl, esz in (("f32", np.float32, 0, 4), ("f64", np.float64, _lib.FP64, 8)):
-        ld = N_STEPS + 1
+    cases = (("f32", np.float32, 0, 4, N_STEPS + 1, "reference layout [n, 251] float32: CTA tile = 32 paths x 251, one TMA bulk store per tile"),
+             ("f64_out_f32_state", np.float64, 0, 8, N_STEPS + 1, "reference layout [n, 251] float64 (what get_sample_paths returns), fp32 path state"),
+             ("f64", np.float64, _lib.FP64, 8, N_STEPS + 1, "reference layout [n, 251] float64, fp64 path state (double exp per step: FP64-pipe bound)"),
+             ("f32_ld256", np.float32, 0, 4, 256, "rows padded to 256 elements: row-tiled kernel, 128-bit shared + global stores"))
+    for name, dt_np, fl, esz, ld, note in cases:
         buf = torch.empty(n_paths * ld * esz, dtype=torch.uint8, device="cuda")
         best = None
         for r in range(reps + 1):
@@ -213,11 +217,12 @@ def hbm_roofline(h, torch, n_paths=1_000_000, reps=3):
             ms = h.timer_end()
             if r > 0:
                 best = ms if best is None else min(best, ms)
-        gbs = n_paths * ld * esz / (best * 1e-3) / 1e9
+        nbytes = n_paths * (N_STEPS + 1) * esz          # algorithmic bytes: the matrix itself, no padding
+        gbs = nbytes / (best * 1e-3) / 1e9
         out[name] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
-                     "kernel": f"k_paths<GBM,{name}>", "path_steps_per_s": n_paths * N_STEPS / (best * 1e-3),
-                     "bytes_per_launch": n_paths * ld * esz, "ms": best, "peak_source": src,
-                     "shape": [n_paths, ld]}
+                     "kernel": "k_paths_tma<GBM>" if ld == N_STEPS + 1 else "k_paths_det<GBM>", "path_steps_per_s": n_paths * N_STEPS / (best * 1e-3),
+                     "bytes_per_launch": nbytes, "ms": best, "peak_source": src, "shape": [n_paths, N_STEPS + 1], "ld": ld,
+                     "note": note}
         del buf
     return out
 

@@ -128,6 +128,244 @@ k_paths(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_g, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------- path store, GBM / DETVAR
+// Dedicated kernel for deterministic variance (the BASELINE path-store configuration): no per-step branching.
+// Column c of the matrix is y_c (y_0 = S0, y_{s+1} = S after step s).  A warp owns 32 consecutive paths and walks
+// the columns in tiles of 32: slot 0 of a tile is the value carried over from the previous tile, slots 1..31 and
+// the next carry come out of four Philox calls (32 normals per lane).  The tile is then written out row by row.
+//   scalar flush  one row per store instruction: 32 lanes x sizeof(O) contiguous bytes
+//   VEC flush     (fp32 output, ld % 4 == 0, 16-byte aligned base) the tile is kept as float4 groups with an
+//                 XOR swizzle (group g of row r lives at g ^ (r & 7)), filled with 128-bit shared stores and
+//                 written with 128-bit global stores, 4 rows (4 x 128 contiguous bytes) per instruction.
+template <bool TAB, typename R, typename O, bool VEC>
+__global__ void __launch_bounds__(PT_THREADS)
+k_paths_det(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_g, const double *__restrict__ dtab_g,
+            O *__restrict__ out)
+{
+    static_assert(!VEC || sizeof(O) == 4, "the 128-bit flush is for fp32 output");
+    constexpr int NW = PT_THREADS / 32;
+    constexpr R UNIT = sizeof(R) == 4 ? (R)1.4426950408889634 : (R)1;     // fp32 carries log2(S/S0), fp64 ln(S/S0)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    O *tiles = reinterpret_cast<O *>(smem_raw);                                     // [NW][32*33] (VEC: [NW][32*32])
+    R *w2 = reinterpret_cast<R *>(tiles + NW * 32 * 33);                            // [wld + 32]  TAB only
+    R *d2 = w2 + a.wld + 32;                                                        // [wld + 32]
+    if constexpr (TAB) {
+        for (int i = threadIdx.x; i < a.wld + 32; i += PT_THREADS) {
+            const bool in = i < a.n_steps;
+            w2[i] = in ? (R)(wtab_g[i] * (double)UNIT) : (R)0;
+            d2[i] = in ? (R)((dtab_g[i] - (i ? dtab_g[i - 1] : 0.0)) * (double)UNIT) : (R)0;
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    O *tile = tiles + warp * 32 * 33;
+    const R S0 = (R)a.m.S0;
+    const R wc = (R)(a.m.x_w[0] * (double)UNIT), dc = (R)(a.m.step_drift[0] * (double)UNIT);
+    const int ncol = a.n_steps + 1;
+    const int ntiles = (ncol + 31) >> 5;
+    const int64_t n_groups = (a.n_paths + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * NW + warp; g < n_groups; g += (int64_t)gridDim.x * NW) {
+        const int64_t path0 = g * 32;
+        int64_t me = path0 + lane;
+        if (me >= a.n_paths) me = a.n_paths - 1;          // idle lanes shadow the last path (never stored)
+        const uint64_t path = a.path0 + (uint64_t)me;
+        const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
+        const int rows = (int)((a.n_paths - path0) < 32 ? (a.n_paths - path0) : 32);
+        R x = (R)0;
+        O carry = (O)a.m.S0;
+        for (int k = 0; k < ntiles; ++k) {
+            O vals[32];
+            vals[0] = carry;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const U4 u = philox4x32_10(c0, c1, (uint32_t)(4 * k + b), B200MC_STREAM_GBM, a.key);
+                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const BM2 bm = box_muller_word(ww[t]);
+                    const int s = 32 * k + 8 * b + 2 * t;          // step index of the first normal of the pair
+                    R wa, wb, da, db;
+                    if constexpr (TAB) { wa = w2[s]; wb = w2[s + 1]; da = d2[s]; db = d2[s + 1]; }
+                    else { wa = wb = wc; da = db = dc; }
+                    x = (x + da) + wa * (R)bm.rc;
+                    O ya, yb;
+                    if constexpr (sizeof(R) == 4) ya = (O)(S0 * ex2_approx((float)x)); else ya = (O)(S0 * exp(x));
+                    x = (x + db) + wb * (R)bm.rs;
+                    if constexpr (sizeof(R) == 4) yb = (O)(S0 * ex2_approx((float)x)); else yb = (O)(S0 * exp(x));
+                    const int idx = 8 * b + 2 * t + 1;             // tile slots idx, idx + 1
+                    vals[idx] = ya;
+                    if (idx + 1 < 32) vals[idx + 1] = yb; else carry = yb;
+                }
+            }
+            const int col0 = 32 * k;
+            const int ncv = ncol - col0 < 32 ? ncol - col0 : 32;   // valid columns of this tile
+            __syncwarp();
+            if constexpr (VEC) {
+                float4 *t4 = reinterpret_cast<float4 *>(tile);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    t4[lane * 8 + (q ^ (lane & 7))] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+                __syncwarp();
+                const int gq = lane & 7;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = 4 * it + (lane >> 3);
+                    const float4 v = t4[r * 8 + (gq ^ (r & 7))];
+                    float *dst = reinterpret_cast<float *>(out) + (size_t)(path0 + r) * a.ld + col0 + 4 * gq;
+                    if (r < rows) {
+                        if (4 * gq + 3 < ncv) *reinterpret_cast<float4 *>(dst) = v;
+                        else {
+                            if (4 * gq + 0 < ncv) dst[0] = v.x;
+                            if (4 * gq + 1 < ncv) dst[1] = v.y;
+                            if (4 * gq + 2 < ncv) dst[2] = v.z;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) tile[lane * 33 + q] = vals[q];
+                __syncwarp();
+                O *dst = out + (size_t)path0 * a.ld + col0 + lane;
+                if (rows == 32 && ncv == 32) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) { *dst = tile[r * 33 + lane]; dst += a.ld; }
+                } else {
+                    for (int r = 0; r < rows; ++r) { if (lane < ncv) *dst = tile[r * 33 + lane]; dst += a.ld; }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- path store, TMA flush
+// The reference layout [n_paths, n_steps + 1] (ld == n_steps + 1, e.g. 251 columns) has rows that start on arbitrary
+// 4-byte boundaries, so row-wise 128-byte stores straddle cache lines and leave partial sectors (measured: 1.96 TB/s
+// against 3.3 TB/s for 1024-byte rows).  But the rows of 32 CONSECUTIVE paths are one contiguous byte range that
+// starts on a 128-byte boundary (32 * ncol * 4 bytes = ncol full lines).  This kernel therefore gives a CTA 32 paths
+// and splits the TIME axis across its warps -- the counter-based generator can start anywhere: warp c, lane p draws
+// steps [32c, 32c + 32) of path p.  Chunk totals meet in shared memory (the only cross-warp dependence of a path),
+// every thread turns its chunk-local log returns into spots and drops them into the CTA's tile, which has exactly
+// the global layout (flat [32][ncol]; the fill is bank-conflict free because ncol is odd for even step counts and
+// lanes walk different rows), and ONE thread hands the whole tile to the TMA engine: a single cp.async.bulk
+// shared -> global copy of 32 * ncol * sizeof(O) bytes (UBLKCP), fully aligned, overlapped with the next tile's
+// Philox work.  No per-row store instructions, no partial sectors.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool TAB, typename R, typename O, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_g, const double *__restrict__ dtab_g,
+            O *__restrict__ out)
+{
+    constexpr R UNIT = sizeof(R) == 4 ? (R)1.4426950408889634 : (R)1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ncol = a.n_steps + 1;
+    const int NCH = blockDim.x >> 5;                                                // chunks of 32 steps = warps
+    O *tile = reinterpret_cast<O *>(smem_raw);                                      // [32][ncol], the global layout
+    const size_t tile_bytes = ((size_t)32 * ncol * sizeof(O) + 127) & ~(size_t)127;
+    R *totals = reinterpret_cast<R *>(smem_raw + tile_bytes);                       // [NCH][32]
+    R *w2 = totals + NCH * 32;                                                      // [wld + 32]  TAB only
+    R *d2 = w2 + a.wld + 32;
+    if constexpr (TAB) {
+        for (int i = threadIdx.x; i < a.wld + 32; i += blockDim.x) {
+            const bool in = i < a.n_steps;
+            w2[i] = in ? (R)(wtab_g[i] * (double)UNIT) : (R)0;
+            d2[i] = in ? (R)((dtab_g[i] - (i ? dtab_g[i - 1] : 0.0)) * (double)UNIT) : (R)0;
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const R S0 = (R)a.m.S0;
+    const R wc = (R)(a.m.x_w[0] * (double)UNIT), dc = (R)(a.m.step_drift[0] * (double)UNIT);
+    const int64_t n_groups = (a.n_paths + 31) / 32;
+    const bool dst_aligned = ((uintptr_t)out & 15) == 0;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t path0 = g * 32;
+        int64_t me = path0 + lane;
+        if (me >= a.n_paths) me = a.n_paths - 1;                                    // idle lanes shadow the last path
+        const uint64_t path = a.path0 + (uint64_t)me;
+        const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
+        const int rows = (int)((a.n_paths - path0) < 32 ? (a.n_paths - path0) : 32);
+        // ---- chunk-local log returns of steps 32c .. 32c + 31 ----------------------------------------------------
+        R xl[32];
+        R x = (R)0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const U4 u = philox4x32_10(c0, c1, (uint32_t)(4 * c + b), B200MC_STREAM_GBM, a.key);
+            const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const BM2 bm = box_muller_word(ww[t]);
+                R wa, wb, da, db;
+                if constexpr (TAB) {
+                    const int s = 32 * c + 8 * b + 2 * t;
+                    wa = w2[s]; wb = w2[s + 1]; da = d2[s]; db = d2[s + 1];
+                } else { wa = wb = wc; da = db = dc; }
+                x = (x + da) + wa * (R)bm.rc;
+                xl[8 * b + 2 * t] = x;
+                x = (x + db) + wb * (R)bm.rs;
+                xl[8 * b + 2 * t + 1] = x;
+            }
+        }
+        totals[c * 32 + lane] = x;
+        // the TMA engine must have finished READING the tile of the previous group before anyone refills it
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        R off = (R)0;
+        for (int cc = 0; cc < c; ++cc) off += totals[cc * 32 + lane];
+        // ---- fill: y_{32c + 1 + j} = S0 exp(off + xl[j]) -----------------------------------------------------------
+        O *row = tile + (size_t)lane * ncol;
+        if (c == 0) row[0] = (O)a.m.S0;                                             // column 0 = S0   (:217)
+        const int colbase = 32 * c + 1;
+        if (colbase + 31 < ncol) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if constexpr (sizeof(R) == 4) row[colbase + j] = (O)(S0 * ex2_approx((float)(off + xl[j])));
+                else row[colbase + j] = (O)(S0 * exp(off + xl[j]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                O y;
+                if constexpr (sizeof(R) == 4) y = (O)(S0 * ex2_approx((float)(off + xl[j]))); else y = (O)(S0 * exp(off + xl[j]));
+                if (colbase + j < ncol) row[colbase + j] = y;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                // generic-proxy writes -> async proxy
+        __syncthreads();
+        // ---- flush ------------------------------------------------------------------------------------------------
+        O *dst = out + (size_t)path0 * ncol;
+        const uint32_t bytes = (uint32_t)((size_t)rows * ncol * sizeof(O));
+        if (dst_aligned && (bytes & 15) == 0) {
+            if (threadIdx.x == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(smem_u32(tile)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {                                                                    // ragged last group / odd base
+            const int64_t E = (int64_t)rows * ncol;
+            for (int64_t f = threadIdx.x; f < E; f += blockDim.x) dst[f] = tile[f];
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <bool TAB, typename R, typename O>
+static void path_det_launch(const PathArgs &a, const double *wtab, const double *dtab, void *out, bool vec, unsigned grid,
+                            size_t smem, cudaStream_t st)
+{
+    if constexpr (sizeof(O) == 4) {
+        if (vec) {
+            auto k = k_paths_det<TAB, R, O, true>;
+            cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<grid, PT_THREADS, smem, st>>>(a, wtab, dtab, (O *)out);
+            return;
+        }
+    }
+    auto k = k_paths_det<TAB, R, O, false>;
+    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, PT_THREADS, smem, st>>>(a, wtab, dtab, (O *)out);
+}
+
 using TermKernel = void (*)(const PathArgs, const double *, void *, void *, void *);
 
 template <int MODE, bool ANTI, typename R, typename O>
@@ -277,7 +515,50 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
         else { if (dtype == B200MC_F64) path_launch<M, float, double>(a, wtab_d, dtab_d, dO, (unsigned)grid, smem, h->stream); \
                else path_launch<M, float, float>(a, wtab_d, dtab_d, dO, (unsigned)grid, smem, h->stream); }         \
     } while (0)
-    DISPATCH_MODE(pr.mode, PATH_CALL);
+    if (pr.mode == MODE_GBM || pr.mode == MODE_DETVAR) {
+        const bool tab = pr.mode == MODE_DETVAR;
+        const bool vec = dtype == B200MC_F32 && (ld % 4 == 0) && (((uintptr_t)dO) % 16 == 0);
+        smem = (size_t)(PT_THREADS / 32) * 32 * 33 * esz + (tab ? (size_t)2 * (pr.wld + 32) * (fp64 ? 8 : 4) : 0);
+#define DET_CALL(TAB)                                                                                              \
+        do {                                                                                                       \
+            if (fp64) { if (dtype == B200MC_F64) path_det_launch<TAB, double, double>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); \
+                        else path_det_launch<TAB, double, float>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); }  \
+            else { if (dtype == B200MC_F64) path_det_launch<TAB, float, double>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); \
+                   else path_det_launch<TAB, float, float>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); }         \
+        } while (0)
+        if (ld == (int64_t)n_steps + 1 && n_steps <= 1024) {
+            const int NCH = (n_steps + 31) / 32;                      // warps per CTA = chunks of 32 steps
+            const size_t rs = fp64 ? 8 : 4;
+            smem = (((size_t)32 * (n_steps + 1) * esz + 127) & ~(size_t)127) + (size_t)NCH * 32 * rs +
+                   (tab ? (size_t)2 * (pr.wld + 32) * rs : 0);
+            int64_t fgrid = (n_paths + 31) / 32;
+            const int64_t fcap = (int64_t)h->sm_count * 16;
+            if (fgrid > fcap) fgrid = fcap;
+#define TMA_CALL(TAB, RR, OO)                                                                                      \
+            do {                                                                                                   \
+                if (NCH <= 8) {                                                                                    \
+                    auto k = k_paths_tma<TAB, RR, OO, 256>;                                                        \
+                    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                    k<<<(unsigned)fgrid, 32 * NCH, smem, h->stream>>>(a, wtab_d, dtab_d, (OO *)dO);                \
+                } else {                                                                                           \
+                    auto k = k_paths_tma<TAB, RR, OO, 1024>;                                                       \
+                    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                    k<<<(unsigned)fgrid, 32 * NCH, smem, h->stream>>>(a, wtab_d, dtab_d, (OO *)dO);                \
+                }                                                                                                  \
+            } while (0)
+            if (tab) {
+                if (fp64) { if (dtype == B200MC_F64) TMA_CALL(true, double, double); else TMA_CALL(true, double, float); }
+                else { if (dtype == B200MC_F64) TMA_CALL(true, float, double); else TMA_CALL(true, float, float); }
+            } else {
+                if (fp64) { if (dtype == B200MC_F64) TMA_CALL(false, double, double); else TMA_CALL(false, double, float); }
+                else { if (dtype == B200MC_F64) TMA_CALL(false, float, double); else TMA_CALL(false, float, float); }
+            }
+#undef TMA_CALL
+        } else if (tab) DET_CALL(true); else DET_CALL(false);
+#undef DET_CALL
+    } else {
+        DISPATCH_MODE(pr.mode, PATH_CALL);
+    }
 #undef PATH_CALL
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;

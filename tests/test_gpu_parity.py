@@ -435,7 +435,7 @@ def test_generate_paths_identical_draws(H, L, golden, mode, n, steps):
     assert got32.dtype == np.float32
     np.testing.assert_allclose(got32, want, rtol=RTOL32)
     padded = H.generate_paths(p, S0, T, steps, n, seed, L.FP64, np.float64, off, ld=steps + 4)
-    np.testing.assert_array_equal(padded, got)
+    np.testing.assert_allclose(padded, got, rtol=1e-13)     # row-tiled kernel vs TMA-tiled kernel: summation order
 
 
 def test_generate_paths_terminal_column_equals_terminal_mode(H, L, golden):
