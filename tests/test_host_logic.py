@@ -1,0 +1,201 @@
+"""CPU: the host-side mirror (dict assembly from the fused sums, steps rule, Sobol/bridge front end, sharding,
+patch_reference) against the oracle and the golden fixtures.  The CUDA library is replaced here by a NumPy stand-in
+that produces b200mc_sums from the ORACLE's terminal spots, so that the algebra from sums to result dictionaries
+(including the reference's pseudo control variate, quirk 2) is checked against MonteCarloOracle / GreeksOracle."""
+import math
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from monte_carlo_option_simulator_b200 import _lib, monte_carlo as MC
+from monte_carlo_option_simulator_b200 import GreeksEngine, MonteCarloEngine, SVJParams
+from monte_carlo_option_simulator_b200.dist import Comm, shard_range, sharded_sums
+
+
+def P(golden, name):
+    return O.Params(**golden["params"][name])
+
+
+class OracleBackedHandle:
+    """Stands in for _lib.Handle: same price_european signature, sums computed with NumPy from oracle paths drawn
+    with PCG64 (so results can be compared with the oracle's own reductions on the same draws)."""
+
+    def __init__(self, n_global=None):
+        self.calls = 0
+        self.n_global = n_global       # total paths of the job: PCG64 streams depend on it, Philox counters do not
+
+    def price_european(self, params, S0, T, n_steps, n_paths, seed, strikes, is_call=True, flags=0, bumps=None,
+                       path_offset=0, out_dev=None):
+        self.calls += 1
+        p = O.as_params(params)
+        Z1, Z2, Zj, Zjs = O.draw_pcg64(seed, self.n_global or (path_offset + n_paths), n_steps)
+        Z1, Z2, Zj, Zjs = (z[path_offset:path_offset + n_paths] for z in (Z1, Z2, Zj, Zjs))
+        S = O._sim(p, S0, T, Z1, Z2, Zj, Zjs, n_steps)[0]
+        A = O._sim(p, S0, T, -Z1, -Z2, Zj, -Zjs, n_steps)[0] if flags & _lib.ANTITHETIC else None
+        rows = []
+        for K in np.atleast_1d(strikes):
+            pay = (lambda s: np.maximum(s - K, 0.0)) if is_call else (lambda s: np.maximum(K - s, 0.0))
+            a = pay(S)
+            b = pay(A) if A is not None else np.zeros_like(a)
+            s_avg = 0.5 * (S + A) if A is not None else S
+            pc = 0.5 * (a + b) if A is not None else a
+            row = [n_paths, a.sum(), b.sum(), (a * a).sum(), (b * b).sum(), (a * b).sum(), s_avg.sum(),
+                   (s_avg ** 2).sum(), (pc * s_avg).sum()] + [0.0] * 8
+            if flags & _lib.GREEKS:
+                itm = (S > K) if is_call else (S < K)
+                sb = bumps.spot_bump
+                row[9] = (itm * S / S0).sum()
+                row[10] = pay(S * (1 + sb)).sum()
+                row[11] = pay(S * (1 - sb)).sum()
+                row[12] = pay(O._sim(p, S0, T, Z1, Z2, Zj, Zjs, n_steps, v0=bumps.v0_up)[0]).sum()
+                row[13] = pay(O._sim(p, S0, T, Z1, Z2, Zj, Zjs, n_steps, v0=bumps.v0_dn)[0]).sum()
+                row[14] = pay(S * math.exp((bumps.r_up - p.r) * T)).sum()
+                row[15] = pay(S * math.exp((bumps.r_dn - p.r) * T)).sum()
+            rows.append(row)
+        return np.array(rows, dtype=np.float64)
+
+
+def test_bs_closed_forms_match_golden(golden):
+    b = golden["cases"]["bs"]
+    assert MC.bs_price(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, True) == pytest.approx(b["cfg1_call"], rel=1e-13)
+    assert MC.bs_price(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, False) == pytest.approx(b["cfg1_put"], rel=1e-13)
+    assert MC.bs_delta(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, True) == pytest.approx(b["cfg1_delta_call"], rel=1e-13)
+    assert MC.bs_delta(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, False) == pytest.approx(b["cfg1_delta_put"], rel=1e-13)
+    assert MC.bs_price(110.0, 100.0, 0.0, 0.05, 0.0, 0.2, True) == b["expired_call"]
+    assert MC.bs_delta(90.0, 100.0, 0.0, 0.05, 0.0, 0.2, False) == b["expired_put_delta"]
+    assert MC.bs_price(22500.0, 22500.0, 0.04, 0.065, 0.012, 0.2, True) == pytest.approx(b["verify_py"], rel=1e-13)
+
+
+def test_steps_rule():
+    assert MC.steps_for(252, 0.04) == 10 and MC.steps_for(250, 1.0) == 250 and MC.steps_for(252, 0.25) == 63
+    assert MC.steps_for(252, 0.1, floor=50) == 50 and MC.steps_for(250, 2.0) == 500
+
+
+def test_reference_front_end_sobol_and_bridge(golden, garr):
+    np.testing.assert_array_equal(MC.generate_sobol_normals(100, 12, seed=3), garr["sobol_100x12_seed3"])
+    for k, want in golden["cases"]["bb_order"].items():
+        assert MC._bb_ordering(int(k)) == want
+    np.testing.assert_allclose(MC.brownian_bridge_reorder(garr["bb_in"], 31), garr["bb_out"], rtol=1e-13, atol=1e-16)
+    Z = MC._reference_draws(42, 64, 20, use_sobol=False)
+    Zo = O.draw_pcg64(42, 64, 20)
+    for a, b in zip(Z, Zo):
+        np.testing.assert_array_equal(a, b)
+    Z = MC._reference_draws(5, 64, 12, use_sobol=True)
+    Zo = O.draw_sobol(5, 64, 12)
+    for a, b in zip(Z, Zo):
+        np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("anti", [False, True])
+@pytest.mark.parametrize("cv", [False, True])
+@pytest.mark.parametrize("is_call", [True, False])
+@pytest.mark.parametrize("pname", ["svj_default", "gbm_cfg1"])
+def test_price_dict_from_sums_equals_oracle(golden, anti, cv, is_call, pname):
+    p = P(golden, pname)
+    n, steps, seed = 3000, 252, 11
+    spot, K, T = 22500.0, 22000.0, 0.25
+    eng = MonteCarloEngine(p, n, steps, seed, use_sobol=False, use_antithetic=anti, use_control_variate=cv,
+                           rng="philox", handle=OracleBackedHandle())
+    got = eng.price(spot, K, T, is_call)
+    want = O.MonteCarloOracle(p, n, steps, seed, False, anti, cv).price(spot, K, T, is_call)
+    assert set(want) <= set(got)
+    for k, w in want.items():
+        assert got[k] == pytest.approx(w, rel=1e-9, abs=2e-7), k        # abs: the degenerate SE == 0 case (quirk 2)
+    assert {"price_cv_spot", "std_error_cv_spot"} <= set(got)
+
+
+def test_price_batch_from_sums_equals_oracle(golden):
+    p = P(golden, "svj_default")
+    ks = np.array([21000.0, 22500.0, 24000.0])
+    for anti, cv in [(True, True), (False, True), (True, False)]:
+        eng = MonteCarloEngine(p, 2048, 252, 7, use_sobol=False, use_antithetic=anti, use_control_variate=cv,
+                               rng="philox", handle=OracleBackedHandle())
+        got = eng.price_batch(22500.0, ks, 0.25, True)
+        want = O.MonteCarloOracle(p, 2048, 252, 7, False, anti, cv).price_batch(22500.0, ks, 0.25, True)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert set(g) == set(w)
+            for k in w:
+                assert g[k] == pytest.approx(w[k], rel=1e-9, abs=1e-9)
+
+
+@pytest.mark.parametrize("is_call", [True, False])
+def test_greeks_from_sums_equal_oracle(golden, is_call):
+    p = P(golden, "svj_default")
+    n, steps, seed = 2048, 252, 42
+    h = OracleBackedHandle()
+    g = GreeksEngine(p, n, steps, seed, rng="philox", handle=h)
+    o = O.GreeksOracle(p, n, steps, seed)
+    args = (22500.0, 22500.0, 0.25, is_call)
+    for name in ("delta", "vega", "gamma"):
+        got, want = getattr(g, name)(*args), getattr(o, name)(*args)
+        for k, w in want.items():
+            assert got[k] == pytest.approx(w, rel=1e-8, abs=1e-10), (name, k)
+    assert h.calls == 1          # ONE fused launch served delta, vega and gamma (the reference runs 9 simulations)
+
+
+def test_int_spot_is_cast_to_float(golden):
+    """Documented divergence from the reference (quirk 3): an int spot must not truncate the paths."""
+    p = P(golden, "gbm_cfg1")
+    eng = MonteCarloEngine(p, 500, 50, 3, use_sobol=False, rng="philox", handle=OracleBackedHandle())
+    a, b = eng.price(2500, 2500, 1.0), eng.price(2500.0, 2500.0, 1.0)
+    assert a["price"] == b["price"]
+
+
+def test_shard_range_partitions_the_paths():
+    for n, w in [(10, 3), (7, 8), (10_000_000, 8), (1, 2), (0, 4)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_sums_single_rank_is_identity(golden):
+    p = P(golden, "gbm_cfg1")
+    h = OracleBackedHandle()
+    whole = h.price_european(p, 100.0, 0.5, 20, 600, 9, [95.0, 105.0], True, _lib.ANTITHETIC)
+    got = sharded_sums(h, Comm(), p, 100.0, 0.5, 20, 600, 9, [95.0, 105.0], True, _lib.ANTITHETIC)
+    np.testing.assert_array_equal(whole, got)
+
+
+def test_patch_reference_rebinds_import_by_name_sites():
+    from monte_carlo_option_simulator_b200 import patch_reference
+    pkg = types.ModuleType("fakeengine")
+    pkg.__path__ = []
+    mods = {}
+    for name, attrs in {"monte_carlo": ["_simulate_svj_paths_numba", "MonteCarloEngine", "bs_price", "bs_delta"],
+                        "greeks": ["_simulate_svj_paths_numba", "MonteCarloEngine", "GreeksEngine"],
+                        "risk": ["MonteCarloEngine", "compute_risk_metrics"],
+                        "calibration": ["MonteCarloEngine"],
+                        "app": ["MonteCarloEngine", "GreeksEngine", "StressTestEngine"]}.items():
+        m = types.ModuleType(f"fakeengine.{name}")
+        for a in attrs:
+            setattr(m, a, object())
+        mods[name] = m
+        sys.modules[f"fakeengine.{name}"] = m
+    sys.modules["fakeengine"] = pkg
+    try:
+        done = patch_reference("fakeengine")
+        assert mods["monte_carlo"].MonteCarloEngine is MonteCarloEngine
+        assert mods["greeks"]._simulate_svj_paths_numba is MC._simulate_svj_paths_numba
+        assert mods["greeks"].GreeksEngine is GreeksEngine
+        assert mods["risk"].MonteCarloEngine is MonteCarloEngine
+        assert mods["calibration"].MonteCarloEngine is MonteCarloEngine
+        assert mods["app"].GreeksEngine is GreeksEngine
+        assert not isinstance(mods["app"].StressTestEngine, type)       # caller class: left alone
+        assert len(done) == 12
+    finally:
+        for k in list(sys.modules):
+            if k.startswith("fakeengine"):
+                del sys.modules[k]
+
+
+def test_engine_rejects_unknown_modes():
+    with pytest.raises(ValueError):
+        MonteCarloEngine(SVJParams(), rng="mt19937")
+    with pytest.raises(ValueError):
+        MonteCarloEngine(SVJParams(), precision="fp16")
