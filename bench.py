@@ -130,6 +130,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is entitled to every host thread
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sample = 50_000
     steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 2))
