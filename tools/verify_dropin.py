@@ -1,0 +1,88 @@
+"""Drop-in check against a checkout of the reference (NOT part of the test suite: the GPU box has no reference).
+
+    python tools/verify_dropin.py /path/to/Monte-Carlo-Option-Simulator
+
+1. runs the reference's own verify.py unpatched (Numba CPU path) and keeps its prices;
+2. patches the reference with patch_reference("engine") and runs verify.py again on the GPU -- it must print
+   "ALL TESTS PASSED";
+3. exercises the callers the north star names with the patched engine: the FastAPI handlers /api/price, /api/greeks,
+   /api/smile, /api/stress (called as coroutines), StressTestEngine, one calibration objective evaluation, and
+   compares patched and unpatched prices within Monte Carlo error.
+"""
+import asyncio
+import contextlib
+import io
+import math
+import os
+import runpy
+import sys
+import time
+
+ref = os.path.abspath(sys.argv[1])
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+sys.path.insert(0, ref)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def run_verify():
+    buf = io.StringIO()
+    t0 = time.time()
+    with contextlib.redirect_stdout(buf):
+        runpy.run_path(os.path.join(ref, "verify.py"), run_name="__main__")
+    return buf.getvalue(), time.time() - t0
+
+
+out_cpu, t_cpu = run_verify()
+assert "ALL TESTS PASSED" in out_cpu
+print(f"[unpatched] verify.py: ALL TESTS PASSED in {t_cpu:.1f} s")
+
+import engine.app  # noqa: E402  (imports every engine module)
+import engine.calibration  # noqa: E402
+from engine.models import SVJParams  # noqa: E402
+from engine.monte_carlo import MonteCarloEngine as RefEngine  # noqa: E402
+
+svj = SVJParams()
+ref_price = RefEngine(svj, num_paths=50_000, use_sobol=False, use_control_variate=False).price(22500.0, 22500.0, 0.25, True)
+
+from monte_carlo_option_simulator_b200 import patch_reference  # noqa: E402
+done = patch_reference("engine")
+print(f"[patch] rebound {len(done)} names: {', '.join(done)}")
+
+out_gpu, t_gpu = run_verify()
+print(out_gpu)
+assert "ALL TESTS PASSED" in out_gpu and "FAIL" not in out_gpu
+print(f"[patched] verify.py: ALL TESTS PASSED in {t_gpu:.1f} s (unpatched {t_cpu:.1f} s)")
+
+from engine.monte_carlo import MonteCarloEngine  # noqa: E402
+assert MonteCarloEngine is not RefEngine
+ours = MonteCarloEngine(svj, num_paths=2_000_000, use_sobol=False, use_control_variate=False).price(22500.0, 22500.0, 0.25, True)
+z = abs(ours["price"] - ref_price["price"]) / math.hypot(ours["std_error"], ref_price["std_error"])
+print(f"[price] reference {ref_price['price']:.3f} +- {ref_price['std_error']:.3f} (50k paths, CPU)   "
+      f"patched {ours['price']:.3f} +- {ours['std_error']:.3f} (2M paths, GPU)   |z| = {z:.2f}")
+assert z < 3.5
+
+app = engine.app
+calls = (("price", app.price_option, app.PriceRequest(spot=22500.0, strike=22500.0, T=0.08, num_paths=50_000)),
+         ("greeks", app.compute_greeks, app.GreeksRequest(spot=22500.0, strike=22500.0, T=0.08, num_paths=50_000)),
+         ("stress", app.run_stress, app.StressRequest(spot=22500.0, strike=22500.0, T=0.08, num_paths=50_000)),
+         ("smile", app.generate_smile, app.SmileRequest(spot=22500.0, T=0.08)),
+         ("hedge", app.run_hedge_backtest, app.HedgeRequest(spot=22500.0, strike=22500.0, T=0.04, num_scenarios=20)))
+for name, handler, req in calls:
+    t0 = time.time()
+    res = asyncio.run(handler(req))
+    keys = list(res.keys()) if isinstance(res, dict) else type(res).__name__
+    print(f"[api] /api/{name}: {time.time() - t0:.2f} s, keys {keys}")
+
+t0 = time.time()
+import numpy as np  # noqa: E402
+obj = engine.calibration._heston_objective(np.array([3.0, 0.04, 0.5, -0.7, 0.04]), 22500.0,
+                                           np.array([22000.0, 22500.0, 23000.0]), 0.08,
+                                           np.array([700.0, 420.0, 230.0]), np.array([1 / 3, 1 / 3, 1 / 3]), 0.065, 0.012,
+                                           True, num_paths=20_000, num_steps=100)
+print(f"[calibration] _heston_objective -> {obj} in {time.time() - t0:.2f} s")
+
+from engine.risk import StressTestEngine  # noqa: E402
+t0 = time.time()
+rep = StressTestEngine(svj, num_paths=200_000).full_stress_report(22500.0, 22500.0, 0.08, True)
+print(f"[stress] full_stress_report: {time.time() - t0:.2f} s, sections {list(rep.keys())}")
+print("DROP-IN OK")
