@@ -199,6 +199,12 @@ int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t path_offset, i
 int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
                        int32_t n_blocks, uint32_t stream, uint32_t *out);
 
+/* Raw moments of the normals the GBM stream produces for paths [path_offset, path_offset + n_paths) x n_blocks
+ * Philox blocks (8 normals each), accumulated in fp64: out = { count, sum z, sum z^2, sum z^3, sum z^4, sum z_a z_b over
+ * the two members of each Box-Muller pair }.  The statistical certificate of the generator (tools/normal_moments.py). */
+int b200mc_normal_moments(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths, int32_t n_blocks,
+                          double out[6]);
+
 /* ---- device memory helpers for callers without a CUDA runtime of their own (ctypes) ---------------------- */
 int b200mc_malloc(b200mc_handle *h, size_t bytes, void **dev_ptr);
 int b200mc_free(b200mc_handle *h, void *dev_ptr);

@@ -83,6 +83,7 @@ _PROTOS = {
     "b200mc_risk_metrics": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dbl, _dp]),
     "b200mc_dump_normals": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, C.c_int, _vp]),
     "b200mc_dump_philox": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, _vp]),
+    "b200mc_normal_moments": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _dp]),
     "b200mc_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "b200mc_free": (C.c_int, [_vp, _vp]),
     "b200mc_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
@@ -303,6 +304,12 @@ class Handle:
         out = np.empty((n_paths, n_steps), dtype=np.float64)
         self._check(self.lib.b200mc_dump_normals(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths),
                                                   int(n_steps), int(stream), int(which), out.ctypes.data))
+        return out
+
+    def normal_moments(self, seed, n_paths, n_blocks, path_offset=0) -> np.ndarray:
+        out = np.empty(6, dtype=np.float64)
+        self._check(self.lib.b200mc_normal_moments(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths),
+                                                    int(n_blocks), out.ctypes.data_as(_dp)))
         return out
 
     def dump_philox(self, seed, n_paths, n_blocks, stream, path_offset=0) -> np.ndarray:

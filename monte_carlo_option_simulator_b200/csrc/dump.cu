@@ -69,8 +69,57 @@ __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, i
     }
 }
 
+// Raw moments of the normals of the GBM stream over paths x blocks (8 draws per block), fp64 accumulation: the
+// statistical certificate of the generator (tools/normal_moments.py).  out[0..5] = sum z^k, k = 0..4, and sum z_a z_b
+// over the two members of every Box-Muller pair.
+__global__ void __launch_bounds__(256)
+k_normal_moments(const __grid_constant__ PhiloxKey key, uint64_t path0, int64_t n_paths, int n_blocks, double *partials,
+                 unsigned int *counter, double *out)
+{
+    __shared__ double smem[(256 / 32) * 6];
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * 256) {
+        const uint64_t path = path0 + (uint64_t)i;
+        for (int j = 0; j < n_blocks; ++j) {
+            const U4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)j, B200MC_STREAM_GBM, key);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const BM2 b = box_muller_word(ww[t]);
+                const double a = B200MC_BM_SCALE * (double)b.rc, c = B200MC_BM_SCALE * (double)b.rs;
+                const double a2 = a * a, c2 = c * c;
+                v[0] += 2.0;
+                v[1] += a + c;
+                v[2] += a2 + c2;
+                v[3] += a2 * a + c2 * c;
+                v[4] += a2 * a2 + c2 * c2;
+                v[5] += a * c;
+            }
+        }
+    }
+    block_finish<6>(v, smem, partials, counter, out);
+}
+
 } // namespace b200mc
 using namespace b200mc;
+
+extern "C" int b200mc_normal_moments(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
+                                     int32_t n_blocks, double out[6])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out || n_paths <= 0 || n_blocks <= 0) return fail(h, B200MC_EINVAL, "bad argument");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const int grid = h->sm_count * 8;
+    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, (size_t)(grid + 1) * 6 * 8));
+    double *partials = (double *)h->d_scratch, *res = partials + (size_t)grid * 6;
+    k_normal_moments<<<grid, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_blocks, partials,
+                                                  h->d_counter, res);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(out, res, 48, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
 
 extern "C" int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
                                   int32_t n_blocks, uint32_t stream, uint32_t *out)
