@@ -28,8 +28,8 @@
  *   B200MC_STREAM_HESTON block j -> steps 4j..4j+3: word i gives (Z1, Z2) of step 4j+i
  *   B200MC_STREAM_SVJ    block j -> steps 2j, 2j+1: (w0 -> (Z1,Z2), w1 -> U_jump), (w2 -> (Z1,Z2), w3 -> U_jump);
  *                        U_jump = (w + 0.5) / 2^32
- *   B200MC_STREAM_JUMP   block s -> word 0 gives Z_jump_size of step s = normcdfinv(((w >> 8) + 0.5) / 2^24)
- *                        (internal to the SVJ mode; drawn only when the jump fires)
+ *                        the jump fires iff U_jump < lambda_j dt and, given that, U_jump / (lambda_j dt) is uniform on
+ *                        (0,1): Z_jump_size = normcdfinv(U_jump / (lambda_j dt)) -- the same word sizes the jump
  * b200mc_dump_normals returns exactly the values the fused kernels use, so the reference (or the oracle) can be
  * fed identical draws.
  */
@@ -61,7 +61,6 @@ extern "C" {
 #define B200MC_STREAM_GBM    0u
 #define B200MC_STREAM_HESTON 1u
 #define B200MC_STREAM_SVJ    2u
-#define B200MC_STREAM_JUMP   3u
 
 /* which array b200mc_dump_normals returns */
 #define B200MC_Z1         0
@@ -191,10 +190,11 @@ int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n, int dtype,
                         double confidence, double out[8]);
 
 /* ---- draws, for feeding the reference the identical numbers ----------------------------------------------
- * out is float64 [n_paths, n_steps] on the host; `stream` one of B200MC_STREAM_*; `which` one of B200MC_Z*.
+ * out is float64 [n_paths, n_steps] on the host; `stream` one of B200MC_STREAM_*; `which` one of B200MC_Z*;
+ * jump_prob = lambda_j * T / n_steps of the run to be reproduced (used only for B200MC_ZJUMP_SIZE of the SVJ stream).
  * Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0). */
 int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
-                        int32_t n_steps, uint32_t stream, int which, double *out);
+                        int32_t n_steps, uint32_t stream, int which, double jump_prob, double *out);
 /* Raw Philox words uint32 [n_paths, n_blocks, 4] (host), for the bit-exact check against the oracle. */
 int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
                        int32_t n_blocks, uint32_t stream, uint32_t *out);

@@ -81,7 +81,7 @@ _PROTOS = {
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                          _u32, C.c_int, C.c_int, _vp, _i64]),
     "b200mc_risk_metrics": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dbl, _dp]),
-    "b200mc_dump_normals": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, C.c_int, _vp]),
+    "b200mc_dump_normals": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, C.c_int, _dbl, _vp]),
     "b200mc_dump_philox": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, _vp]),
     "b200mc_normal_moments": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _dp]),
     "b200mc_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -300,10 +300,12 @@ class Handle:
                                                   out.ctypes.data_as(_dp)))
         return out
 
-    def dump_normals(self, seed, n_paths, n_steps, stream, which, path_offset=0) -> np.ndarray:
+    def dump_normals(self, seed, n_paths, n_steps, stream, which, path_offset=0, jump_prob=0.0) -> np.ndarray:
+        """jump_prob = lambda_j * T / n_steps of the run being reproduced (only Z_jump_size of the SVJ stream uses it)."""
         out = np.empty((n_paths, n_steps), dtype=np.float64)
         self._check(self.lib.b200mc_dump_normals(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths),
-                                                  int(n_steps), int(stream), int(which), out.ctypes.data))
+                                                  int(n_steps), int(stream), int(which), float(jump_prob),
+                                                  out.ctypes.data))
         return out
 
     def normal_moments(self, seed, n_paths, n_blocks, path_offset=0) -> np.ndarray:

@@ -4,8 +4,8 @@
 // b200mc_dump_normals returns, as float64 [n_paths, n_steps], exactly the values the fused kernels consume:
 //   Z1 / Z2        BM_SCALE * (double)raw   with raw the fp32 Box-Muller output of philox.cuh
 //   Z_jump         (w + 0.5) / 2^32                                   (SVJ stream; 1.0 = "never jumps" elsewhere)
-//   Z_jump_size    (double)normcdfinvf(((w >> 8) + 0.5) / 2^24)       (SVJ stream, every step -- the fused kernel
-//                  draws it only when the jump fires, from the same counter; 0 elsewhere)
+//   Z_jump_size    (double)normcdfinvf(U_jump / jump_prob) where the jump fires (U_jump < jump_prob = lambda_j dt),
+//                  0 elsewhere -- the reference only reads it where the jump fires (monte_carlo.py:233-234)
 // Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0).
 #include "common.cuh"
 
@@ -24,7 +24,7 @@ __global__ void k_dump_philox(PhiloxKey key, uint64_t path0, int64_t n_paths, in
 }
 
 __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_steps, uint32_t stream, int which,
-                               double *__restrict__ out)
+                               double jump_prob, double *__restrict__ out)
 {
     const int per = stream == B200MC_STREAM_GBM ? 8 : (stream == B200MC_STREAM_HESTON ? 4 : 2);
     const int n_blocks = (n_steps + per - 1) / per;
@@ -56,9 +56,9 @@ __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, i
                 if (which == B200MC_Z1) vals[t] = B200MC_BM_SCALE * (double)b.rc;
                 else if (which == B200MC_Z2) vals[t] = B200MC_BM_SCALE * (double)b.rs;
                 else if (which == B200MC_ZJUMP_U) vals[t] = jump_uniform(ww[2 * t + 1]);
-                else {
-                    const U4 uj = philox4x32_10(c0, c1, (uint32_t)(blk * 2 + t), B200MC_STREAM_JUMP, key);
-                    vals[t] = (double)jump_size_normal(uj.x);
+                else {   // defined where the jump fires (U < jump_prob); 0 elsewhere (the reference never reads it there)
+                    const bool fired = jump_uniform(ww[2 * t + 1]) < jump_prob;
+                    vals[t] = fired ? (double)jump_size_normal(ww[2 * t + 1], 1.0 / (jump_prob * 4294967296.0)) : 0.0;
                 }
             }
         }
@@ -139,7 +139,7 @@ extern "C" int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path
 }
 
 extern "C" int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
-                                   int32_t n_steps, uint32_t stream, int which, double *out)
+                                   int32_t n_steps, uint32_t stream, int which, double jump_prob, double *out)
 {
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
     if (!out || n_paths <= 0 || n_steps <= 0) return fail(h, B200MC_EINVAL, "bad argument");
@@ -149,7 +149,7 @@ extern "C" int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t pat
     const size_t bytes = (size_t)n_paths * n_steps * 8;
     B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, bytes));
     k_dump_normals<<<h->sm_count * 4, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_steps, stream,
-                                                           which, (double *)h->d_stage);
+                                                           which, jump_prob, (double *)h->d_stage);
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
     B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));

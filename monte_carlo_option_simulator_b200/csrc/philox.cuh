@@ -122,11 +122,12 @@ __device__ __forceinline__ double jump_uniform(uint32_t w)
     return ((double)w + 0.5) * 2.3283064365386963e-10;
 }
 
-// jump-size standard normal from one word (only evaluated when a jump fires): inverse normal CDF of a
-// 24-bit uniform strictly inside (0,1)
-__device__ __forceinline__ float jump_size_normal(uint32_t w)
+// jump-size standard normal from the jump word itself (only evaluated when the jump fired, i.e. w < jump_thr):
+// conditional on the event, (w + 0.5) * scale with scale = 1 / (lambda dt 2^32) is uniform on (0, 1).
+__device__ __forceinline__ float jump_size_normal(uint32_t w, double scale)
 {
-    const float u = ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    float u = (float)(((double)w + 0.5) * scale);
+    u = fminf(fmaxf(u, 2.9802322387695312e-08f), 0.99999994f);
     return normcdfinvf(u);
 }
 

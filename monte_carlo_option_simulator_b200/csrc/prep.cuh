@@ -42,6 +42,8 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
     m.half_dt = 0.5 * dt;
     m.sqrt_dt_s = sqrt_dt * B200MC_BM_SCALE;
     m.kappa_dt = p->kappa * dt;
+    m.one_m_kdt = 1.0 - p->kappa * dt;
+    m.kdt_theta = p->kappa * dt * p->theta;
     m.theta = p->theta;
     m.xi_sqrt_dt_s = p->xi * sqrt_dt * B200MC_BM_SCALE;
     m.rho = p->rho;
@@ -53,6 +55,7 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
         if (!(lim > 0.0)) m.jump_thr = 0;
         else if (lim >= 4294967296.0) m.jump_thr = 4294967296ull;
         else m.jump_thr = (uint64_t)ceil(lim);
+        m.jump_scale = m.jump_thr ? 1.0 / (p->lambda_j * dt * 4294967296.0) : 0.0;
     }
     m.v0[0] = p->v0;
     m.v0[1] = (flags & B200MC_GREEKS) ? bumps->v0_up : p->v0;

@@ -29,6 +29,9 @@ struct ModelArgs {
     double half_dt;         // dt / 2
     double sqrt_dt_s;       // sqrt(dt) * BM_SCALE  (the draws are unscaled, see philox.cuh)
     double kappa_dt, theta;
+    double one_m_kdt;       // 1 - kappa dt
+    double kdt_theta;       // kappa dt theta
+    double jump_scale;      // 1 / (lambda_j dt 2^32): (w + 0.5) * jump_scale is uniform on (0,1) GIVEN that the jump fired
     double xi_sqrt_dt_s;    // xi sqrt(dt) BM_SCALE
     double rho, crho;       // crho = sqrt(1 - rho^2)                        :227
     double mu_j, sigma_j;
@@ -40,10 +43,10 @@ struct ModelArgs {
 };
 
 template <typename R> struct Consts {
-    R drift_dt, half_dt, sqrt_dt_s, kappa_dt, theta, xi_sqrt_dt_s, rho, crho, mu_j, sigma_j;
+    R drift_dt, half_dt, sqrt_dt_s, one_m_kdt, kdt_theta, xi_sqrt_dt_s, rho, crho, mu_j, sigma_j;
     __device__ __forceinline__ explicit Consts(const ModelArgs &m)
-        : drift_dt((R)m.drift_dt), half_dt((R)m.half_dt), sqrt_dt_s((R)m.sqrt_dt_s), kappa_dt((R)m.kappa_dt),
-          theta((R)m.theta), xi_sqrt_dt_s((R)m.xi_sqrt_dt_s), rho((R)m.rho), crho((R)m.crho),
+        : drift_dt((R)m.drift_dt), half_dt((R)m.half_dt), sqrt_dt_s((R)m.sqrt_dt_s), one_m_kdt((R)m.one_m_kdt),
+          kdt_theta((R)m.kdt_theta), xi_sqrt_dt_s((R)m.xi_sqrt_dt_s), rho((R)m.rho), crho((R)m.crho),
           mu_j((R)m.mu_j), sigma_j((R)m.sigma_j) {}
 };
 
@@ -61,28 +64,28 @@ template <bool ANTI, bool GREEKS> struct StateLayout {
     static constexpr int DN_IDX = UP_IDX + 1;
 };
 
-// One stochastic-variance step for all states.  z1, z2 are UNSCALED draws (scale folded in the constants).
+// One stochastic-variance step for all states.  z1, zc are UNSCALED draws (zc = rho z1 + sqrt(1-rho^2) z2; the Box-Muller
+// scale is folded in the constants).  Lean form of monte_carlo.py:223-238:
+//   * the constant drift (r - q - lambda k) dt is NOT added here: n_steps * drift_dt is added once at the end;
+//   * v is carried unclamped -- the clamp of :238 is the max(v, 0) of :223 at the next step (and of the final v_T);
+//   * jumps are added by the caller inside the (rare) branch that detects them.
+// 7 FP32 + 1 MUFU per state and step.
 template <typename R, bool ANTI, bool GREEKS>
 __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R (&v)[StateLayout<ANTI, GREEKS>::NS],
-                                        const Consts<R> &c, R z1, R zc, R jmu, R jsz)
+                                        const Consts<R> &c, R z1, R zc)
 {
     constexpr int NS = StateLayout<ANTI, GREEKS>::NS;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const bool neg = ANTI && k == 1;
-        const R vp = rmax(v[k], (R)0);
-        const R sv = rsqrt_of(vp);
+        const bool neg = ANTI && k == 1;                 // twin: -Z1, -Z2  (:323)
+        const R vp = rmax(v[k], (R)0);                   // :223
+        const R sv = rsqrt_of(vp);                       // :224
         const R a = sv * c.sqrt_dt_s;                    // sqrt(v+) sqrt(dt)
-        const R d = c.drift_dt - c.half_dt * vp;         // :229
         const R b = sv * c.xi_sqrt_dt_s;
-        const R mr = vp + c.kappa_dt * (c.theta - vp);   // :237
-        if (neg) {
-            x[k] = x[k] + (d - a * z1 + (jmu - jsz));      // twin: -Z1, -Z2, same U, -Zjs  (:323)
-            v[k] = rmax(mr - b * zc, (R)0);
-        } else {
-            x[k] = x[k] + (d + a * z1 + (jmu + jsz));
-            v[k] = rmax(mr + b * zc, (R)0);
-        }
+        const R t = x[k] - c.half_dt * vp;               // :229 without the constant part
+        const R mr = vp * c.one_m_kdt + c.kdt_theta;     // v+ + kappa (theta - v+) dt      :237
+        x[k] = neg ? t - a * z1 : t + a * z1;            // :230,236
+        v[k] = neg ? mr - b * zc : mr + b * zc;          // :237
     }
 }
 
@@ -90,8 +93,9 @@ __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R
 // every 32-bit output word w yields one Box-Muller pair (rc, rs) = box_muller_word(w):
 //   GBM / DETVAR  stream 0, block j -> steps 8j..8j+7: word i gives the normals of steps 8j+2i (rc) and 8j+2i+1 (rs)
 //   HESTON        stream 1, block j -> steps 4j..4j+3: word i gives (Z1, Z2) = (rc, rs) of step 4j+i
-//   SVJ           stream 2, block j -> steps 2j, 2j+1: (w0 -> (Z1, Z2), w1 -> U_jump) and (w2, w3) likewise;
-//                 stream 3, block s -> word 0 gives Z_jump_size of step s (drawn only when the jump fires)
+//   SVJ           stream 2, block j -> steps 2j, 2j+1: (w0 -> (Z1, Z2), w1 -> U_jump) and (w2, w3) likewise; the jump
+//                 fires iff U_jump = (w + 0.5) / 2^32 < lambda dt, and GIVEN that, U_jump / (lambda dt) is uniform on
+//                 (0,1): Z_jump_size = normcdfinv(U_jump / (lambda dt)) -- no second draw
 //
 // Simulates global path `path` to T.  On return xT[k] = log(S_T / S0) of state k and vT[k] its variance
 // (GBM / DETVAR: vT is left untouched); sumz_out = sum of the raw draws (GBM only; feeds the pathwise vega).
@@ -193,6 +197,7 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
 #pragma unroll
         for (int k = 0; k < NS; ++k) { x[k] = (R)0; v[k] = (R)m.v0[0]; }
         if constexpr (GREEKS) { v[L::UP_IDX] = (R)m.v0[1]; v[L::DN_IDX] = (R)m.v0[2]; }
+        R dacc = (R)0;                                   // running constant drift, only for the path store
         if constexpr (MODE == MODE_HESTON) {
             const int nblk = (n_steps + 3) >> 2;
             for (int j = 0; j < nblk; ++j) {
@@ -202,8 +207,8 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                 for (int t = 0; t < 4; ++t) {
                     if (t == 0 || 4 * j + t < n_steps) {
                         const BM2 b = box_muller_word(ww[t]);
-                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs, (R)0, (R)0);
-                        if constexpr (Rec::enabled) rec(4 * j + t, x[0]);
+                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs);
+                        if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(4 * j + t, x[0] + dacc); }
                     }
                 }
             }
@@ -217,17 +222,22 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                     const int s = 2 * j + t;
                     if (t == 0 || s < n_steps) {
                         const BM2 b = box_muller_word(wz[t]);
-                        R jmu = (R)0, jsz = (R)0;
-                        if ((uint64_t)wu[t] < m.jump_thr) {                          // :233-234
-                            const U4 uj = philox4x32_10(c0, c1, (uint32_t)s, B200MC_STREAM_JUMP, key);
-                            jmu = c.mu_j;
-                            jsz = c.sigma_j * (R)jump_size_normal(uj.x);
+                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs);
+                        if ((uint64_t)wu[t] < m.jump_thr) {                              // :233-234, rare
+                            // given that it fired, the same word is uniform on (0, jump_thr): it also sizes the jump
+                            const R jsz = c.sigma_j * (R)jump_size_normal(wu[t], m.jump_scale);
+#pragma unroll
+                            for (int k = 0; k < NS; ++k) x[k] += (ANTI && k == 1) ? c.mu_j - jsz : c.mu_j + jsz;
                         }
-                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs, jmu, jsz);
-                        if constexpr (Rec::enabled) rec(s, x[0]);
+                        if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }
                     }
                 }
             }
+        }
+        {
+            const R total_drift = (R)((double)n_steps * m.drift_dt);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { x[k] += total_drift; v[k] = rmax(v[k], (R)0); }
         }
         sumz_out = (R)0;
 #pragma unroll

@@ -68,10 +68,13 @@ def test_normals_are_standard(H, L):
     z1 = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.Z1)
     z2 = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.Z2)
     u = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_U)
-    zj = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_SIZE)
+    zj = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_SIZE, jump_prob=0.25)
     assert abs(np.corrcoef(z1.ravel(), z2.ravel())[0, 1]) < 5 / math.sqrt(z1.size)
     assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 5 / math.sqrt(12 * u.size)
-    assert abs(zj.mean()) < 5 / math.sqrt(zj.size) and abs(zj.var() - 1) < 5 * math.sqrt(2 / zj.size)
+    zf = zj[u < 0.25]                    # jump sizes exist where the jump fires (U < jump_prob) and are N(0,1) there
+    assert abs(zf.size / u.size - 0.25) < 0.01 and np.all(zj[u >= 0.25] == 0)
+    assert abs(zf.mean()) < 5 / math.sqrt(zf.size) and abs(zf.var() - 1) < 5 * math.sqrt(2 / zf.size)
+    assert abs(np.corrcoef(zf, z1[u < 0.25])[0, 1]) < 5 / math.sqrt(zf.size)
 
 
 # ---------------------------------------------------------------------------------------------- a1: given normals
@@ -147,8 +150,12 @@ def _mode_params(golden, mode):
     return P(golden, "svj_default"), 2
 
 
-def _draws(H, L, seed, n, steps, stream, off=0):
-    return [H.dump_normals(seed, n, steps, stream, w, path_offset=off) for w in (L.Z1, L.Z2, L.ZJUMP_U, L.ZJUMP_SIZE)]
+def _draws(H, L, seed, n, steps, stream, off=0, p=None, T=None):
+    """The four arrays the reference kernel consumes, exactly as the fused kernels draw them.  jump_prob (needed for
+    the jump sizes of the SVJ stream) is lambda_j * (T / steps), computed in the library's own order."""
+    jp = p.lambda_j * (T / steps) if p is not None else 0.0
+    return [H.dump_normals(seed, n, steps, stream, w, path_offset=off, jump_prob=jp)
+            for w in (L.Z1, L.Z2, L.ZJUMP_U, L.ZJUMP_SIZE)]
 
 
 @pytest.mark.parametrize("mode", ["gbm", "detvar", "heston", "svj"])
@@ -157,7 +164,7 @@ def test_fused_terminal_identical_draws(H, L, golden, mode, steps):
     """north_star deterministic mode: the reference recurrence (oracle) fed the IDENTICAL draws."""
     p, stream = _mode_params(golden, mode)
     n, seed, off, T, S0 = 1500, 99, 12345, 0.8, 2500.0
-    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, stream, off)
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, stream, off, p, T)
     So, vo, _ = O._sim(p, S0, T, Z1, Z2, Zj, Zjs, steps)
     Sao = O._sim(p, S0, T, -Z1, -Z2, Zj, -Zjs, steps)[0]
     S, A, V = H.simulate_terminal(p, S0, T, steps, n, seed, L.ANTITHETIC | L.FP64, np.float64, off, True, True)
@@ -175,8 +182,13 @@ def test_fused_jumps_fire_like_reference(H, L, golden):
     """A jump-heavy parameter set: the integer jump test in the kernel must equal the reference's float compare."""
     p = P(golden, "jumpy")
     n, steps, seed = 4000, 40, 5
-    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, 2)
-    assert (Zj < p.lambda_j * 0.5 / steps).sum() > 100
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, 2, 0, p, 0.5)
+    fired = Zj < p.lambda_j * (0.5 / steps)
+    assert fired.sum() > 100
+    # jump sizes are standard normal where the jump fires, and are never consulted elsewhere
+    zs = Zjs[fired]
+    assert abs(zs.mean()) < 4 / math.sqrt(zs.size) and abs(zs.var() - 1) < 5 * math.sqrt(2 / zs.size)
+    assert np.all(Zjs[~fired] == 0.0)
     So = O._sim(p, 100.0, 0.5, Z1, Z2, Zj, Zjs, steps)[0]
     S = H.simulate_terminal(p, 100.0, 0.5, steps, n, seed, L.FP64, np.float64)[0]
     np.testing.assert_allclose(S, So, rtol=1e-10)
@@ -185,7 +197,7 @@ def test_fused_jumps_fire_like_reference(H, L, golden):
 def test_force_svj_on_gbm_params(H, L, golden):
     p, _ = _mode_params(golden, "gbm")
     n, steps, seed = 512, 30, 3
-    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, 2)
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, 2, 0, p, 1.0)
     So = O._sim(p, 2500.0, 1.0, Z1, Z2, Zj, Zjs, steps)[0]
     S = H.simulate_terminal(p, 2500.0, 1.0, steps, n, seed, L.FP64 | L.FORCE_SVJ, np.float64)[0]
     np.testing.assert_allclose(S, So, rtol=1e-10)
@@ -229,7 +241,7 @@ def test_fused_greek_sums_vs_oracle(H, L, golden, mode, is_call):
     reference's CRN construction, greeks.py:65-80,:124-147)."""
     p, stream = _mode_params(golden, mode)
     n, steps, seed, S0, T, K, b = 2000, 40, 21, 2500.0, 0.5, 2450.0, 0.01
-    Z = _draws(H, L, seed, n, steps, stream)
+    Z = _draws(H, L, seed, n, steps, stream, 0, p, T)
     bumps = L.Bumps(b, p.v0 + 0.01, max(p.v0 - 0.01, 0.001), p.r + 1e-4, max(p.r - 1e-4, 0))
     row = H.price_european(p, S0, T, steps, n, seed, [K], is_call, L.FP64 | L.GREEKS, bumps)[0]
     col = {k: row[i] for i, k in enumerate(L.SUMS_FIELDS)}
@@ -426,7 +438,7 @@ def test_greeks_engine_philox_vs_black_scholes(golden):
 def test_generate_paths_identical_draws(H, L, golden, mode, n, steps):
     p, stream = _mode_params(golden, mode)
     seed, off, S0, T = 4, 1000, 2500.0, 1.0
-    Z = _draws(H, L, seed, n, steps, stream, off)
+    Z = _draws(H, L, seed, n, steps, stream, off, p, T)
     want = O._sim(p, S0, T, *Z, steps, record=True)[2]
     got = H.generate_paths(p, S0, T, steps, n, seed, L.FP64, np.float64, off)
     assert got.shape == (n, steps + 1) and np.all(got[:, 0] == S0)
