@@ -332,16 +332,38 @@ def run_b200(args):
             except Exception as e:  # noqa: BLE001
                 line["roofline_hbm"] = {"error": str(e)}
             extras = {}
-            for name, fl, pp in (("fp64_price_only", _lib.FP64, p), ("fp32_price_only", 0, p),
-                                 ("fp32_antithetic", _lib.ANTITHETIC, p)):
-                h.timer_begin()
-                h.price_european(pp, SPOT, T, N_STEPS, n, 7, [STRIKE], True, fl, None, out_dev=out.data_ptr())
-                extras[name] = n * N_STEPS / (h.timer_end() * 1e-3)
             from monte_carlo_option_simulator_b200 import SVJParams
-            for name, pp in (("fp32_heston", SVJParams(lambda_j=0.0)), ("fp32_svj", SVJParams())):
-                h.timer_begin()
-                h.price_european(pp, 22500.0, T, N_STEPS, n // 4, 7, [22500.0], True, _lib.ANTITHETIC, None, out_dev=out.data_ptr())
-                extras[name] = (n // 4) * N_STEPS / (h.timer_end() * 1e-3)
+
+            def rate(pp, spot, npaths, fl, ks):
+                best = None
+                for r in range(4):                                  # first call loads the kernel: not timed
+                    h.timer_begin()
+                    h.price_european(pp, spot, T, N_STEPS, npaths, 7 + r, ks, True, fl, None, out_dev=out_many.data_ptr())
+                    ms_ = h.timer_end()
+                    if r:
+                        best = ms_ if best is None else min(best, ms_)
+                return npaths * N_STEPS / (best * 1e-3)
+
+            out_many = torch.zeros(64 * _lib.NSUMS, dtype=torch.float64, device="cuda")
+            extras["fp32_price_only"] = rate(p, SPOT, n, 0, [STRIKE])
+            extras["fp32_antithetic"] = rate(p, SPOT, n, _lib.ANTITHETIC, [STRIKE])
+            extras["fp64_price_only"] = rate(p, SPOT, n, _lib.FP64, [STRIKE])
+            extras["fp32_64_strikes_shared_paths"] = rate(p, SPOT, n, _lib.ANTITHETIC, list(np.linspace(0.7, 1.3, 64) * SPOT))
+            extras["fp32_heston_antithetic"] = rate(SVJParams(lambda_j=0.0), 22500.0, n // 4, _lib.ANTITHETIC, [22500.0])
+            extras["fp32_svj_antithetic"] = rate(SVJParams(), 22500.0, n // 4, _lib.ANTITHETIC, [22500.0])
+            # BASELINE cfg3, API-parity reading: 64 strikes x 16 expiries, 1M paths per expiry shared across strikes
+            from monte_carlo_option_simulator_b200 import MonteCarloEngine
+            eng = MonteCarloEngine(p, 1_000_000, N_STEPS, 42, use_sobol=False, use_antithetic=False,
+                                   use_control_variate=False, rng="philox", handle=h)
+            ks, Ts = np.linspace(0.7, 1.3, 64) * SPOT, [j / 8 for j in range(1, 17)]
+            eng.price_grid(SPOT, ks, Ts, True)
+            t0 = time.perf_counter()
+            grid = eng.price_grid(SPOT, ks, Ts, True)
+            dtg = time.perf_counter() - t0
+            extras["cfg3_grid_64x16_1M_paths"] = 1_000_000 * float(grid["num_steps"].sum()) / dtg
+            line["cfg3_grid"] = {"seconds": dtg, "cells": 1024, "path_steps": 1_000_000 * int(grid["num_steps"].sum()),
+                                 "reading": "price_batch semantics: paths shared across the 64 strikes of an expiry",
+                                 "atm_1y_price": float(grid["prices"][7, 32])}
             line["extras_path_steps_per_s"] = extras
             v, cores, dt = cpu_reference_steps(2, 1, 50_000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

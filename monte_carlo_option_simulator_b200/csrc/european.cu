@@ -29,6 +29,7 @@ struct EuroArgs {
     double up_mul, dn_mul, rup_mul, rdn_mul;   // S_T multipliers of the spot and rate bumps
     double sigmaT;                             // sqrt(v0) T        (pathwise vega, GBM only)
     double w_scale;                            // sqrt(dt) BM_SCALE (W_T = w_scale * sum raw z)
+    double strikes[EU_THREADS];                // by value: no host->device copy, no stream sync on the call path
 };
 
 template <typename R> __device__ __forceinline__ R payoff(R s, R k, bool call)
@@ -36,37 +37,39 @@ template <typename R> __device__ __forceinline__ R payoff(R s, R k, bool call)
     return call ? rmax(s - k, (R)0) : rmax(k - s, (R)0);
 }
 
-// Adds one path's payoff terms for strike K into the fp64 accumulators (order = b200mc_sums after .n).
-template <int MODE, bool ANTI, bool GREEKS, typename R>
-__device__ __forceinline__ void accumulate(double (&acc)[NACC], const EuroArgs &a, R K, R S0, bool call, R sa, R sb,
+// Adds one path's payoff terms for strike K into the accumulators (order = b200mc_sums after .n).  A = double for the
+// per-thread running sums; A = float for the per-batch partials of the multi-strike fp32 kernels (at most 256 paths
+// are added in fp32 before the partial is folded into the fp64 sum, so the relative rounding error stays ~1e-7).
+template <int MODE, bool ANTI, bool GREEKS, typename R, typename A>
+__device__ __forceinline__ void accumulate(A (&acc)[NACC], const EuroArgs &a, R K, R S0, bool call, R sa, R sb,
                                            R s_up, R s_dn, R sumz)
 {
-    const double da = (double)payoff<R>(sa, K, call);
-    double db = 0.0, s_avg = (double)sa, pay = da;
+    const A da = (A)payoff<R>(sa, K, call);
+    A db = (A)0, s_avg = (A)sa, pay = da;
     if constexpr (ANTI) {
-        db = (double)payoff<R>(sb, K, call);
-        s_avg = 0.5 * ((double)sa + (double)sb);
-        pay = 0.5 * (da + db);
+        db = (A)payoff<R>(sb, K, call);
+        s_avg = (A)0.5 * ((A)sa + (A)sb);
+        pay = (A)0.5 * (da + db);
     }
     acc[0] += da;
     acc[1] += db;
-    acc[2] = fma(da, da, acc[2]);
-    acc[3] = fma(db, db, acc[3]);
-    acc[4] = fma(da, db, acc[4]);
+    acc[2] += da * da;
+    acc[3] += db * db;
+    acc[4] += da * db;
     acc[5] += s_avg;
-    acc[6] = fma(s_avg, s_avg, acc[6]);
-    acc[7] = fma(pay, s_avg, acc[7]);
+    acc[6] += s_avg * s_avg;
+    acc[7] += pay * s_avg;
     if constexpr (GREEKS) {
         const bool itm = call ? (sa > K) : (sa < K);                       // greeks.py:72,75
-        if (itm) acc[8] += (double)(sa / S0);
-        acc[9] += (double)payoff<R>(sa * (R)a.up_mul, K, call);
-        acc[10] += (double)payoff<R>(sa * (R)a.dn_mul, K, call);
-        acc[11] += (double)payoff<R>(s_up, K, call);
-        acc[12] += (double)payoff<R>(s_dn, K, call);
-        acc[13] += (double)payoff<R>(sa * (R)a.rup_mul, K, call);
-        acc[14] += (double)payoff<R>(sa * (R)a.rdn_mul, K, call);
+        if (itm) acc[8] += (A)(sa / S0);
+        acc[9] += (A)payoff<R>(sa * (R)a.up_mul, K, call);
+        acc[10] += (A)payoff<R>(sa * (R)a.dn_mul, K, call);
+        acc[11] += (A)payoff<R>(s_up, K, call);
+        acc[12] += (A)payoff<R>(s_dn, K, call);
+        acc[13] += (A)payoff<R>(sa * (R)a.rup_mul, K, call);
+        acc[14] += (A)payoff<R>(sa * (R)a.rdn_mul, K, call);
         if constexpr (MODE == MODE_GBM) {
-            if (itm) acc[15] += (double)sa * ((double)sumz * a.w_scale - a.sigmaT);
+            if (itm) acc[15] += (A)sa * ((A)sumz * (A)a.w_scale - (A)a.sigmaT);
         }
     }
 }
@@ -75,8 +78,7 @@ __device__ __forceinline__ void accumulate(double (&acc)[NACC], const EuroArgs &
 // inside the path loop.  Otherwise phase A / phase B as described at the top of the file.
 template <int MODE, bool ANTI, bool GREEKS, typename R, bool SINGLE>
 __global__ void __launch_bounds__(EU_THREADS)
-k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strikes_g,
-           const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
+k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
            double *__restrict__ out)
 {
     using L = StateLayout<ANTI, GREEKS>;
@@ -89,7 +91,7 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
     R *wtab = sW + (SINGLE ? 0 : EU_THREADS);                             // [3][wld] (DETVAR)
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < a.n_strikes; i += EU_THREADS) strikes[i] = strikes_g[i];
+    for (int i = tid; i < a.n_strikes; i += EU_THREADS) strikes[i] = a.strikes[i];
     if constexpr (MODE == MODE_DETVAR)
         for (int i = tid; i < 3 * a.wld; i += EU_THREADS) wtab[i] = (R)wtab_g[i];
     __syncthreads();
@@ -114,7 +116,7 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
             R sv[NS];
 #pragma unroll
             for (int k = 0; k < NS; ++k) sv[k] = S0 * rexp(xT[k]);
-            accumulate<MODE, ANTI, GREEKS, R>(acc, a, K, S0, call, sv[0], ANTI ? sv[NS > 1 ? 1 : 0] : (R)0,
+            accumulate<MODE, ANTI, GREEKS, R, double>(acc, a, K, S0, call, sv[0], ANTI ? sv[NS > 1 ? 1 : 0] : (R)0,
                                               GREEKS ? sv[L::UP_IDX < NS ? L::UP_IDX : 0] : (R)0,
                                               GREEKS ? sv[L::DN_IDX < NS ? L::DN_IDX : 0] : (R)0, sumz);
         }
@@ -136,12 +138,17 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
             const int64_t left = a.n_paths - base;
             const int nvalid = left < EU_THREADS ? (int)left : EU_THREADS;
             if (worker) {
+                R part[NACC];                            // per-batch partial in the state's own precision
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) part[j] = (R)0;
                 for (int p = my_slice; p < nvalid; p += nslices) {
-                    accumulate<MODE, ANTI, GREEKS, R>(acc, a, K, S0, call, sT[p], ANTI ? sT[EU_THREADS + p] : (R)0,
-                                                      GREEKS ? sT[L::UP_IDX * EU_THREADS + p] : (R)0,
-                                                      GREEKS ? sT[L::DN_IDX * EU_THREADS + p] : (R)0,
-                                                      (GREEKS && MODE == MODE_GBM) ? sW[p] : (R)0);
+                    accumulate<MODE, ANTI, GREEKS, R, R>(part, a, K, S0, call, sT[p], ANTI ? sT[EU_THREADS + p] : (R)0,
+                                                         GREEKS ? sT[L::UP_IDX * EU_THREADS + p] : (R)0,
+                                                         GREEKS ? sT[L::DN_IDX * EU_THREADS + p] : (R)0,
+                                                         (GREEKS && MODE == MODE_GBM) ? sW[p] : (R)0);
                 }
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) acc[j] += (double)part[j];
             }
             __syncthreads();
         }
@@ -178,7 +185,7 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ strike
     }
 }
 
-using EuroKernel = void (*)(const EuroArgs, const double *, const double *, double *, unsigned int *, double *);
+using EuroKernel = void (*)(const EuroArgs, const double *, double *, unsigned int *, double *);
 
 template <int MODE, typename R, bool SINGLE> static EuroKernel pick3(bool anti, bool greeks)
 {
@@ -247,21 +254,20 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
     int64_t grid = (int64_t)h->sm_count * occ;
     if (grid > need) grid = need;
 
-    // scratch: [strikes n_strikes][wtab 3*wld][partials grid*n_strikes*NACC]
-    const size_t off_w = (size_t)n_strikes * 8;
-    const size_t off_p = off_w + pr.wtab.size() * 8;
+    // scratch: [wtab 3*wld][partials grid*n_strikes*NACC]
+    memcpy(a.strikes, strikes, (size_t)n_strikes * 8);
+    const size_t off_p = pr.wtab.size() * 8;
     const size_t total = off_p + (size_t)grid * n_strikes * NACC * 8;
     B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, total));
-    const size_t hbytes = off_p;
-    B200MC_TRY(ensure(h, &h->h_pinned, &h->pinned_bytes, hbytes > 4096 ? hbytes : 4096, true));
-    // the pinned bounce buffer may still feed the previous launch's copy
-    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
-    memcpy(h->h_pinned, strikes, (size_t)n_strikes * 8);
-    if (!pr.wtab.empty()) memcpy((char *)h->h_pinned + off_w, pr.wtab.data(), pr.wtab.size() * 8);
-    B200MC_CUDA(h, cudaMemcpyAsync(h->d_scratch, h->h_pinned, hbytes, cudaMemcpyHostToDevice, h->stream));
+    if (!pr.wtab.empty()) {     // deterministic-variance tables (rare mode): staged through the pinned bounce buffer
+        B200MC_TRY(ensure(h, &h->h_pinned, &h->pinned_bytes, off_p > 4096 ? off_p : 4096, true));
+        B200MC_CUDA(h, cudaStreamSynchronize(h->stream));      // the buffer may still feed the previous launch's copy
+        memcpy(h->h_pinned, pr.wtab.data(), off_p);
+        B200MC_CUDA(h, cudaMemcpyAsync(h->d_scratch, h->h_pinned, off_p, cudaMemcpyHostToDevice, h->stream));
+    }
     char *sc = (char *)h->d_scratch;
-    kern<<<(unsigned)grid, EU_THREADS, smem, h->stream>>>(a, (const double *)sc, (const double *)(sc + off_w),
-                                                          (double *)(sc + off_p), h->d_counter, out_dev);
+    kern<<<(unsigned)grid, EU_THREADS, smem, h->stream>>>(a, (const double *)sc, (double *)(sc + off_p), h->d_counter,
+                                                          out_dev);
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
     return 0;

@@ -312,6 +312,58 @@ class MonteCarloEngine:
                 results.append(res)
         return results
 
+    def price_grid(self, spot: float, strikes, maturities, is_call: bool = True) -> Dict[str, np.ndarray]:
+        """NEW (BASELINE config 3): strike x maturity grid in the (n_mat, n_k) layout engine/surface.py:69-126
+        (extract_iv_surface) consumes.  Per expiry this is exactly price_batch (paths shared across strikes, the steps
+        rule of monte_carlo.py:287, same seed); all expiries are queued on the stream before one synchronisation and one
+        device->host copy of the sums.  Returns prices, std_errors (raw, as price_batch), num_steps."""
+        if self.rng == "reference":
+            rows = [self._price_batch_reference(spot, strikes, float(T), is_call) for T in maturities]
+            steps = [steps_for(self.num_steps, float(T)) for T in maturities]
+        else:
+            from ._lib import NSUMS
+            p = self.params
+            ks = np.ascontiguousarray(np.asarray(strikes, dtype=np.float64).ravel())
+            Ts = [float(T) for T in maturities]
+            if ks.size > 256:
+                raise ValueError("price_grid takes at most 256 strikes")
+            h = self.handle
+            steps = [steps_for(self.num_steps, T) for T in Ts]
+            n = int(self.num_paths)
+            lo, hi = 0, n
+            if self.comm is not None and self.comm.world > 1:
+                from .dist import shard_range
+                lo, hi = shard_range(n, self.comm.rank, self.comm.world)
+            nbytes = len(Ts) * ks.size * NSUMS * 8
+            buf = h.malloc(nbytes)
+            try:
+                sums = np.zeros((len(Ts), ks.size, NSUMS))
+                if hi > lo:
+                    for j, (T, st) in enumerate(zip(Ts, steps)):
+                        h.price_european(p, float(spot), T, st, hi - lo, self.seed, ks, is_call, self._flags(), None,
+                                         path_offset=lo, out_dev=buf + j * ks.size * NSUMS * 8)
+                    h.d2h(sums, buf)
+            finally:
+                h.free(buf)
+            if self.comm is not None and self.comm.world > 1:
+                sums = self.comm.allreduce_sum(sums).reshape(len(Ts), ks.size, NSUMS)
+            rows = []
+            for T, block in zip(Ts, sums):
+                discount = math.exp(-p.r * T)
+                out = []
+                for K, row in zip(ks, block):
+                    nn, mean, var, mean_a, _ = self._moments(row, self.use_antithetic)
+                    res = {"strike": K, "price": discount * mean, "std_error": discount * math.sqrt(var) / math.sqrt(nn)}
+                    if self.use_control_variate:
+                        bs_ref = bs_price(float(spot), float(K), T, p.r, p.q, math.sqrt(p.v0), is_call)
+                        res["price"] = res["price"] - (discount * mean_a - bs_ref)
+                    out.append(res)
+                rows.append(out)
+        return {"strikes": np.asarray(strikes, dtype=np.float64), "maturities": np.asarray(maturities, dtype=np.float64),
+                "prices": np.array([[r["price"] for r in row] for row in rows]),
+                "std_errors": np.array([[r["std_error"] for r in row] for row in rows]),
+                "num_steps": np.asarray(steps)}
+
     def get_sample_paths(self, spot: float, T: float, num_samples: int = 50) -> np.ndarray:
         """[num_samples, steps + 1] float64, column 0 = spot (monte_carlo.py:452-471)."""
         steps = steps_for(self.num_steps, T, floor=50)                         # :455

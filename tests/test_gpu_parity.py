@@ -272,12 +272,17 @@ def test_fused_fp32_sums_close_to_fp64(H, L, golden):
 
 def test_fused_launch_is_reproducible_and_offsets_add(H, L, golden):
     p, _ = _mode_params(golden, "svj")
-    a = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, [95.0, 105.0], True, L.ANTITHETIC)
-    b = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, [95.0, 105.0], True, L.ANTITHETIC)
-    np.testing.assert_array_equal(a, b)
-    lo = H.price_european(p, 100.0, 0.5, 20, 3_333, 9, [95.0, 105.0], True, L.ANTITHETIC)
-    hi = H.price_european(p, 100.0, 0.5, 20, 6_667, 9, [95.0, 105.0], True, L.ANTITHETIC, path_offset=3_333)
-    np.testing.assert_allclose(lo + hi, a, rtol=1e-12)
+    for ks in ([95.0, 105.0], [100.0]):
+        a = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, ks, True, L.ANTITHETIC)
+        b = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, ks, True, L.ANTITHETIC)
+        np.testing.assert_array_equal(a, b)                     # same geometry => bitwise identical
+        for fl, tol in ((L.ANTITHETIC | L.FP64, 1e-12), (L.ANTITHETIC, 2e-6)):
+            whole = H.price_european(p, 100.0, 0.5, 20, 10_000, 9, ks, True, fl)
+            lo = H.price_european(p, 100.0, 0.5, 20, 3_333, 9, ks, True, fl)
+            hi = H.price_european(p, 100.0, 0.5, 20, 6_667, 9, ks, True, fl, path_offset=3_333)
+            # disjoint path ranges add up (what multi-GPU sharding relies on): exactly in fp64; in fp32 the
+            # multi-strike kernel folds per-batch fp32 partials, so the sum depends on the batching at the 1e-7 level
+            np.testing.assert_allclose(lo + hi, whole, rtol=tol)
 
 
 # ---------------------------------------------------------------------------------------------- production mode
@@ -392,6 +397,24 @@ def test_philox_price_batch_keys_and_consistency(golden):
         assert abs(g["price"] - w["price"]) <= 4 * math.hypot(g["std_error"], w["std_error"]) + 1e-9
         single = eng.price(c["spot"], w["strike"], c["T"], c["is_call"])
         assert single["price"] == pytest.approx(g["price"], rel=1e-9)      # same paths whatever the strike count
+
+
+def test_price_grid_equals_price_batch_per_expiry(golden):
+    """BASELINE config 3 in miniature: 64 strikes x 4 expiries, (n_mat, n_k) layout, same numbers as price_batch."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    p = SVJParams(**golden["params"]["gbm_cfg1"])
+    ks = np.linspace(0.7, 1.3, 64) * 2500.0
+    Ts = [0.125, 0.25, 1.0, 2.0]
+    eng = MonteCarloEngine(p, 200_000, 250, 42, use_sobol=False, use_antithetic=True, use_control_variate=False, rng="philox")
+    g = eng.price_grid(2500.0, ks, Ts, True)
+    assert g["prices"].shape == (4, 64) and list(g["num_steps"]) == [31, 62, 250, 500]
+    for j, T in enumerate(Ts):
+        rows = eng.price_batch(2500.0, ks, T, True)
+        np.testing.assert_allclose(g["prices"][j], [r["price"] for r in rows], rtol=1e-12)
+        np.testing.assert_allclose(g["std_errors"][j], [r["std_error"] for r in rows], rtol=1e-12)
+        bs = np.array([O.bs_price(2500.0, K, T, p.r, p.q, 0.3, True) for K in ks])
+        assert np.all(np.abs(g["prices"][j] - bs) <= 4.5 * g["std_errors"][j] + 1e-9)
+    assert np.all(np.diff(g["prices"], axis=1) <= 1e-9)          # calls decrease in strike (same paths)
 
 
 # ---------------------------------------------------------------------------------------------- Greeks
