@@ -58,7 +58,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
         try:
@@ -69,6 +69,10 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples before this call (pre-roll, GPU idle) are not reported."""
+        self.first = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -85,7 +89,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -274,6 +278,8 @@ def run_b200(args):
     l0 = h.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark()
     e0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
@@ -281,7 +287,19 @@ def run_b200(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = h.launches - l0
+    # The timed region is tens of milliseconds, shorter than nvidia-smi's sampling period, so the sampler keeps
+    # running over ~1 s of the SAME steps issued back to back right after it (not timed): the reported clocks, power
+    # and throttle reasons are those of this workload under sustained load.
+    t_end = time.perf_counter() + 1.0
+    k = 0
+    while time.perf_counter() < t_end:
+        for _ in range(8):
+            step(args.warmup + args.steps + k)
+            k += 1
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed region + 1 s of the same steps back to back"
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

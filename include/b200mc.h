@@ -189,6 +189,22 @@ int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *p, double S
 int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device,
                         double confidence, double out[8]);
 
+/* Multi-rank form of the same metrics: every rank holds a shard of the P&L vector in its own HBM and
+ * calls these three primitives; the host all-reduces their small outputs (2 doubles, 512 counters per radix pass,
+ * 6 doubles) and takes the decisions, so every rank walks the same radix tree and ends with the GLOBAL order
+ * statistics -- no P&L element ever leaves its GPU.  monte_carlo_option_simulator_b200/risk.py
+ * (compute_risk_metrics_sharded) is the host side.  The state lives in the handle's scratch: do not interleave other
+ * calls on the same handle between begin and finish.
+ *   begin : out = { sum x, count of x < 0 } of the local shard (n may be 0)
+ *   hist  : pass 7..0 (most significant byte first); hist[s][b] = number of local keys whose bytes above `pass` equal
+ *           those of prefix[s] and whose byte `pass` is b; keys are the order-preserving 64-bit images of the doubles
+ *           (negative: ~bits, else bits | 2^63)
+ *   finish: out = { sum d^2, sum d^3, sum d^4, count(x < thr[0]), sum(x < thr[0]), sum log(x / thr[1]) over x < thr[1] },
+ *           d = x - mean */
+int b200mc_risk_begin(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device, double out[2]);
+int b200mc_risk_hist(b200mc_handle *h, int pass, int nsel, const uint64_t prefix[2], uint64_t hist[512]);
+int b200mc_risk_finish(b200mc_handle *h, double mean, int nsel, const double thr[2], double out[6]);
+
 /* ---- draws, for feeding the reference the identical numbers ----------------------------------------------
  * out is float64 [n_paths, n_steps] on the host; `stream` one of B200MC_STREAM_*; `which` one of B200MC_Z*;
  * jump_prob = lambda_j * T / n_steps of the run to be reproduced (used only for B200MC_ZJUMP_SIZE of the SVJ stream).

@@ -81,6 +81,9 @@ _PROTOS = {
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                          _u32, C.c_int, C.c_int, _vp, _i64]),
     "b200mc_risk_metrics": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dbl, _dp]),
+    "b200mc_risk_begin": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dp]),
+    "b200mc_risk_hist": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_u64), C.POINTER(_u64)]),
+    "b200mc_risk_finish": (C.c_int, [_vp, _dbl, C.c_int, _dp, _dp]),
     "b200mc_dump_normals": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, C.c_int, _dbl, _vp]),
     "b200mc_dump_philox": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, _vp]),
     "b200mc_normal_moments": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _dp]),
@@ -298,6 +301,36 @@ class Handle:
         code = F64 if a.dtype == np.float64 else F32
         self._check(self.lib.b200mc_risk_metrics(self.h, a.ctypes.data, a.size, code, 0, float(confidence),
                                                   out.ctypes.data_as(_dp)))
+        return out
+
+    # multi-rank tail-metric primitives (host side: risk.compute_risk_metrics_sharded)
+    def risk_begin(self, pnl, n: Optional[int] = None, dtype=None) -> np.ndarray:
+        out = np.zeros(2, dtype=np.float64)
+        if isinstance(pnl, int):
+            code = F64 if np.dtype(dtype) == np.float64 else F32
+            self._check(self.lib.b200mc_risk_begin(self.h, _vp(pnl), int(n), code, 1, out.ctypes.data_as(_dp)))
+            return out
+        a = np.asarray(pnl)
+        if a.dtype != np.float32:
+            a = a.astype(np.float64, copy=False)
+        a = np.ascontiguousarray(a).ravel()
+        self._risk_keepalive = a
+        self._check(self.lib.b200mc_risk_begin(self.h, a.ctypes.data if a.size else None, a.size,
+                                               F64 if a.dtype == np.float64 else F32, 0, out.ctypes.data_as(_dp)))
+        return out
+
+    def risk_hist(self, radix_pass: int, nsel: int, prefix) -> np.ndarray:
+        pre = np.ascontiguousarray(prefix, dtype=np.uint64)
+        hist = np.zeros((2, 256), dtype=np.uint64)
+        self._check(self.lib.b200mc_risk_hist(self.h, int(radix_pass), int(nsel), pre.ctypes.data_as(C.POINTER(_u64)),
+                                              hist.ctypes.data_as(C.POINTER(_u64))))
+        return hist
+
+    def risk_finish(self, mean: float, nsel: int, thr) -> np.ndarray:
+        t = np.ascontiguousarray(thr, dtype=np.float64)
+        out = np.zeros(6, dtype=np.float64)
+        self._check(self.lib.b200mc_risk_finish(self.h, float(mean), int(nsel), t.ctypes.data_as(_dp),
+                                                out.ctypes.data_as(_dp)))
         return out
 
     def dump_normals(self, seed, n_paths, n_steps, stream, which, path_offset=0, jump_prob=0.0) -> np.ndarray:

@@ -23,6 +23,7 @@ struct b200mc_handle {
     void *h_pinned;         size_t pinned_bytes;       // pinned bounce buffer for small arguments
     void *d_result;         size_t result_bytes;       // device-side results of the synchronous entry points
     bool own_stream;                                   // false after b200mc_set_stream
+    const void *risk_x; int64_t risk_n; int risk_dtype; // vector of the multi-rank tail-metric primitives (risk.cu)
     unsigned int *d_counter;                           // "last block reduces" ticket
     char err[512];
 };

@@ -184,8 +184,123 @@ static int risk_run(b200mc_handle *h, const T *x_dev, int64_t n, double confiden
     return 0;
 }
 
+// scratch layout shared by the single-call and the multi-rank entry points
+struct RiskScratch {
+    unsigned long long *keys;
+    SelectState *st;
+    double *partials, *res;
+    int64_t grid;
+};
+static int risk_scratch(b200mc_handle *h, int64_t n, RiskScratch &r)
+{
+    r.grid = (n + RK_THREADS - 1) / RK_THREADS;
+    const int64_t cap = (int64_t)h->sm_count * 8;
+    if (r.grid > cap) r.grid = cap;
+    const size_t off_st = ((size_t)n * 8 + 255) & ~(size_t)255;
+    const size_t off_pa = off_st + ((sizeof(SelectState) + 255) & ~(size_t)255);
+    const size_t off_re = off_pa + (size_t)r.grid * 6 * 8;
+    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, off_re + 64));
+    char *sc = (char *)h->d_scratch;
+    r.keys = (unsigned long long *)sc;
+    r.st = (SelectState *)(sc + off_st);
+    r.partials = (double *)(sc + off_pa);
+    r.res = (double *)(sc + off_re);
+    return 0;
+}
+
 } // namespace b200mc
 using namespace b200mc;
+
+// ---- multi-rank primitives: every rank holds a shard of the P&L vector; the host all-reduces the tiny results ----------
+// (1) begin: order-preserving keys of the local shard + local { sum, count of negatives }.
+extern "C" int b200mc_risk_begin(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device, double out[2])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out || n < 0 || (n > 0 && !pnl)) return fail(h, B200MC_EINVAL, "bad argument");
+    if (dtype != B200MC_F32 && dtype != B200MC_F64) return fail(h, B200MC_EINVAL, "dtype must be B200MC_F32 or B200MC_F64");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    h->risk_x = nullptr; h->risk_n = n; h->risk_dtype = dtype;
+    out[0] = out[1] = 0.0;
+    if (n == 0) return 0;
+    const size_t esz = dtype == B200MC_F64 ? 8 : 4;
+    const void *x = pnl;
+    if (!on_device) {
+        B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, (size_t)n * esz + 256));
+        B200MC_CUDA(h, cudaMemcpyAsync(h->d_stage, pnl, (size_t)n * esz, cudaMemcpyHostToDevice, h->stream));
+        x = h->d_stage;
+    }
+    RiskScratch r;
+    B200MC_TRY(risk_scratch(h, n, r));
+    if (dtype == B200MC_F64)
+        k_risk_pass1<double><<<(unsigned)r.grid, RK_THREADS, 0, h->stream>>>((const double *)x, n, r.keys, r.partials, h->d_counter, r.res);
+    else
+        k_risk_pass1<float><<<(unsigned)r.grid, RK_THREADS, 0, h->stream>>>((const float *)x, n, r.keys, r.partials, h->d_counter, r.res);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(out, r.res, 16, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->risk_x = x;
+    return 0;
+}
+
+// (2) one radix pass: local 256-bin histograms of digit `pass` (7 = most significant byte) among the keys whose higher
+// digits equal those of prefix[s], for nsel (1 or 2) concurrent selections.  hist = [2][256] counts.
+extern "C" int b200mc_risk_hist(b200mc_handle *h, int pass, int nsel, const uint64_t prefix[2], uint64_t hist[512])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!prefix || !hist || pass < 0 || pass > 7 || nsel < 1 || nsel > 2) return fail(h, B200MC_EINVAL, "bad argument");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    memset(hist, 0, 512 * sizeof(uint64_t));
+    if (h->risk_n == 0) return 0;
+    if (!h->risk_x) return fail(h, B200MC_EINVAL, "b200mc_risk_begin has not been called");
+    RiskScratch r;
+    B200MC_TRY(risk_scratch(h, h->risk_n, r));
+    SelectState init;
+    memset(&init, 0, sizeof(init));
+    init.prefix[0] = prefix[0];
+    init.prefix[1] = prefix[1];
+    B200MC_TRY(ensure(h, &h->h_pinned, &h->pinned_bytes, sizeof(SelectState) > 4096 ? sizeof(SelectState) : 4096, true));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->h_pinned, &init, sizeof(init));
+    B200MC_CUDA(h, cudaMemcpyAsync(r.st, h->h_pinned, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    k_risk_hist<<<(unsigned)r.grid, RK_THREADS, 0, h->stream>>>(r.keys, h->risk_n, pass, nsel, r.st);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(hist, &r.st->hist[0][0], 512 * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// (3) finish: local { sum d^2, sum d^3, sum d^4, count(x < thr0), sum(x < thr0), sum log(x / thr1) over x < thr1 } with
+// d = x - mean (the GLOBAL mean) and the GLOBAL thresholds.
+extern "C" int b200mc_risk_finish(b200mc_handle *h, double mean, int nsel, const double thr[2], double out[6])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!thr || !out || nsel < 1 || nsel > 2) return fail(h, B200MC_EINVAL, "bad argument");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    for (int i = 0; i < 6; ++i) out[i] = 0.0;
+    if (h->risk_n == 0) return 0;
+    if (!h->risk_x) return fail(h, B200MC_EINVAL, "b200mc_risk_begin has not been called");
+    RiskScratch r;
+    B200MC_TRY(risk_scratch(h, h->risk_n, r));
+    SelectState init;
+    memset(&init, 0, sizeof(init));
+    init.thr[0] = thr[0];
+    init.thr[1] = thr[1];
+    B200MC_TRY(ensure(h, &h->h_pinned, &h->pinned_bytes, sizeof(SelectState) > 4096 ? sizeof(SelectState) : 4096, true));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->h_pinned, &init, sizeof(init));
+    B200MC_CUDA(h, cudaMemcpyAsync(r.st, h->h_pinned, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    if (h->risk_dtype == B200MC_F64)
+        k_risk_pass2<double><<<(unsigned)r.grid, RK_THREADS, 0, h->stream>>>((const double *)h->risk_x, h->risk_n, mean, nsel, r.st, r.partials, h->d_counter, r.res);
+    else
+        k_risk_pass2<float><<<(unsigned)r.grid, RK_THREADS, 0, h->stream>>>((const float *)h->risk_x, h->risk_n, mean, nsel, r.st, r.partials, h->d_counter, r.res);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(out, r.res, 48, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
 
 extern "C" int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device,
                                    double confidence, double out[8])

@@ -58,3 +58,16 @@ def sharded_sums(handle, comm: Comm, params, spot, T, steps, n_paths, seed, stri
     else:
         local = np.zeros((ks.size, NSUMS))
     return comm.allreduce_sum(local).reshape(ks.size, NSUMS)
+
+
+def sharded_generate_paths(handle, comm: Comm, params, spot, T, steps, n_paths, seed, flags=0, dtype=np.float32,
+                           out_dev: Optional[int] = None):
+    """Path-storing mode across ranks (BASELINE config 4): rank r simulates the contiguous range [lo, hi) of the GLOBAL
+    path index into its OWN memory -- no exchange; rows are identical to those of a single-GPU run of n_paths paths.
+    Returns (lo, hi, local) with local the [hi - lo, steps + 1] array (None when out_dev, a device pointer with room for
+    (hi - lo) * (steps + 1) elements, is given)."""
+    lo, hi = shard_range(n_paths, comm.rank, comm.world)
+    if hi == lo:
+        return lo, hi, (None if out_dev is not None else np.empty((0, steps + 1), dtype=dtype))
+    local = handle.generate_paths(params, spot, T, steps, hi - lo, seed, flags, dtype, path_offset=lo, out_dev=out_dev)
+    return lo, hi, local

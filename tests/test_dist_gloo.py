@@ -35,7 +35,12 @@ def _worker(rank, world, port, q):
         eng = MonteCarloEngine(p, n, 252, 5, use_sobol=False, rng="philox", handle=h, comm=comm)
         price = eng.price(22500.0, 22500.0, 0.25, True)
         delta = GreeksEngine(p, n, 252, 5, rng="philox", handle=h, comm=comm).delta(22500.0, 22500.0, 0.25, True)
-        q.put((rank, got, price, delta, shard_range(n, rank, world)))
+        from test_host_logic import NumpyRiskHandle
+        from monte_carlo_option_simulator_b200.risk import compute_risk_metrics_sharded
+        x = np.random.default_rng(3).standard_t(3, size=20_001) * 0.01
+        lo, hi = shard_range(x.size, rank, world)
+        risk = compute_risk_metrics_sharded(x[lo:hi], 0.99, comm=comm, handle=NumpyRiskHandle())
+        q.put((rank, got, price, delta, shard_range(n, rank, world), risk))
     finally:
         dist.destroy_process_group()
 
@@ -65,7 +70,10 @@ def test_two_rank_sharding_matches_single_process():
     price = MonteCarloEngine(p, 1001, 252, 5, use_sobol=False, rng="philox", handle=h).price(22500.0, 22500.0, 0.25, True)
     delta = GreeksEngine(p, 1001, 252, 5, rng="philox", handle=h).delta(22500.0, 22500.0, 0.25, True)
     assert results[0][4] == (0, 501) and results[1][4] == (501, 1001)
-    for rank, got, pr_, dl, _ in results:
+    want_risk = O.risk_metrics(np.random.default_rng(3).standard_t(3, size=20_001) * 0.01, 0.99)
+    for rank, got, pr_, dl, _, risk in results:
+        for k, w in want_risk.items():
+            assert risk[k] == pytest.approx(w, rel=1e-10, abs=1e-13), k
         np.testing.assert_allclose(got, whole, rtol=1e-12)
         for k, w in price.items():
             assert pr_[k] == pytest.approx(w, rel=1e-10, abs=1e-9)

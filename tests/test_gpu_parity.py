@@ -480,6 +480,19 @@ def test_generate_paths_terminal_column_equals_terminal_mode(H, L, golden):
     np.testing.assert_allclose(paths[:, -1], S, rtol=1e-13)
 
 
+def test_sharded_path_store_rows_equal_single_run(H, L, golden):
+    """SURVEY 8e, path-storing mode: every rank keeps its own shard, rows are those of the single-GPU run."""
+    from monte_carlo_option_simulator_b200.dist import Comm, sharded_generate_paths
+    p, _ = _mode_params(golden, "gbm")
+    whole = H.generate_paths(p, 2500.0, 1.0, 250, 1000, 9, 0, np.float32)
+    for world in (2, 3):
+        for r in range(world):
+            c = Comm()
+            c.rank, c.world = r, world
+            lo, hi, part = sharded_generate_paths(H, c, p, 2500.0, 1.0, 250, 1000, 9, 0, np.float32)
+            np.testing.assert_array_equal(part, whole[lo:hi])
+
+
 def test_sample_paths_philox_shape(golden):
     from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
     eng = MonteCarloEngine(SVJParams(**golden["params"]["svj_default"]), 1000, seed=42, rng="philox")
@@ -537,6 +550,55 @@ def test_cfg4_terminal_pnl_var(H, L, golden):
             assert math.isnan(v)
         else:
             assert v == pytest.approx(want[k], rel=1e-9, abs=1e-9), k
+
+
+class _ThreadComm:
+    """In-process communicator for emulating ranks with threads (one Handle per thread on the same GPU)."""
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self.s = rank, world, shared
+
+    def allreduce_sum(self, a):
+        import numpy as _np
+        self.s["buf"][self.rank] = _np.array(a, dtype=_np.float64, copy=True)
+        self.s["bar"].wait()
+        out = sum(self.s["buf"])
+        self.s["bar"].wait()
+        return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_risk_metrics_equal_the_global_ones(L, garr, world):
+    """VaR/CVaR/Hill over a P&L vector sharded across ranks; only histograms and a few sums are exchanged.
+    Ranks are emulated as threads with one handle each; shards are ragged (one of them may be empty)."""
+    import threading
+    from monte_carlo_option_simulator_b200.risk import compute_risk_metrics_sharded
+    g = np.random.default_rng(5)
+    cases = [(garr["risk_student_t3"], 0.99), (garr["risk_ties"], 0.95), (g.standard_t(4, size=300_001) * 0.01, 0.99),
+             (garr["risk_tiny"], 0.99)]
+    for x, conf in cases:
+        want = O.risk_metrics(x, conf)
+        cuts = [0] + sorted(g.integers(0, x.size + 1, size=world - 1).tolist()) + [x.size]
+        shared = {"buf": [None] * world, "bar": threading.Barrier(world)}
+        res = [None] * world
+
+        def run(r):
+            h = L.Handle(0)
+            try:
+                res[r] = compute_risk_metrics_sharded(x[cuts[r]:cuts[r + 1]], conf, comm=_ThreadComm(r, world, shared), handle=h)
+            finally:
+                h.close()
+
+        th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t_.start() for t_ in th]
+        [t_.join() for t_ in th]
+        for r in range(world):
+            assert res[r] is not None
+            for k, w in want.items():
+                if math.isnan(w):
+                    assert math.isnan(res[r][k]), k
+                else:
+                    assert res[r][k] == pytest.approx(w, rel=1e-10, abs=1e-13), (k, world)
 
 
 # ---------------------------------------------------------------------------------------------- patched reference callers

@@ -199,3 +199,50 @@ def test_engine_rejects_unknown_modes():
         MonteCarloEngine(SVJParams(), rng="mt19937")
     with pytest.raises(ValueError):
         MonteCarloEngine(SVJParams(), precision="fp16")
+
+
+class NumpyRiskHandle:
+    """NumPy stand-in for the three multi-rank tail-metric primitives of libb200mc (csrc/risk.cu)."""
+
+    def risk_begin(self, pnl, n=None, dtype=None):
+        self.x = np.asarray(pnl, dtype=np.float64).ravel()
+        bits = self.x.view(np.uint64)
+        neg = (bits >> np.uint64(63)).astype(bool)
+        self.keys = np.where(neg, ~bits, bits | np.uint64(1 << 63))
+        return np.array([self.x.sum(), float((self.x < 0).sum())])
+
+    def risk_hist(self, radix_pass, nsel, prefix):
+        hist = np.zeros((2, 256), dtype=np.uint64)
+        shift = np.uint64(8 * radix_pass)
+        digit = ((self.keys >> shift) & np.uint64(255)).astype(np.int64)
+        for s in range(nsel):
+            if radix_pass == 7:
+                sel = np.ones(self.keys.size, dtype=bool)
+            else:
+                hi = np.uint64(8 * radix_pass + 8)
+                sel = (self.keys >> hi) == (np.uint64(prefix[s]) >> hi)
+            hist[s] = np.bincount(digit[sel], minlength=256).astype(np.uint64)
+        return hist
+
+    def risk_finish(self, mean, nsel, thr):
+        d = self.x - mean
+        lt = self.x < thr[0]
+        tail = np.log(self.x[self.x < thr[1]] / thr[1]).sum() if nsel > 1 else 0.0
+        return np.array([(d ** 2).sum(), (d ** 3).sum(), (d ** 4).sum(), float(lt.sum()), self.x[lt].sum(), tail])
+
+
+def test_sharded_risk_host_logic_single_rank_equals_oracle(golden, garr):
+    """The host side of the distributed radix select (risk.compute_risk_metrics_sharded) against the oracle."""
+    from conftest import unnan
+    from monte_carlo_option_simulator_b200.risk import compute_risk_metrics_sharded, _key_to_value
+    assert _key_to_value(0x8000000000000000 | np.array([1.5]).view(np.uint64)[0].item()) == 1.5
+    assert _key_to_value((~np.array([-2.25]).view(np.uint64)[0]).item() & 0xFFFFFFFFFFFFFFFF) == -2.25
+    for c in golden["cases"]["risk"]:
+        got = compute_risk_metrics_sharded(garr[f"risk_{c['name']}"], c["confidence"], comm=Comm(), handle=NumpyRiskHandle())
+        want = unnan(c["result"])
+        assert set(got) == set(want)
+        for k, w in want.items():
+            if np.isnan(w):
+                assert np.isnan(got[k]), (c["name"], k)
+            else:
+                assert got[k] == pytest.approx(w, rel=1e-11, abs=1e-13), (c["name"], k)
