@@ -15,6 +15,9 @@
 namespace b200mc {
 
 constexpr int EU_THREADS = 256;
+#ifndef EU_MIN_BLOCKS
+#define EU_MIN_BLOCKS 1
+#endif
 constexpr int NACC = 16;   // doubles per strike after b200mc_sums.n
 
 struct EuroArgs {
@@ -77,7 +80,7 @@ __device__ __forceinline__ void accumulate(A (&acc)[NACC], const EuroArgs &a, R 
 // SINGLE = exactly one strike: every thread finishes its own paths, no shared-memory staging and no block barrier
 // inside the path loop.  Otherwise phase A / phase B as described at the top of the file.
 template <int MODE, bool ANTI, bool GREEKS, typename R, bool SINGLE>
-__global__ void __launch_bounds__(EU_THREADS)
+__global__ void __launch_bounds__(EU_THREADS, (sizeof(R) == 4 && MODE <= MODE_DETVAR) ? EU_MIN_BLOCKS : 1)
 k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
            double *__restrict__ out)
 {
