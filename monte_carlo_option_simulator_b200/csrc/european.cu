@@ -15,6 +15,9 @@
 namespace b200mc {
 
 constexpr int EU_THREADS = 256;
+// Register budget: measured on B200, letting ptxas take ~100 registers (2 CTAs = 4 warps per sub-partition) beats every
+// capped variant (min blocks 4/5/6: 1.58 / 1.59 / 1.57e12 vs 1.69e12 path-steps/s) and two paths per thread (1.60e12):
+// the kernel is XU/MIO-queue bound and more resident warps only deepen that queue.
 #ifndef EU_MIN_BLOCKS
 #define EU_MIN_BLOCKS 1
 #endif
