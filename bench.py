@@ -189,7 +189,9 @@ def instruction_roofline(h, achieved_path_steps_per_gpu, sm_mhz):
     binding = min(b_algo, key=b_algo.get)
     peak = b_algo[binding]
     return {"bound": binding, "achieved": achieved_path_steps_per_gpu, "peak": peak, "unit": UNIT,
-            "frac": achieved_path_steps_per_gpu / peak, "traffic": None,
+            "frac": achieved_path_steps_per_gpu / peak, "traffic": 38144,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
+                              "profiles/r01_ncu_k_european_gbm_fp32_greeks.txt (algorithmic bytes: 0 per path-step)",
             "kernel": "k_european<GBM, fp32, greeks>", "kind": "instruction roofline (the kernel moves no data): "
             "algorithmic instructions per path-step over issue rates measured in this run",
             "algorithmic_per_path_step": algo, "pipe_bounds_algorithmic": b_algo,
@@ -225,7 +227,9 @@ def hbm_roofline(h, torch, n_paths=4_000_000, reps=3):
                 best = ms if best is None else min(best, ms)
         nbytes = n_paths * (N_STEPS + 1) * esz          # algorithmic bytes: the matrix itself, no padding
         gbs = nbytes / (best * 1e-3) / 1e9
-        out[name] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+        out[name] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                     "traffic": 3956231456 if name == "f32" else None,
+                     "traffic_source": "ncu --set full, profiles/r01_ncu_k_paths_tma_fp32.txt (4M x 251 fp32 launch)" if name == "f32" else None,
                      "kernel": "k_paths_tma<GBM>" if ld == N_STEPS + 1 else "k_paths_det<GBM>", "path_steps_per_s": n_paths * N_STEPS / (best * 1e-3),
                      "bytes_per_launch": nbytes, "ms": best, "peak_source": src, "shape": [n_paths, N_STEPS + 1], "ld": ld,
                      "note": note}
