@@ -262,6 +262,38 @@ def test_fused_greek_sums_vs_oracle(H, L, golden, mode, is_call):
         assert col[k] == pytest.approx(w, rel=1e-9), k
 
 
+@pytest.mark.parametrize("mode", ["gbm", "svj"])
+def test_multi_strike_greek_sums_equal_single_strike_launches(H, L, golden, mode):
+    """The strike-major phase B with bump accumulators (multi-strike + GREEKS) against one launch per strike."""
+    p, _ = _mode_params(golden, mode)
+    ks = [2300.0, 2500.0, 2750.0]
+    bumps = L.Bumps(0.01, p.v0 + 0.01, max(p.v0 - 0.01, 0.001), p.r + 1e-4, max(p.r - 1e-4, 0))
+    for fl, tol in ((L.GREEKS | L.FP64, 1e-12), (L.GREEKS | L.FP64 | L.ANTITHETIC, 1e-12), (L.GREEKS, 2e-6)):
+        many = H.price_european(p, 2500.0, 0.5, 40, 5000, 3, ks, False, fl, bumps)
+        for K, row in zip(ks, many):
+            one = H.price_european(p, 2500.0, 0.5, 40, 5000, 3, [K], False, fl, bumps)[0]
+            np.testing.assert_allclose(row, one, rtol=tol, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["gbm", "detvar", "heston", "svj"])
+def test_edge_shapes(H, L, golden, mode):
+    """One path, one step, 256 strikes, very many steps, tiny maturities: shapes the reference's callers can produce
+    (steps = max(int(252 T), 10), verify.py uses T = 0.04)."""
+    p, stream = _mode_params(golden, mode)
+    for n, steps, T in [(1, 1, 0.004), (3, 10, 0.04), (257, 9, 0.3), (40, 1200, 3.0)]:
+        Z = _draws(H, L, 17, n, steps, stream, 5, p, T)
+        want = O._sim(p, 100.0, T, *Z, steps)[0]
+        got = H.simulate_terminal(p, 100.0, T, steps, n, 17, L.FP64, np.float64, 5)[0]
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+        ks = list(np.linspace(60.0, 140.0, 256))
+        rows = H.price_european(p, 100.0, T, steps, n, 17, ks, True, L.FP64, None, path_offset=5)
+        np.testing.assert_allclose(rows[:, 1], [np.maximum(want - K, 0).sum() for K in ks], rtol=1e-9, atol=1e-9)
+        paths = H.generate_paths(p, 100.0, T, steps, n, 17, L.FP64, np.float64, 5)
+        np.testing.assert_allclose(paths[:, -1], want, rtol=1e-9)
+    with pytest.raises(L.B200MCError):
+        H.price_european(p, 100.0, 1.0, 10, 10, 1, list(np.linspace(60.0, 140.0, 257)))
+
+
 def test_fused_fp32_sums_close_to_fp64(H, L, golden):
     p, _ = _mode_params(golden, "gbm")
     ks = list(np.linspace(0.8, 1.2, 5) * 2500.0)
