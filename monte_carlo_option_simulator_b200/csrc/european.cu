@@ -2,14 +2,17 @@
 // sums reduced on chip.  Replaces, for the pseudo-random case, the RNG front end + both kernel runs + the NumPy
 // reductions of MonteCarloEngine.price / price_batch (engine/monte_carlo.py:273-450) and the three re-simulations
 // each of GreeksEngine.delta / vega / gamma (engine/greeks.py:53-203).  No path matrix touches HBM: the only
-// global traffic is one 128-byte-per-strike partial per block and the final b200mc_sums.
+// global traffic is one 128-byte partial per (CTA, strike) and the final b200mc_sums; strikes travel in the kernel
+// parameters, so a call makes no host->device copy and no stream synchronisation.
 //
-// Block = 256 threads.  Phase A: every thread simulates one path (sim.cuh) and parks S_T of each state in
-// shared memory.  Phase B: thread t owns strike (t % n_strikes) and path slice (t / n_strikes) of the batch
-// and adds the payoff terms of that strike into fp64 register accumulators (for one strike this degenerates
-// to "every thread finishes its own path").  After the last batch the slices are folded through shared
-// memory, one partial per (block, strike) goes to scratch and the last block to arrive adds the partials in
-// block order, so a given launch geometry is bitwise reproducible.
+// CTA = 256 threads, one persistent wave.
+//   one strike    every thread simulates its own paths (sim.cuh) and adds their payoff terms into 16 fp64 register
+//                 accumulators -- no shared memory, no barrier inside the path loop.
+//   many strikes  phase A: every thread simulates one path of a 256-path batch and parks S_T of each state in shared
+//                 memory; phase B: thread t owns strike (t % n_strikes) and slice (t / n_strikes) of the batch and adds
+//                 the payoff terms of that strike (per-batch partials in the state's precision, folded into fp64).
+// At the end the threads of a CTA are folded through shared memory, one partial per (CTA, strike) goes to scratch and
+// the last CTA to arrive adds the partials in CTA order, so a given launch geometry is bitwise reproducible.
 #include "prep.cuh"
 
 namespace b200mc {

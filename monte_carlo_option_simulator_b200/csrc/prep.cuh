@@ -41,7 +41,6 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
     m.drift_dt = drift_comp * dt;
     m.half_dt = 0.5 * dt;
     m.sqrt_dt_s = sqrt_dt * B200MC_BM_SCALE;
-    m.kappa_dt = p->kappa * dt;
     m.one_m_kdt = 1.0 - p->kappa * dt;
     m.kdt_theta = p->kappa * dt * p->theta;
     m.theta = p->theta;

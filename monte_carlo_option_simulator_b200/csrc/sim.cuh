@@ -13,8 +13,8 @@
 //     GBM     xi = 0, lambda = 0, variance constant: x_T = drift + w * sum(z); only sum(z) is carried
 //     DETVAR  xi = 0, lambda = 0, variance deterministic but moving (kappa != 0, theta != v0): per-step
 //             weights w_s = sqrt(v_s dt) come from a table in shared memory (built on the host in fp64)
-//     HESTON  lambda = 0: two normals per step, two steps per Philox call
-//     SVJ     everything: one Philox call per step (Z1, Z2, U_jump, Z_jump_size)
+//     HESTON  lambda = 0: one Box-Muller pair (Z1, Z2) per step, four steps per Philox call
+//     SVJ     everything: a pair word and a jump-uniform word per step, two steps per Philox call
 // R is the type of the path state (float or double); the draws are float in both cases.
 #pragma once
 #include "common.cuh"
@@ -28,7 +28,7 @@ struct ModelArgs {
     double drift_dt;        // (r - q - lambda_j k) dt                       :210,229
     double half_dt;         // dt / 2
     double sqrt_dt_s;       // sqrt(dt) * BM_SCALE  (the draws are unscaled, see philox.cuh)
-    double kappa_dt, theta;
+    double theta;
     double one_m_kdt;       // 1 - kappa dt
     double kdt_theta;       // kappa dt theta
     double jump_scale;      // 1 / (lambda_j dt 2^32): (w + 0.5) * jump_scale is uniform on (0,1) GIVEN that the jump fired
