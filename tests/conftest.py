@@ -14,6 +14,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # The CUDA library is a build artefact (git-ignored).  A fresh checkout has none: build it once (nvcc cross-compiles
+    # sm_100a without a GPU).  The tests never fall back to anything else when it is missing.
+    lib = os.path.join(ROOT, "monte_carlo_option_simulator_b200", "libb200mc.so")
+    if not os.path.exists(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "monte_carlo_option_simulator_b200", "csrc"), "-j8", "-s"],
+                           check=False)
 
 
 @pytest.fixture(scope="session")
