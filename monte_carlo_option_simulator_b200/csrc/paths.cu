@@ -526,7 +526,9 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
             else { if (dtype == B200MC_F64) path_det_launch<TAB, float, double>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); \
                    else path_det_launch<TAB, float, float>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); }         \
         } while (0)
-        if (ld == (int64_t)n_steps + 1 && n_steps <= 1024) {
+        const size_t tma_smem = (((size_t)32 * (n_steps + 1) * esz + 127) & ~(size_t)127) + (size_t)((n_steps + 31) / 32) * 32 * (fp64 ? 8 : 4) +
+                                (tab ? (size_t)2 * (pr.wld + 32) * (fp64 ? 8 : 4) : 0);
+        if (ld == (int64_t)n_steps + 1 && n_steps <= 1024 && tma_smem <= 200 * 1024) {
             const int NCH = (n_steps + 31) / 32;                      // warps per CTA = chunks of 32 steps
             const size_t rs = fp64 ? 8 : 4;
             smem = (((size_t)32 * (n_steps + 1) * esz + 127) & ~(size_t)127) + (size_t)NCH * 32 * rs +

@@ -505,6 +505,18 @@ def test_generate_paths_identical_draws(H, L, golden, mode, n, steps):
     np.testing.assert_allclose(padded, got, rtol=1e-13)     # row-tiled kernel vs TMA-tiled kernel: summation order
 
 
+@pytest.mark.parametrize("steps", [1000, 1024, 1500])
+def test_generate_paths_long_paths(H, L, golden, steps):
+    """Many steps: 32 warps per CTA in the TMA-tiled kernel (fp32), shared-memory limit fallback (fp64), row-tiled
+    kernel beyond 1024 steps."""
+    p, stream = _mode_params(golden, "gbm")
+    n, seed, T = 70, 8, 2.0
+    Z = _draws(H, L, seed, n, steps, stream, 0, p, T)
+    want = O._sim(p, 2500.0, T, *Z, steps, record=True)[2]
+    np.testing.assert_allclose(H.generate_paths(p, 2500.0, T, steps, n, seed, L.FP64, np.float64), want, rtol=1e-10)
+    np.testing.assert_allclose(H.generate_paths(p, 2500.0, T, steps, n, seed, 0, np.float32), want, rtol=RTOL32)
+
+
 def test_generate_paths_terminal_column_equals_terminal_mode(H, L, golden):
     p, _ = _mode_params(golden, "svj")
     paths = H.generate_paths(p, 100.0, 0.5, 77, 1000, 3, L.FP64, np.float64)
