@@ -15,8 +15,51 @@ from . import monte_carlo as _mc
 from . import risk as _r
 
 
-def patch_reference(package: str = "engine") -> List[str]:
-    """Returns the list of 'module.attribute' names that were rebound."""
+def _batched_objectives(calib):
+    """Same objectives as engine/calibration.py:53-135, with the per-strike loop of price() calls (:78-89, :119-130)
+    replaced by ONE price_batch launch per candidate.  Numerically identical: the reference re-creates the same paths
+    for every strike (same engine, same seed), which is exactly price_batch's "paths shared across strikes", and the
+    two methods apply the same control-variate formula (monte_carlo.py:365 and :447).  REGULARIZATION, check_feller and
+    SVJParams are taken from the patched module itself."""
+    import numpy as np
+
+    def _sum_sq(engine, spot, strikes, T, market_prices, weights, is_call):
+        try:
+            rows = engine.price_batch(spot, np.asarray(strikes, dtype=float), T, is_call=is_call)
+        except Exception:
+            return float(len(strikes))                      # every strike "failed": +1.0 each (:88-89)
+        return float(sum(weights[i] * (rows[i]["price"] - market_prices[i]) ** 2 for i in range(len(strikes))))
+
+    def _heston_objective(x, spot, strikes, T, market_prices, weights, r, q, is_call, num_paths=100_000, num_steps=100):
+        kappa, theta, xi, rho, v0 = x
+        feller_penalty = 0.0
+        if not calib.check_feller(kappa, theta, xi):
+            feller_penalty = 10.0 * (xi ** 2 - 2 * kappa * theta) ** 2
+        params = calib.SVJParams(kappa=kappa, theta=theta, xi=xi, rho=rho, v0=v0, lambda_j=0.0, mu_j=0.0, sigma_j=0.01,
+                                 r=r, q=q)
+        engine = calib.MonteCarloEngine(params, num_paths=num_paths, num_steps=num_steps, use_sobol=True,
+                                        use_antithetic=True, use_control_variate=True)
+        total = _sum_sq(engine, spot, strikes, T, market_prices, weights, is_call)
+        reg = calib.REGULARIZATION["xi"] * xi ** 2 + calib.REGULARIZATION["rho"] * rho ** 2
+        return total + reg + feller_penalty
+
+    def _svj_objective(x_jump, heston_params, spot, strikes, T, market_prices, weights, r, q, is_call,
+                       num_paths=100_000, num_steps=100):
+        lambda_j, mu_j, sigma_j = x_jump
+        kappa, theta, xi, rho, v0 = heston_params
+        params = calib.SVJParams(kappa=kappa, theta=theta, xi=xi, rho=rho, v0=v0, lambda_j=lambda_j, mu_j=mu_j,
+                                 sigma_j=sigma_j, r=r, q=q)
+        engine = calib.MonteCarloEngine(params, num_paths=num_paths, num_steps=num_steps, use_sobol=True,
+                                        use_antithetic=True, use_control_variate=True)
+        total = _sum_sq(engine, spot, strikes, T, market_prices, weights, is_call)
+        return total + calib.REGULARIZATION["lambda_j"] * lambda_j ** 2
+
+    return _heston_objective, _svj_objective
+
+
+def patch_reference(package: str = "engine", batch_calibration: bool = True) -> List[str]:
+    """Returns the list of 'module.attribute' names that were rebound.  batch_calibration: also replace the two
+    calibration objectives by versions that price all strikes of a candidate in one launch."""
     done = []
 
     def rebind(modname, attr, obj):
@@ -39,6 +82,13 @@ def patch_reference(package: str = "engine") -> List[str]:
     rebind(f"{package}.risk", "MonteCarloEngine", _mc.MonteCarloEngine)
     rebind(f"{package}.risk", "compute_risk_metrics", _r.compute_risk_metrics)
     rebind(f"{package}.calibration", "MonteCarloEngine", _mc.MonteCarloEngine)
+    calib = sys.modules.get(f"{package}.calibration")
+    if batch_calibration and calib is not None and all(hasattr(calib, a) for a in
+                                                      ("_heston_objective", "_svj_objective", "REGULARIZATION",
+                                                       "check_feller", "SVJParams")):
+        h_obj, s_obj = _batched_objectives(calib)
+        rebind(f"{package}.calibration", "_heston_objective", h_obj)
+        rebind(f"{package}.calibration", "_svj_objective", s_obj)
     for attr, obj in (("MonteCarloEngine", _mc.MonteCarloEngine), ("GreeksEngine", _g.GreeksEngine)):
         rebind(f"{package}.app", attr, obj)
     return done

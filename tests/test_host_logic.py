@@ -187,7 +187,7 @@ def test_patch_reference_rebinds_import_by_name_sites():
         assert mods["calibration"].MonteCarloEngine is MonteCarloEngine
         assert mods["app"].GreeksEngine is GreeksEngine
         assert not isinstance(mods["app"].StressTestEngine, type)       # caller class: left alone
-        assert len(done) == 12
+        assert len(done) == 12          # (no calibration objectives in this stub module)
     finally:
         for k in list(sys.modules):
             if k.startswith("fakeengine"):
@@ -246,3 +246,48 @@ def test_sharded_risk_host_logic_single_rank_equals_oracle(golden, garr):
                 assert np.isnan(got[k]), (c["name"], k)
             else:
                 assert got[k] == pytest.approx(w, rel=1e-11, abs=1e-13), (c["name"], k)
+
+
+def test_batched_calibration_objectives_equal_the_per_strike_loop(golden, monkeypatch):
+    """the patched objectives (one price_batch launch per candidate) return what the reference's
+    per-strike loop of price() calls returns (engine/calibration.py:53-135)."""
+    from monte_carlo_option_simulator_b200 import patch_reference
+    from monte_carlo_option_simulator_b200.models import SVJParams as OurParams
+    handle = OracleBackedHandle()
+    monkeypatch.setattr(_lib, "default_handle", lambda device=None: handle)
+    monkeypatch.setenv("B200MC_RNG", "philox")
+    REG = {"xi": 0.01, "rho": 0.005, "lambda_j": 0.01}
+
+    def check_feller(kappa, theta, xi):
+        return 2.0 * kappa * theta > xi * xi
+
+    def ref_heston(x, spot, strikes, T, mkt, w, r, q, is_call, num_paths, num_steps):          # calibration.py:53-95
+        kappa, theta, xi, rho, v0 = x
+        pen = 0.0 if check_feller(kappa, theta, xi) else 10.0 * (xi ** 2 - 2 * kappa * theta) ** 2
+        eng = MonteCarloEngine(OurParams(kappa=kappa, theta=theta, xi=xi, rho=rho, v0=v0, lambda_j=0.0, mu_j=0.0,
+                                         sigma_j=0.01, r=r, q=q), num_paths=num_paths, num_steps=num_steps)
+        tot = sum(w[i] * (eng.price(spot, K, T, is_call=is_call)["price"] - mkt[i]) ** 2 for i, K in enumerate(strikes))
+        return tot + REG["xi"] * xi ** 2 + REG["rho"] * rho ** 2 + pen
+
+    calib = types.ModuleType("fakecal.calibration")
+    calib.MonteCarloEngine, calib.REGULARIZATION, calib.check_feller, calib.SVJParams = object(), REG, check_feller, OurParams
+    calib._heston_objective = calib._svj_objective = None
+    pkg = types.ModuleType("fakecal")
+    pkg.__path__ = []
+    sys.modules["fakecal"], sys.modules["fakecal.calibration"] = pkg, calib
+    try:
+        done = patch_reference("fakecal")
+        assert "fakecal.calibration._heston_objective" in done and "fakecal.calibration._svj_objective" in done
+        ks, mkt, w = np.array([21500.0, 22500.0, 23500.0]), np.array([1500.0, 900.0, 480.0]), np.array([0.3, 0.4, 0.3])
+        for x in ([3.0, 0.04, 0.5, -0.7, 0.04], [1.0, 0.02, 0.6, -0.3, 0.05]):       # Feller satisfied / violated
+            got = calib._heston_objective(np.array(x), 22500.0, ks, 0.25, mkt, w, 0.065, 0.012, True, num_paths=600, num_steps=80)
+            want = ref_heston(x, 22500.0, ks, 0.25, mkt, w, 0.065, 0.012, True, 600, 80)
+            assert got == pytest.approx(want, rel=1e-10)
+        calls = handle.calls
+        calib._svj_objective(np.array([1.0, -0.05, 0.1]), np.array([3.0, 0.04, 0.5, -0.7, 0.04]), 22500.0, ks, 0.25, mkt, w,
+                             0.065, 0.012, True, num_paths=600, num_steps=80)
+        assert handle.calls == calls + 1                   # ONE launch for the three strikes
+    finally:
+        for k in list(sys.modules):
+            if k.startswith("fakecal"):
+                del sys.modules[k]
