@@ -253,10 +253,20 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
     size_t smem = (size_t)(EU_THREADS + n_strikes) * 8 + (single ? 0 : (size_t)(ns + 1) * EU_THREADS * rsz);
     if (pr.mode == MODE_DETVAR) smem += (size_t)3 * pr.wld * rsz;
     if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
-    B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // dynamic-smem opt-in and occupancy are properties of (kernel, smem): query once, then reuse (small calls are
+    // latency bound, calibration issues 1e4-1e5 of them)
     int occ = 0;
-    B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, EU_THREADS, smem));
-    if (occ < 1) return fail(h, B200MC_ECUDA, "fused kernel does not fit on an SM");
+    for (int i = 0; i < h->n_occ; ++i)
+        if (h->occ_kern[i] == (const void *)kern && h->occ_smem[i] == smem) occ = h->occ_val[i];
+    if (occ == 0) {
+        B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, EU_THREADS, smem));
+        if (occ < 1) return fail(h, B200MC_ECUDA, "fused kernel does not fit on an SM");
+        const int slot = h->n_occ < 64 ? h->n_occ++ : 63;
+        h->occ_kern[slot] = (const void *)kern;
+        h->occ_smem[slot] = smem;
+        h->occ_val[slot] = occ;
+    }
     // One persistent wave: CTAs stride over the paths.  (Measured: 4 or 16 waves of smaller CTAs are not faster --
     // 1.64e12 -> 1.64e12 / 1.35e12 path-steps/s -- the final per-CTA fold is what grows.)
     const int64_t need = (n_paths + EU_THREADS - 1) / EU_THREADS;
@@ -309,9 +319,12 @@ extern "C" int b200mc_price_european(b200mc_handle *h, const b200mc_svj_params *
     B200MC_CUDA(h, cudaSetDevice(h->device));
     const size_t bytes = (size_t)n_strikes * sizeof(b200mc_sums);
     B200MC_TRY(ensure(h, &h->d_result, &h->result_bytes, bytes));
+    B200MC_TRY(ensure(h, &h->h_result, &h->h_result_bytes, bytes, true));
     B200MC_TRY(launch_european(h, p, S0, T, n_steps, n_paths, seed, path_offset, strikes, n_strikes, is_call, flags,
                                bumps, reinterpret_cast<double *>(h->d_result)));
-    B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
+    // device -> PINNED host (a pageable destination makes the copy a staged, much slower one), then a plain memcpy
+    B200MC_CUDA(h, cudaMemcpyAsync(h->h_result, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_result, bytes);
     return 0;
 }
