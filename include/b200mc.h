@@ -211,6 +211,11 @@ int b200mc_risk_finish(b200mc_handle *h, double mean, int nsel, const double thr
  * Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0). */
 int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
                         int32_t n_steps, uint32_t stream, int which, double jump_prob, double *out);
+/* The stream a fused call with these parameters draws from: B200MC_STREAM_GBM when xi == 0 and lambda_j dt <= 0 (constant
+ * or deterministic variance; deterministic-variance runs of more than 4096 steps fall to the Heston stream),
+ * B200MC_STREAM_HESTON when lambda_j dt <= 0, else B200MC_STREAM_SVJ (always, with B200MC_FORCE_SVJ).  h may be NULL. */
+int b200mc_select_stream(b200mc_handle *h, const b200mc_svj_params *p, double T, int32_t n_steps, uint32_t flags,
+                         const b200mc_bumps *bumps, uint32_t *stream);
 /* Raw Philox words uint32 [n_paths, n_blocks, 4] (host), for the bit-exact check against the oracle. */
 int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
                        int32_t n_blocks, uint32_t stream, uint32_t *out);

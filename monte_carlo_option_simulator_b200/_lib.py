@@ -85,6 +85,7 @@ _PROTOS = {
     "b200mc_risk_hist": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_u64), C.POINTER(_u64)]),
     "b200mc_risk_finish": (C.c_int, [_vp, _dbl, C.c_int, _dp, _dp]),
     "b200mc_dump_normals": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, C.c_int, _dbl, _vp]),
+    "b200mc_select_stream": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _i32, _u32, C.POINTER(Bumps), C.POINTER(_u32)]),
     "b200mc_dump_philox": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, _vp]),
     "b200mc_normal_moments": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _dp]),
     "b200mc_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -117,6 +118,17 @@ def load() -> C.CDLL:
             fn.argtypes = args
         _lib = lib
         return lib
+
+
+def select_stream(params, T: float, n_steps: int, flags: int = 0, bumps: Optional["Bumps"] = None) -> int:
+    """Which B200MC_STREAM_* a fused call with these parameters draws from (needs no device)."""
+    out = _u32()
+    sp = to_params(params)
+    rc = load().b200mc_select_stream(None, C.byref(sp), float(T), int(n_steps), int(flags),
+                                     C.byref(bumps) if bumps is not None else None, C.byref(out))
+    if rc != OK:
+        raise B200MCError(rc, (load().b200mc_last_error(None) or b"").decode())
+    return int(out.value)
 
 
 def to_params(p) -> SvjParams:

@@ -7,7 +7,7 @@
 //   Z_jump_size    (double)normcdfinvf(U_jump / jump_prob) where the jump fires (U_jump < jump_prob = lambda_j dt),
 //                  0 elsewhere -- the reference only reads it where the jump fires (monte_carlo.py:233-234)
 // Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0).
-#include "common.cuh"
+#include "prep.cuh"
 
 namespace b200mc {
 
@@ -154,5 +154,18 @@ extern "C" int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t pat
     h->launches += 1;
     B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+
+// Which draw stream a fused call with these parameters consumes (the mode selection of prep.cuh), so that a caller of
+// b200mc_dump_normals can ask instead of re-deriving the rule.
+extern "C" int b200mc_select_stream(b200mc_handle *h, const b200mc_svj_params *p, double T, int32_t n_steps, uint32_t flags,
+                                    const b200mc_bumps *bumps, uint32_t *stream)
+{
+    if (!stream) return fail(h, B200MC_EINVAL, "stream is NULL");
+    Prep pr;
+    B200MC_TRY(prepare(h, p, 1.0, T, n_steps, 1, 0, flags, bumps, pr));
+    *stream = pr.mode == MODE_SVJ ? B200MC_STREAM_SVJ : (pr.mode == MODE_HESTON ? B200MC_STREAM_HESTON : B200MC_STREAM_GBM);
     return 0;
 }

@@ -65,3 +65,20 @@ def test_product_package_never_imports_the_oracle():
                 checked += 1
                 assert not bad.search(open(os.path.join(dirpath, f)).read()), f"{f} reaches into oracle/"
     assert checked >= 12
+
+
+def test_stream_selection_rule_needs_no_device():
+    from monte_carlo_option_simulator_b200 import SVJParams, _lib
+    g = SVJParams.gbm(0.3)
+    assert _lib.select_stream(g, 1.0, 250) == _lib.STREAM_GBM
+    assert _lib.select_stream(g, 1.0, 250, _lib.FORCE_SVJ) == _lib.STREAM_SVJ
+    moving = SVJParams(kappa=3.0, theta=0.05, xi=0.0, v0=0.09, lambda_j=0.0)
+    assert _lib.select_stream(moving, 1.0, 250) == _lib.STREAM_GBM                 # deterministic variance: weight table
+    assert _lib.select_stream(moving, 1.0, 5000) == _lib.STREAM_HESTON             # table too long
+    assert _lib.select_stream(SVJParams(lambda_j=0.0), 1.0, 250) == _lib.STREAM_HESTON
+    assert _lib.select_stream(SVJParams(), 1.0, 250) == _lib.STREAM_SVJ
+    # a v0 bump away from theta turns constant variance into a moving one (kappa != 0): still the GBM stream
+    kap = SVJParams(kappa=3.0, theta=0.09, xi=0.0, v0=0.09, lambda_j=0.0)
+    assert _lib.select_stream(kap, 1.0, 250, _lib.GREEKS, _lib.Bumps(0.01, 0.10, 0.08, 0.0651, 0.0649)) == _lib.STREAM_GBM
+    with pytest.raises(_lib.B200MCError):
+        _lib.select_stream(g, -1.0, 250)

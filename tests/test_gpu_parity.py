@@ -194,6 +194,19 @@ def test_fused_jumps_fire_like_reference(H, L, golden):
     np.testing.assert_allclose(S, So, rtol=1e-10)
 
 
+def test_very_long_deterministic_variance_run_uses_the_heston_stream(H, L, golden):
+    """xi = 0 with a moving variance and more steps than the weight table holds: the library falls back to the general
+    stochastic-variance kernel (Heston stream); b200mc_select_stream tells the caller which draws to dump."""
+    p, _ = _mode_params(golden, "detvar")
+    n, steps, T = 64, 4100, 4.0
+    stream = L.select_stream(p, T, steps)
+    assert stream == L.STREAM_HESTON and L.select_stream(p, T, 4096) == L.STREAM_GBM
+    Z = _draws(H, L, 6, n, steps, stream, 0, p, T)
+    want = O._sim(p, 100.0, T, *Z, steps)[0]
+    got = H.simulate_terminal(p, 100.0, T, steps, n, 6, L.FP64, np.float64)[0]
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
 def test_force_svj_on_gbm_params(H, L, golden):
     p, _ = _mode_params(golden, "gbm")
     n, steps, seed = 512, 30, 3
