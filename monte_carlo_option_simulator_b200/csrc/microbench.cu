@@ -9,7 +9,7 @@
 namespace b200mc {
 
 enum { MB_FFMA = 0, MB_IMAD_WIDE = 1, MB_LOP3 = 2, MB_MUFU_EX2 = 3, MB_MUFU_SIN = 4, MB_IADD3 = 5, MB_PHILOX = 6,
-       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_COUNT = 12 };
+       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_COUNT = 15 };
 
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, const __grid_constant__ PhiloxKey key,
@@ -42,6 +42,27 @@ __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, co
                 uint64_t p;
                 asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(p) : "r"(a[k]));
                 a[k] = (uint32_t)(p >> 32);       // hi word feeds the next multiply (a register move at most)
+            }
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s ^= a[k];
+        if (s == 0x12345u) sink[0] = t;
+    } else if constexpr (WHICH == MB_IMAD_LO || WHICH == MB_IMAD_HI || WHICH == MB_IMAD_LOHI) {
+        uint32_t a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = t * 8u + k + seed;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (WHICH == MB_IMAD_LO) asm volatile("mul.lo.u32 %0, %0, 0xD2511F53;" : "+r"(a[k]));
+                else if constexpr (WHICH == MB_IMAD_HI) asm volatile("mul.hi.u32 %0, %0, 0xD2511F53;" : "+r"(a[k]));
+                else {   // the pair that replaces one mul.wide: lo and hi of the same product
+                    uint32_t lo, hi;
+                    asm volatile("mul.lo.u32 %0, %1, 0xD2511F53;" : "=r"(lo) : "r"(a[k]));
+                    asm volatile("mul.hi.u32 %0, %1, 0xD2511F53;" : "=r"(hi) : "r"(a[k]));
+                    a[k] = lo ^ hi;
+                }
             }
         }
         uint32_t s = 0;
@@ -221,7 +242,10 @@ extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double 
         case 8: mb_launch<8>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         case 9: mb_launch<9>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         case 10: mb_launch<10>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        default: mb_launch<11>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 11: mb_launch<11>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 12: mb_launch<12>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 13: mb_launch<13>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        default: mb_launch<14>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         }
         B200MC_CUDA(h, cudaGetLastError());
         B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));

@@ -18,7 +18,7 @@ for combo in range(17):
     floors = (c[0] * 4, c[1] * 2, c[2] * 8, c[3] * 1, sum(c))      # heavy, alu, xu, fp32 (both pipes), issue
     print(f"{combo:3d}   {c[0]:3d} {c[1]:3d} {c[2]:3d} {c[3]:3d}   {r:.4e}   {cyc:8.1f}   floors heavy/alu/xu/fma/issue = {floors} -> {max(floors)}")
 for w, name in enumerate(["FFMA", "IMAD.WIDE", "LOP3", "MUFU.EX2", "MUFU.SIN", "IADD", "philox calls", "philox+BM calls", "FMUL",
-                          "MUFU.LG2", "MUFU.SQRT", "FFMA+LOP3 pairs"]):
+                          "MUFU.LG2", "MUFU.SQRT", "FFMA+LOP3 pairs", "IMAD (mul.lo)", "IMAD.HI (mul.hi)", "mul.lo + mul.hi + xor (per triple)"]):
     r = h.microbench(w)
     print(f"{name:18s} {r:.4e} ops/s = {r / (info['sm_count'] * clk):7.2f} per clk per SM")
 h.close()
