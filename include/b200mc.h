@@ -189,6 +189,13 @@ int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *p, double S
 int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n, int dtype, int on_device,
                         double confidence, double out[8]);
 
+/* Discounted option P&L on the device: pnl[i] = discount * payoff(S[i * stride]) - premium, S and pnl DEVICE pointers
+ * (stride in elements: 1 for a terminal-spot vector, ld for the last column of a path matrix -- pass S + n_steps).
+ * Asynchronous on the handle's stream.  With b200mc_generate_paths / b200mc_simulate_terminal before and
+ * b200mc_risk_metrics after, BASELINE config 4 (paths -> terminal P&L -> VaR/CVaR) never leaves the GPU. */
+int b200mc_option_pnl(b200mc_handle *h, const void *S_dev, int64_t n, int64_t stride, int dtype_in, double strike,
+                      int is_call, double discount, double premium, int dtype_out, void *pnl_dev);
+
 /* Multi-rank form of the same metrics: every rank holds a shard of the P&L vector in its own HBM and
  * calls these three primitives; the host all-reduces their small outputs (2 doubles, 512 counters per radix pass,
  * 6 doubles) and takes the decisions, so every rank walks the same radix tree and ends with the GLOBAL order

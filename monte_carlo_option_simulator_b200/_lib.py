@@ -81,6 +81,7 @@ _PROTOS = {
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                          _u32, C.c_int, C.c_int, _vp, _i64]),
     "b200mc_risk_metrics": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dbl, _dp]),
+    "b200mc_option_pnl": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _dbl, C.c_int, _dbl, _dbl, C.c_int, _vp]),
     "b200mc_risk_begin": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dp]),
     "b200mc_risk_hist": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_u64), C.POINTER(_u64)]),
     "b200mc_risk_finish": (C.c_int, [_vp, _dbl, C.c_int, _dp, _dp]),
@@ -314,6 +315,14 @@ class Handle:
         self._check(self.lib.b200mc_risk_metrics(self.h, a.ctypes.data, a.size, code, 0, float(confidence),
                                                   out.ctypes.data_as(_dp)))
         return out
+
+    def option_pnl(self, S_dev: int, n: int, strike: float, is_call: bool, discount: float, premium: float, pnl_dev: int,
+                   dtype_in=np.float64, dtype_out=np.float64, stride: int = 1):
+        """pnl[i] = discount * payoff(S[i * stride]) - premium, device pointers in and out (asynchronous)."""
+        ci = F64 if np.dtype(dtype_in) == np.float64 else F32
+        co = F64 if np.dtype(dtype_out) == np.float64 else F32
+        self._check(self.lib.b200mc_option_pnl(self.h, _vp(S_dev), int(n), int(stride), ci, float(strike), int(bool(is_call)),
+                                                float(discount), float(premium), co, _vp(pnl_dev)))
 
     # multi-rank tail-metric primitives (host side: risk.compute_risk_metrics_sharded)
     def risk_begin(self, pnl, n: Optional[int] = None, dtype=None) -> np.ndarray:

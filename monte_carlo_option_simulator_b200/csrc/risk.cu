@@ -184,6 +184,20 @@ static int risk_run(b200mc_handle *h, const T *x_dev, int64_t n, double confiden
     return 0;
 }
 
+// Discounted option P&L from terminal spots, element-wise on the device: pnl[i] = discount * payoff(S[i * stride]) - premium
+// (BASELINE config 4: "then a10 on D*max(S_T - K, 0) - premium").  stride > 1 reads a column of a path matrix in place.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(RK_THREADS)
+k_option_pnl(const TI *__restrict__ S, int64_t n, int64_t stride, double strike, int is_call, double discount,
+             double premium, TO *__restrict__ pnl)
+{
+    for (int64_t i = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RK_THREADS) {
+        const double s = (double)S[i * stride];
+        const double pay = is_call ? fmax(s - strike, 0.0) : fmax(strike - s, 0.0);
+        pnl[i] = (TO)(discount * pay - premium);
+    }
+}
+
 // scratch layout shared by the single-call and the multi-rank entry points
 struct RiskScratch {
     unsigned long long *keys;
@@ -210,6 +224,26 @@ static int risk_scratch(b200mc_handle *h, int64_t n, RiskScratch &r)
 
 } // namespace b200mc
 using namespace b200mc;
+
+extern "C" int b200mc_option_pnl(b200mc_handle *h, const void *S_dev, int64_t n, int64_t stride, int dtype_in, double strike,
+                                 int is_call, double discount, double premium, int dtype_out, void *pnl_dev)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!S_dev || !pnl_dev || n <= 0 || stride <= 0) return fail(h, B200MC_EINVAL, "bad argument");
+    if ((dtype_in != B200MC_F32 && dtype_in != B200MC_F64) || (dtype_out != B200MC_F32 && dtype_out != B200MC_F64))
+        return fail(h, B200MC_EINVAL, "dtype must be B200MC_F32 or B200MC_F64");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    int64_t grid = (n + RK_THREADS - 1) / RK_THREADS;
+    const int64_t cap = (int64_t)h->sm_count * 16;
+    if (grid > cap) grid = cap;
+#define PNL(TI, TO) k_option_pnl<TI, TO><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>((const TI *)S_dev, n, stride, strike, is_call, discount, premium, (TO *)pnl_dev)
+    if (dtype_in == B200MC_F32) { if (dtype_out == B200MC_F32) PNL(float, float); else PNL(float, double); }
+    else { if (dtype_out == B200MC_F32) PNL(double, float); else PNL(double, double); }
+#undef PNL
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
 
 // ---- multi-rank primitives: every rank holds a shard of the P&L vector; the host all-reduces the tiny results ----------
 // (1) begin: order-preserving keys of the local shard + local { sum, count of negatives }.

@@ -89,13 +89,26 @@ def compute_risk_metrics_sharded(local_returns, confidence: float = 0.99, *, com
 
 def terminal_pnl_metrics(params, spot: float, strike: float, T: float, n_paths: int, n_steps: int, seed: int = 42,
                          is_call: bool = True, premium: Optional[float] = None, confidence: float = 0.99, *,
-                         handle=None) -> Dict[str, float]:
-    """BASELINE config 4: simulate terminal spots on the device, form the discounted option P&L
-    D*payoff(S_T) - premium on the host and reduce it with compute_risk_metrics."""
+                         handle=None, dtype=np.float64) -> Dict[str, float]:
+    """BASELINE config 4 without leaving the GPU: terminal spots (fused simulator) -> discounted option P&L
+    D * payoff(S_T) - premium -> compute_risk_metrics.  premium defaults to the Monte Carlo price of the same paths."""
     h = handle or _lib.default_handle()
-    S, _, _ = h.simulate_terminal(params, float(spot), float(T), int(n_steps), int(n_paths), seed, 0, np.float64)
-    pay = np.maximum(S - strike, 0.0) if is_call else np.maximum(strike - S, 0.0)
-    disc = np.exp(-params.r * T)
-    if premium is None:
-        premium = float(disc * pay.mean())
-    return compute_risk_metrics(disc * pay - premium, confidence, handle=h)
+    dt = np.dtype(dtype)
+    n = int(n_paths)
+    disc = float(np.exp(-params.r * T))
+    S = h.malloc(n * dt.itemsize)
+    pnl = h.malloc(n * 8)
+    try:
+        h.simulate_terminal(params, float(spot), float(T), int(n_steps), n, seed, _lib.FP64 if dt == np.float64 else 0, dt,
+                            dev_ptrs=(S, None, None))
+        if premium is None:
+            h.option_pnl(S, n, strike, is_call, disc, 0.0, pnl, dtype_in=dt)
+            premium = float(h.risk_metrics(pnl, confidence, n=n, dtype=np.float64)[6])      # mean of D * payoff
+        h.option_pnl(S, n, strike, is_call, disc, premium, pnl, dtype_in=dt)
+        out = h.risk_metrics(pnl, confidence, n=n, dtype=np.float64)
+    finally:
+        h.free(S)
+        h.free(pnl)
+    res = {k: float(v) for k, v in zip(KEYS, out)}
+    res["premium"] = float(premium)
+    return res

@@ -658,6 +658,37 @@ def test_sharded_risk_metrics_equal_the_global_ones(L, garr, world):
                     assert res[r][k] == pytest.approx(w, rel=1e-10, abs=1e-13), (k, world)
 
 
+def test_cfg4_pipeline_stays_on_device(H, L, golden):
+    """paths / terminal spots -> option P&L -> VaR/CVaR, all device resident, against the host pipeline + oracle sort."""
+    from monte_carlo_option_simulator_b200.risk import terminal_pnl_metrics
+    from monte_carlo_option_simulator_b200 import SVJParams
+    p = SVJParams(**golden["params"]["gbm_cfg1"])
+    got = terminal_pnl_metrics(p, 2500.0, 2500.0, 1.0, 200_000, 250, seed=42, handle=H)
+    S = H.simulate_terminal(p, 2500.0, 1.0, 250, 200_000, 42, L.FP64, np.float64)[0]
+    pay = math.exp(-p.r) * np.maximum(S - 2500.0, 0.0)
+    assert got["premium"] == pytest.approx(pay.mean(), rel=1e-12)
+    want = O.risk_metrics(pay - pay.mean(), 0.99)
+    for k, w in want.items():
+        if math.isnan(w):          # all the largest losses are ties (-premium): the Hill sum is 0 -> NaN, as in the reference
+            assert math.isnan(got[k]), k
+        else:
+            assert got[k] == pytest.approx(w, rel=1e-9, abs=1e-9), k
+    # the last column of a device-resident path matrix works as the spot vector (stride = ld)
+    n, steps = 5000, 50
+    mat = H.malloc(n * (steps + 1) * 8)
+    pnl = H.malloc(n * 8)
+    try:
+        H.generate_paths(p, 2500.0, 1.0, steps, n, 3, L.FP64, np.float64, out_dev=mat)
+        H.option_pnl(mat + steps * 8, n, 2400.0, False, 0.9, 10.0, pnl, stride=steps + 1)
+        host = np.empty(n)
+        H.d2h(host, pnl)
+    finally:
+        H.free(mat)
+        H.free(pnl)
+    paths = H.generate_paths(p, 2500.0, 1.0, steps, n, 3, L.FP64, np.float64)
+    np.testing.assert_allclose(host, 0.9 * np.maximum(2400.0 - paths[:, -1], 0.0) - 10.0, rtol=1e-13, atol=1e-12)
+
+
 # ---------------------------------------------------------------------------------------------- patched reference callers
 def test_full_size_linearity_property(H, L, golden):
     """BASELINE config 2 size (1e7 x 250): sums over two halves of the path range add up to the whole-range sums
