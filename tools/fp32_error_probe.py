@@ -22,4 +22,7 @@ for name, (p, T, steps) in cases.items():
     paths32 = h.generate_paths(p, 100.0, T, steps, 2000, 11, 0, np.float32)
     pw = O._sim(O.as_params(p), 100.0, T, *[z[:2000] for z in Z], steps, record=True)[2]
     e1 = np.max(np.abs(S32 / want - 1)); e2 = np.max(np.abs(A32 / wantA - 1)); e3 = np.max(np.abs(paths32 / pw - 1))
+    S64 = h.simulate_terminal(p, 100.0, T, steps, n, 11, _lib.FP64, np.float64)[0]
+    p64 = h.generate_paths(p, 100.0, T, steps, 2000, 11, _lib.FP64, np.float64)
+    print(f"{name:36s} fp64 state: S_T {np.max(np.abs(S64 / want - 1)):.1e} path matrix {np.max(np.abs(p64 / pw - 1)):.1e}")
     print(f"{name:36s} max rel err fp32: S_T {e1:.2e}  twin {e2:.2e}  path matrix {e3:.2e}   (min S_T {want.min():.3g}, max {want.max():.3g})")
