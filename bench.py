@@ -332,6 +332,25 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * N_STEPS * e2e_steps / float(t.item())
 
+    # BASELINE cfg3, benchmark reading: 64 strikes x 16 expiries, 1M paths PER CELL (disjoint counter ranges), cells dealt
+    # round-robin to the ranks, no path-level collective (one all-reduce gathers the 1024 sum vectors)
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine
+    cfg3 = None
+    if not args.no_extras:
+        eng3 = MonteCarloEngine(p, 1_000_000, N_STEPS, 42, use_sobol=False, use_antithetic=False, use_control_variate=False,
+                                rng="philox", handle=h, comm=comm)
+        ks3, Ts3 = np.linspace(0.7, 1.3, 64) * SPOT, [j / 8 for j in range(1, 17)]
+        eng3.price_grid(SPOT, ks3[:2], Ts3[:2], True, independent_cells=True)          # warm-up (kernel load)
+        barrier()
+        t0 = time.perf_counter()
+        g3 = eng3.price_grid(SPOT, ks3, Ts3, True, independent_cells=True)
+        barrier()
+        dt3 = time.perf_counter() - t0
+        work3 = 64 * 1_000_000 * float(g3["num_steps"].sum())
+        cfg3 = {"seconds": dt3, "cells": 1024, "path_steps": work3, "path_steps_per_s": work3 / dt3,
+                "reading": "independent cells: 1M paths per (expiry, strike) cell, cells sharded over the ranks",
+                "atm_1y_price": float(g3["prices"][7, 32]), "atm_1y_std_error": float(g3["std_errors"][7, 32])}
+
     if rank == 0:
         disc = float(np.exp(-p.r * T))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -344,6 +363,7 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": _lib.NSUMS * 8,
                         "api": "GreeksEngine.delta + .vega + .gamma (one fused launch behind them), host dicts out",
                         "ms_per_step": e2e_s / e2e_steps * 1e3},
+                "cfg3_grid_independent_cells": cfg3,
                 "check": {"price": disc * sums[1] / sums[0], "delta_pathwise": disc * sums[9] / sums[0],
                           "api_delta": last[0]["pathwise"], "api_gamma": last[2]["gamma"]}}
         if world == 1 and not args.no_extras:

@@ -312,11 +312,18 @@ class MonteCarloEngine:
                 results.append(res)
         return results
 
-    def price_grid(self, spot: float, strikes, maturities, is_call: bool = True) -> Dict[str, np.ndarray]:
+    def price_grid(self, spot: float, strikes, maturities, is_call: bool = True, *,
+                   independent_cells: bool = False) -> Dict[str, np.ndarray]:
         """NEW (BASELINE config 3): strike x maturity grid in the (n_mat, n_k) layout engine/surface.py:69-126
-        (extract_iv_surface) consumes.  Per expiry this is exactly price_batch (paths shared across strikes, the steps
-        rule of monte_carlo.py:287, same seed); all expiries are queued on the stream before one synchronisation and one
-        device->host copy of the sums.  Returns prices, std_errors (raw, as price_batch), num_steps."""
+        (extract_iv_surface) consumes.  Returns prices, std_errors (raw, as price_batch), num_steps.
+
+        independent_cells=False (API-parity reading): per expiry this is exactly price_batch -- paths shared across
+        strikes, the steps rule of monte_carlo.py:287, same seed -- one fused launch per expiry; with a communicator the
+        PATHS of every expiry are sharded and the sums all-reduced once.
+        independent_cells=True (benchmark reading): every (expiry, strike) cell gets its own num_paths paths (disjoint
+        Philox counter ranges: path_offset = cell * num_paths), one launch per cell; with a communicator the CELLS are
+        dealt round-robin to the ranks and no path-level collective is needed (only the final gather of the sums).
+        All launches are queued on the stream before one synchronisation and one device->host copy."""
         if self.rng == "reference":
             rows = [self._price_batch_reference(spot, strikes, float(T), is_call) for T in maturities]
             steps = [steps_for(self.num_steps, float(T)) for T in maturities]
@@ -330,22 +337,34 @@ class MonteCarloEngine:
             h = self.handle
             steps = [steps_for(self.num_steps, T) for T in Ts]
             n = int(self.num_paths)
-            lo, hi = 0, n
-            if self.comm is not None and self.comm.world > 1:
-                from .dist import shard_range
-                lo, hi = shard_range(n, self.comm.rank, self.comm.world)
+            rank, world = (self.comm.rank, self.comm.world) if self.comm is not None else (0, 1)
             nbytes = len(Ts) * ks.size * NSUMS * 8
             buf = h.malloc(nbytes)
             try:
                 sums = np.zeros((len(Ts), ks.size, NSUMS))
-                if hi > lo:
+                h.h2d(buf, sums)
+                if independent_cells:
                     for j, (T, st) in enumerate(zip(Ts, steps)):
-                        h.price_european(p, float(spot), T, st, hi - lo, self.seed, ks, is_call, self._flags(), None,
-                                         path_offset=lo, out_dev=buf + j * ks.size * NSUMS * 8)
+                        for i in range(ks.size):
+                            cell = j * ks.size + i
+                            if cell % world != rank:
+                                continue
+                            h.price_european(p, float(spot), T, st, n, self.seed, ks[i:i + 1], is_call, self._flags(), None,
+                                             path_offset=cell * n, out_dev=buf + cell * NSUMS * 8)
                     h.d2h(sums, buf)
+                else:
+                    lo, hi = 0, n
+                    if world > 1:
+                        from .dist import shard_range
+                        lo, hi = shard_range(n, rank, world)
+                    if hi > lo:
+                        for j, (T, st) in enumerate(zip(Ts, steps)):
+                            h.price_european(p, float(spot), T, st, hi - lo, self.seed, ks, is_call, self._flags(), None,
+                                             path_offset=lo, out_dev=buf + j * ks.size * NSUMS * 8)
+                        h.d2h(sums, buf)
             finally:
                 h.free(buf)
-            if self.comm is not None and self.comm.world > 1:
+            if world > 1:
                 sums = self.comm.allreduce_sum(sums).reshape(len(Ts), ks.size, NSUMS)
             rows = []
             for T, block in zip(Ts, sums):

@@ -460,6 +460,34 @@ def test_price_grid_equals_price_batch_per_expiry(golden):
         bs = np.array([O.bs_price(2500.0, K, T, p.r, p.q, 0.3, True) for K in ks])
         assert np.all(np.abs(g["prices"][j] - bs) <= 4.5 * g["std_errors"][j] + 1e-9)
     assert np.all(np.diff(g["prices"], axis=1) <= 1e-9)          # calls decrease in strike (same paths)
+    # benchmark reading: every cell has its own paths (disjoint counter ranges); cells dealt to ranks give the same grid
+    from monte_carlo_option_simulator_b200.dist import Comm
+    ind = eng.price_grid(2500.0, ks[::8], Ts[:2], True, independent_cells=True)
+    assert ind["prices"].shape == (2, 8)
+    one = MonteCarloEngine(p, 200_000, 250, 42, use_sobol=False, use_antithetic=True, use_control_variate=False, rng="philox")
+    cell = 1 * 8 + 3
+    row = one.handle.price_european(p, 2500.0, Ts[1], 62, 200_000, 42, [ks[24]], True, one._flags(), None, path_offset=cell * 200_000)[0]
+    assert ind["prices"][1, 3] == pytest.approx(math.exp(-p.r * Ts[1]) * 0.5 * (row[1] + row[2]) / row[0], rel=1e-12)
+    # three emulated ranks (threads, one handle each): cells are dealt round-robin, one all-reduce gathers the sums
+    import threading
+    from monte_carlo_option_simulator_b200 import _lib
+    shared = {"buf": [None] * 3, "bar": threading.Barrier(3)}
+    res = [None] * 3
+
+    def run(r):
+        hh = _lib.Handle(0)
+        try:
+            e3 = MonteCarloEngine(p, 200_000, 250, 42, use_sobol=False, use_antithetic=True, use_control_variate=False,
+                                  rng="philox", handle=hh, comm=_ThreadComm(r, 3, shared))
+            res[r] = e3.price_grid(2500.0, ks[::8], Ts[:2], True, independent_cells=True)
+        finally:
+            hh.close()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for r in range(3):
+        np.testing.assert_allclose(res[r]["prices"], ind["prices"], rtol=1e-12)
 
 
 # ---------------------------------------------------------------------------------------------- Greeks
