@@ -213,6 +213,14 @@ class MonteCarloEngine:
             self._handle = _lib.default_handle()
         return self._handle
 
+    def _extra_handles(self, k: int):
+        """k more handles on the device of self.handle (own stream, scratch and counters), created once per engine."""
+        have = getattr(self, "_lanes", [])
+        while len(have) < k:
+            have.append(_lib.Handle(self.handle.device))
+        self._lanes = have
+        return have[:max(k, 0)]
+
     # ---- fused path -------------------------------------------------------------------------------------
     def _flags(self) -> int:
         return (ANTITHETIC if self.use_antithetic else 0) | (FP64 if self.precision == "fp64" else 0)
@@ -344,13 +352,19 @@ class MonteCarloEngine:
                 sums = np.zeros((len(Ts), ks.size, NSUMS))
                 h.h2d(buf, sums)
                 if independent_cells:
-                    for j, (T, st) in enumerate(zip(Ts, steps)):
-                        for i in range(ks.size):
-                            cell = j * ks.size + i
-                            if cell % world != rank:
-                                continue
-                            h.price_european(p, float(spot), T, st, n, self.seed, ks[i:i + 1], is_call, self._flags(), None,
-                                             path_offset=cell * n, out_dev=buf + cell * NSUMS * 8)
+                    # cells are small launches (1M paths x 31..500 steps = 20..300 us): a few handles (= streams with
+                    # their own scratch) on the same device let the tail of one launch overlap the head of the next
+                    lanes = [h] + self._extra_handles(int(os.environ.get("B200MC_GRID_STREAMS", "4")) - 1)
+                    mine = [(j, i) for j in range(len(Ts)) for i in range(ks.size) if (j * ks.size + i) % world == rank]
+                    mine.sort(key=lambda ji: -steps[ji[0]])                  # longest first
+                    h.synchronize()                                          # the zero-fill above is on h's stream
+                    for q, (j, i) in enumerate(mine):
+                        cell = j * ks.size + i
+                        lanes[q % len(lanes)].price_european(p, float(spot), Ts[j], steps[j], n, self.seed, ks[i:i + 1],
+                                                             is_call, self._flags(), None, path_offset=cell * n,
+                                                             out_dev=buf + cell * NSUMS * 8)
+                    for lane in lanes[1:]:
+                        lane.synchronize()
                     h.d2h(sums, buf)
                 else:
                     lo, hi = 0, n
