@@ -11,6 +11,10 @@
 // 16 consecutive doubles (one full 128-byte line), the tile is parked in shared memory with a padded pitch, and
 // each lane then reads its own row.  The optional path record goes the other way through the same kind of tile.
 // Arrays the parameters make irrelevant (Z2 when xi == 0, the jump arrays when lambda_j <= 0) are never read.
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b200mc {
@@ -104,6 +108,58 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
             v_final[me] = v;
         }
     }
+}
+
+// Host -> device copy of a large PAGEABLE array at PCIe speed.  A plain cudaMemcpy from pageable memory is staged by
+// the driver through one thread (measured 11 GB/s); here H2D_THREADS workers each own two pinned 4 MiB buffers and a
+// stream: they memcpy their slices into pinned memory and hand them to the DMA engine, so the CPU copy is parallel and
+// overlaps the transfers.  The pinned pool (64 MiB) is allocated once per handle.
+constexpr int H2D_THREADS = 8;
+constexpr size_t H2D_CHUNK = (size_t)4 << 20;
+
+static int parallel_h2d(b200mc_handle *h, void *dst, const void *src, size_t bytes)
+{
+    if (bytes < 8 * H2D_CHUNK) {
+        B200MC_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    B200MC_TRY(ensure(h, &h->h_pool, &h->h_pool_bytes, (size_t)H2D_THREADS * 2 * H2D_CHUNK, true));
+    const size_t n_chunks = (bytes + H2D_CHUNK - 1) / H2D_CHUNK;
+    std::vector<cudaError_t> err(H2D_THREADS, cudaSuccess);
+    std::vector<std::thread> workers;
+    const int device = h->device;
+    char *pool = (char *)h->h_pool;
+    for (int t = 0; t < H2D_THREADS; ++t) {
+        workers.emplace_back([=, &err]() {
+            cudaError_t e = cudaSetDevice(device);
+            cudaStream_t st = nullptr;
+            cudaEvent_t ev[2] = {nullptr, nullptr};
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+            char *buf[2] = {pool + (size_t)(2 * t) * H2D_CHUNK, pool + (size_t)(2 * t + 1) * H2D_CHUNK};
+            int k = 0;
+            for (size_t c = t; c < n_chunks && e == cudaSuccess; c += H2D_THREADS, k ^= 1) {
+                const size_t off = c * H2D_CHUNK, len = std::min(H2D_CHUNK, bytes - off);
+                e = cudaEventSynchronize(ev[k]);                       // the DMA that last read this buffer is done
+                if (e != cudaSuccess) break;
+                memcpy(buf[k], (const char *)src + off, len);
+                e = cudaMemcpyAsync((char *)dst + off, buf[k], len, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[k], st);
+            }
+            if (st) {
+                const cudaError_t e2 = cudaStreamSynchronize(st);
+                if (e == cudaSuccess) e = e2;
+                cudaStreamDestroy(st);
+            }
+            for (int q = 0; q < 2; ++q)
+                if (ev[q]) cudaEventDestroy(ev[q]);
+            err[t] = e;
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (int t = 0; t < H2D_THREADS; ++t)
+        if (err[t] != cudaSuccess) return fail(h, B200MC_ECUDA, "parallel host->device copy failed: %s", cudaGetErrorString(err[t]));
+    return 0;
 }
 
 static int check_given(b200mc_handle *h, const b200mc_svj_params *p, int64_t n_paths, int32_t n_steps, double T,
@@ -207,9 +263,7 @@ extern "C" int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_
     for (int64_t p0 = 0; p0 < n_paths; p0 += chunk) {
         const int64_t np = (n_paths - p0 < chunk) ? (n_paths - p0) : chunk;
         for (int i = 0; i < 4; ++i) {
-            if (use[i])
-                B200MC_CUDA(h, cudaMemcpyAsync(dZ[i], src[i] + (size_t)p0 * n_steps, (size_t)np * in_row,
-                                               cudaMemcpyHostToDevice, h->stream));
+            if (use[i]) B200MC_TRY(parallel_h2d(h, dZ[i], src[i] + (size_t)p0 * n_steps, (size_t)np * in_row));
         }
         a.n_paths = np;
         B200MC_TRY(launch_given(h, a, dZ[0], dZ[1] ? dZ[1] : dZ[0], dZ[2] ? dZ[2] : dZ[0], dZ[3] ? dZ[3] : dZ[0], dS, dv,

@@ -66,6 +66,7 @@ extern "C" int b200mc_destroy(b200mc_handle *h)
     if (h->d_result) cudaFree(h->d_result);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->h_result) cudaFreeHost(h->h_result);
+    if (h->h_pool) cudaFreeHost(h->h_pool);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
