@@ -95,7 +95,7 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *red = reinterpret_cast<double *>(smem_raw);                   // [256]
     double *strikes = red + EU_THREADS;                                   // [n_strikes]
-    R *sT = reinterpret_cast<R *>(strikes + a.n_strikes);                 // [NS][256]   (not SINGLE)
+    R *sT = reinterpret_cast<R *>(strikes + ((a.n_strikes + 1) & ~1));    // [NS][256]   (not SINGLE); 16-byte aligned
     R *sW = sT + (SINGLE ? 0 : NS * EU_THREADS);                          // [256]  sum of raw z (not SINGLE)
     R *wtab = sW + (SINGLE ? 0 : EU_THREADS);                             // [3][wld] (DETVAR)
 
@@ -250,7 +250,7 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
     EuroKernel kern = fp64 ? pick1<double>(pr.mode, anti, greeks, single) : pick1<float>(pr.mode, anti, greeks, single);
     const int ns = 1 + (anti ? 1 : 0) + (greeks ? 2 : 0);
     const size_t rsz = fp64 ? 8 : 4;
-    size_t smem = (size_t)(EU_THREADS + n_strikes) * 8 + (single ? 0 : (size_t)(ns + 1) * EU_THREADS * rsz);
+    size_t smem = (size_t)(EU_THREADS + ((n_strikes + 1) & ~1)) * 8 + (single ? 0 : (size_t)(ns + 1) * EU_THREADS * rsz);
     if (pr.mode == MODE_DETVAR) smem += (size_t)3 * pr.wld * rsz;
     if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
     // dynamic-smem opt-in and occupancy are properties of (kernel, smem): query once, then reuse (small calls are

@@ -174,12 +174,23 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
             const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
                       b3 = box_muller_word(u.w);
             const R z[8] = {(R)b0.rc, (R)b0.rs, (R)b1.rc, (R)b1.rs, (R)b2.rc, (R)b2.rs, (R)b3.rc, (R)b3.rs};
+            // the 8 weights of a row come in with 128-bit shared loads (rows are 16-byte aligned, wld % 8 == 0): every
+            // scalar LDS would be one more entry in the MIO queue the MUFUs already saturate
+            R w[NS][8];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                if (ANTI && k == 1) continue;
+                const int4 *src = reinterpret_cast<const int4 *>(wtab + row(k) * wld + 8 * j);
+                int4 *dst = reinterpret_cast<int4 *>(w[k]);
+#pragma unroll
+                for (int q = 0; q < (int)(8 * sizeof(R) / 16); ++q) dst[q] = src[q];
+            }
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     if (ANTI && k == 1) continue;
-                    acc[k] += wtab[row(k) * wld + 8 * j + t] * z[t];
+                    acc[k] += w[k][t] * z[t];
                 }
                 if constexpr (Rec::enabled) { if (8 * j + t < n_steps) rec(8 * j + t, acc[0]); }
             }

@@ -12,7 +12,10 @@ h = _lib.Handle(0)
 g = SVJParams.gbm(0.3, r=0.065)
 bumps = _lib.Bumps(0.01, g.v0 + 0.01, g.v0 - 0.01, g.r + 1e-4, g.r - 1e-4)
 out = h.malloc(17 * 8 * 256)
+gk = SVJParams(kappa=3.0, theta=0.09, xi=0.0, rho=0.0, v0=0.09, lambda_j=0.0, mu_j=0.0, sigma_j=0.0, r=0.065, q=0.0)
 cases = [("gbm fp32 greeks", g, _lib.GREEKS, bumps, [2500.0], 2500.0, n),
+         ("kappa=3 fp32 greeks (detvar)", gk, _lib.GREEKS, bumps, [2500.0], 2500.0, n),
+         ("kappa=3 fp32 price (gbm)", gk, 0, None, [2500.0], 2500.0, n),
          ("gbm fp32 price", g, 0, None, [2500.0], 2500.0, n),
          ("gbm fp32 anti", g, _lib.ANTITHETIC, None, [2500.0], 2500.0, n),
          ("gbm fp64 price", g, _lib.FP64, None, [2500.0], 2500.0, n),
@@ -28,5 +31,5 @@ for name, p, fl, b, ks, s0, nn in cases:
         ms = h.timer_end()
         if r:
             best = min(best, ms)
-    print(f"{name:22s} {nn:9d} paths x 250: {best:8.3f} ms  {nn * 250 / best / 1e9:8.2f} Gpath-steps/ms -> {nn * 250 / best / 1e6:9.1f} G/s", flush=True)
+    print(f"{name:28s} {nn:9d} paths x 250: {best:8.3f} ms  {nn * 250 / best / 1e9:8.2f} Gpath-steps/ms -> {nn * 250 / best / 1e6:9.1f} G/s", flush=True)
 h.close()
