@@ -25,6 +25,7 @@ struct b200mc_handle {
     void *h_result;         size_t h_result_bytes;     // pinned landing buffer of those results
     void *h_pool;           size_t h_pool_bytes;       // pinned chunk pool of the parallel host->device copy
     bool own_stream;                                   // false after b200mc_set_stream
+    int smem_optin;                                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
     const void *occ_kern[64]; size_t occ_smem[64]; int occ_val[64]; int n_occ;   // (kernel, smem) -> resident CTAs per SM
     const void *risk_x; int64_t risk_n; int risk_dtype; // vector of the multi-rank tail-metric primitives (risk.cu)
     unsigned int *d_counter;                           // "last block reduces" ticket

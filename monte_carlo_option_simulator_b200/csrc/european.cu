@@ -259,7 +259,11 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
     for (int i = 0; i < h->n_occ; ++i)
         if (h->occ_kern[i] == (const void *)kern && h->occ_smem[i] == smem) occ = h->occ_val[i];
     if (occ == 0) {
-        B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the attribute is a CAP on the dynamic shared memory of later launches, not a reservation: raise it to the
+        // device limit once and never lower it (setting it to this call's size would make a later, larger launch of
+        // the same kernel fail with "invalid argument" when its occupancy comes out of the cache)
+        B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            h->smem_optin - 1024));      // minus the kernel's few static bytes
         B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)kern, EU_THREADS, smem));
         if (occ < 1) return fail(h, B200MC_ECUDA, "fused kernel does not fit on an SM");
         const int slot = h->n_occ < 64 ? h->n_occ++ : 63;

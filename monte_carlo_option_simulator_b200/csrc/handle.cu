@@ -39,6 +39,7 @@ extern "C" int b200mc_create(int device, b200mc_handle **out)
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     h->sm_clock_khz = khz;
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaError_t e1 = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaEventCreate(&h->ev0);
     cudaError_t e3 = cudaEventCreate(&h->ev1);

@@ -178,6 +178,48 @@ def test_fused_terminal_identical_draws(H, L, golden, mode, steps):
     np.testing.assert_allclose(V32, vo, rtol=2e-3, atol=2e-6)   # variance near the zero boundary amplifies fp32 rounding
 
 
+@pytest.mark.parametrize("case", range(24))
+def test_fused_random_configurations(H, L, case):
+    """Randomised deterministic-mode parity: random SVJ parameters (every mode), shapes, offsets (also across the
+    2^32 path-index carry), flags; terminal values, variance, sums and the path matrix against the oracle fed the
+    identical draws (fp64 state)."""
+    g = np.random.default_rng(1000 + case)
+    xi = 0.0 if g.random() < 0.4 else float(g.uniform(0.05, 1.2))
+    lam = 0.0 if g.random() < 0.5 else float(g.uniform(0.2, 8.0))
+    kappa = 0.0 if g.random() < 0.25 else float(g.uniform(0.2, 6.0))
+    v0 = float(g.uniform(0.005, 0.3))
+    theta = v0 if g.random() < 0.3 else float(g.uniform(0.005, 0.3))
+    p = O.Params(kappa=kappa, theta=theta, xi=xi, rho=float(g.uniform(-0.95, 0.95)), v0=v0, lambda_j=lam,
+                 mu_j=float(g.uniform(-0.2, 0.1)), sigma_j=float(g.uniform(0.01, 0.3)), r=float(g.uniform(0.0, 0.1)),
+                 q=float(g.uniform(0.0, 0.05)))
+    n, steps = int(g.integers(1, 700)), int(g.integers(1, 300))
+    T = float(g.uniform(0.02, 3.0))
+    S0 = float(g.uniform(1.0, 30000.0))
+    seed = int(g.integers(0, 2 ** 63))
+    off = int(g.choice([0, 17, 2 ** 32 - n // 2 - 1, 2 ** 40 + 3]))
+    anti = bool(g.integers(0, 2))
+    fl = L.FP64 | (L.ANTITHETIC if anti else 0)
+    stream = L.select_stream(p, T, steps, fl)
+    Z1, Z2, Zj, Zjs = _draws(H, L, seed, n, steps, stream, off, p, T)
+    So, vo, po = O._sim(p, S0, T, Z1, Z2, Zj, Zjs, steps, record=True)
+    S, A, V = H.simulate_terminal(p, S0, T, steps, n, seed, fl, np.float64, off, anti, True)
+    np.testing.assert_allclose(S, So, rtol=2e-9)
+    np.testing.assert_allclose(V, vo, rtol=1e-8, atol=1e-14)
+    if anti:
+        np.testing.assert_allclose(A, O._sim(p, S0, T, -Z1, -Z2, Zj, -Zjs, steps)[0], rtol=2e-9)
+    np.testing.assert_allclose(H.generate_paths(p, S0, T, steps, n, seed, L.FP64, np.float64, off), po, rtol=2e-9)
+    ks = sorted(float(S0 * x) for x in g.uniform(0.6, 1.4, size=int(g.choice([1, 2, 7]))))
+    is_call = bool(g.integers(0, 2))
+    rows = H.price_european(p, S0, T, steps, n, seed, ks, is_call, fl, None, path_offset=off)
+    for K, row in zip(ks, rows):
+        pay = np.maximum(S - K, 0.0) if is_call else np.maximum(K - S, 0.0)
+        assert row[0] == n and row[1] == pytest.approx(pay.sum(), rel=1e-11, abs=1e-9)
+        assert row[3] == pytest.approx((pay * pay).sum(), rel=1e-11, abs=1e-9)
+    # fp32 state on the same draws: inside the north star's 1e-4 unless the variance sits on the zero boundary
+    S32 = H.simulate_terminal(p, S0, T, steps, n, seed, 0, np.float32, off)[0]
+    assert np.median(np.abs(S32 / So - 1)) < 2e-6
+
+
 def test_fused_jumps_fire_like_reference(H, L, golden):
     """A jump-heavy parameter set: the integer jump test in the kernel must equal the reference's float compare."""
     p = P(golden, "jumpy")
@@ -305,6 +347,16 @@ def test_edge_shapes(H, L, golden, mode):
         np.testing.assert_allclose(paths[:, -1], want, rtol=1e-9)
     with pytest.raises(L.B200MCError):
         H.price_european(p, 100.0, 1.0, 10, 10, 1, list(np.linspace(60.0, 140.0, 257)))
+
+
+def test_strike_count_sequence_regression(H, L, golden):
+    """Regression (found by the randomised test): large, small, large strike counts on the same kernel -- the cached
+    launch configuration must not leave the dynamic shared-memory cap at the smaller size."""
+    p, _ = _mode_params(golden, "svj")
+    for nk in (64, 2, 64, 7, 256, 3, 256):
+        ks = list(np.linspace(80.0, 120.0, nk))
+        rows = H.price_european(p, 100.0, 0.5, 16, 700, 1, ks, True, L.FP64)
+        assert rows.shape == (nk, L.NSUMS) and np.all(rows[:, 0] == 700)
 
 
 def test_fused_fp32_sums_close_to_fp64(H, L, golden):
