@@ -359,6 +359,47 @@ def test_strike_count_sequence_regression(H, L, golden):
         assert rows.shape == (nk, L.NSUMS) and np.all(rows[:, 0] == 700)
 
 
+@pytest.mark.parametrize("case", range(12))
+def test_greek_sums_random_configurations(H, L, case):
+    """Randomised parameters / bumps / strike counts: every bump accumulator of the fused launch against oracle
+    re-simulation on the identical draws (the reference's CRN construction), antithetic on or off."""
+    g = np.random.default_rng(2000 + case)
+    xi = 0.0 if g.random() < 0.4 else float(g.uniform(0.05, 1.0))
+    lam = 0.0 if g.random() < 0.5 else float(g.uniform(0.2, 6.0))
+    kappa = 0.0 if g.random() < 0.3 else float(g.uniform(0.2, 5.0))
+    v0 = float(g.uniform(0.02, 0.25))
+    p = O.Params(kappa=kappa, theta=v0 if g.random() < 0.3 else float(g.uniform(0.02, 0.25)), xi=xi,
+                 rho=float(g.uniform(-0.9, 0.9)), v0=v0, lambda_j=lam, mu_j=float(g.uniform(-0.15, 0.05)),
+                 sigma_j=float(g.uniform(0.02, 0.25)), r=float(g.uniform(0.0, 0.08)), q=float(g.uniform(0.0, 0.04)))
+    n, steps, T, S0 = int(g.integers(50, 900)), int(g.integers(3, 120)), float(g.uniform(0.05, 2.0)), float(g.uniform(50, 5000))
+    b = float(g.choice([0.01, 0.02, 0.005]))
+    bumps = L.Bumps(b, p.v0 + 0.01, max(p.v0 - 0.01, 0.001), p.r + 1e-4, max(p.r - 1e-4, 0))
+    anti = bool(g.integers(0, 2))
+    fl = L.FP64 | L.GREEKS | (L.ANTITHETIC if anti else 0)
+    is_call = bool(g.integers(0, 2))
+    ks = sorted(float(S0 * x) for x in g.uniform(0.7, 1.3, size=int(g.choice([1, 3]))))
+    seed = int(g.integers(0, 2 ** 40))
+    stream = L.select_stream(p, T, steps, fl, bumps)
+    Z = _draws(H, L, seed, n, steps, stream, 0, p, T)
+    rows = H.price_european(p, S0, T, steps, n, seed, ks, is_call, fl, bumps)
+    S = O._sim(p, S0, T, *Z, steps)[0]
+    for K, row in zip(ks, rows):
+        col = {k: row[i] for i, k in enumerate(L.SUMS_FIELDS)}
+        pay = (lambda s: np.maximum(s - K, 0.0)) if is_call else (lambda s: np.maximum(K - s, 0.0))
+        itm = (S > K) if is_call else (S < K)
+        want = {"sum_a": pay(S).sum(), "sum_pw_delta": (itm * S / S0).sum(),
+                "sum_spot_up": pay(O._sim(p, S0 * (1 + b), T, *Z, steps)[0]).sum(),
+                "sum_spot_dn": pay(O._sim(p, S0 * (1 - b), T, *Z, steps)[0]).sum(),
+                "sum_v0_up": pay(O._sim(p, S0, T, *Z, steps, v0=bumps.v0_up)[0]).sum(),
+                "sum_v0_dn": pay(O._sim(p, S0, T, *Z, steps, v0=bumps.v0_dn)[0]).sum(),
+                "sum_r_up": pay(O._sim(p.replace(r=bumps.r_up), S0, T, *Z, steps)[0]).sum(),
+                "sum_r_dn": pay(O._sim(p.replace(r=bumps.r_dn), S0, T, *Z, steps)[0]).sum()}
+        if anti:
+            want["sum_b"] = pay(O._sim(p, S0, T, -Z[0], -Z[1], Z[2], -Z[3], steps)[0]).sum()
+        for k, w in want.items():
+            assert col[k] == pytest.approx(w, rel=2e-9, abs=1e-7), (k, K)
+
+
 def test_fused_fp32_sums_close_to_fp64(H, L, golden):
     p, _ = _mode_params(golden, "gbm")
     ks = list(np.linspace(0.8, 1.2, 5) * 2500.0)
@@ -662,6 +703,36 @@ def test_risk_metrics_large_and_fp32(H):
     got32 = H.risk_metrics(x32, 0.95)
     want32 = O.risk_metrics(x32.astype(np.float64), 0.95)
     assert got32[0] == pytest.approx(want32["var"], rel=1e-12) and got32[1] == pytest.approx(want32["cvar"], rel=1e-9)
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_risk_metrics_random(H, case):
+    """Randomised: sizes from 1 to 3e5, heavy tails, heavy ties, few or no losses, float32 input, several confidence
+    levels -- device radix select against the oracle's sort (engine/risk.py:117-173 conventions)."""
+    g = np.random.default_rng(500 + case)
+    n = int(g.choice([1, 2, 19, 21, 22, 97, 1000, 4001, 50_000, 300_001]))
+    kind = int(g.integers(0, 5))
+    if kind == 0:
+        x = g.standard_normal(n) * 0.02
+    elif kind == 1:
+        x = g.standard_t(3, size=n) * 0.01
+    elif kind == 2:
+        x = np.round(g.standard_normal(n), 1)                  # heavy ties, exact zeros
+    elif kind == 3:
+        x = np.abs(g.standard_normal(n)) + (g.random(n) < 15 / max(n, 15)) * -5.0     # ~15 losses at most
+    else:
+        x = -np.abs(g.standard_t(4, size=n))                    # every return is a loss
+    conf = float(g.choice([0.9, 0.95, 0.99, 0.999]))
+    if bool(g.integers(0, 2)):
+        x = x.astype(np.float32)
+    got = H.risk_metrics(x, conf)
+    want = O.risk_metrics(x.astype(np.float64), conf)
+    for k, v in zip(("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std"), got):
+        w = want[k]
+        if math.isnan(w):
+            assert math.isnan(v), (k, n, kind)
+        else:
+            assert v == pytest.approx(w, rel=1e-9, abs=1e-12), (k, n, kind)
 
 
 def test_risk_metrics_edge_cases(H, L):
