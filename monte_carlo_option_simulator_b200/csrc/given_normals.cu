@@ -7,10 +7,12 @@
 // the last-bit behaviour of exp().
 //
 // The arrays are path-major, so "one thread per path" would read with a stride of n_steps*8 bytes.  Each warp
-// instead owns 32 consecutive paths and walks the time axis in tiles of 16 steps: a half-warp loads one path's
-// 16 consecutive doubles (one full 128-byte line), the tile is parked in shared memory with a padded pitch, and
-// each lane then reads its own row.  The optional path record goes the other way through the same kind of tile.
-// Arrays the parameters make irrelevant (Z2 when xi == 0, the jump arrays when lambda_j <= 0) are never read.
+// instead owns 32 consecutive paths and walks the time axis in tiles of 8 steps: a quarter-warp loads one path's
+// 8 consecutive doubles (two full sectors), the tile is parked in shared memory with a padded pitch, and each lane
+// then reads its own row.  The optional path record goes the other way through the same kind of tile.
+// Arrays the parameters make irrelevant (Z2 when xi == 0, the jump arrays when lambda_j <= 0) are never read and get
+// no tile: shared memory per warp is 2.3 KB per array in use, which is what sets the number of resident warps -- the
+// per-step fp64 chain (sqrt, exp, separately rounded products) has a latency of several hundred cycles and needs them.
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -20,7 +22,7 @@
 namespace b200mc {
 
 constexpr int GN_WARPS = 4;
-constexpr int GN_TS = 16;                 // steps per tile
+constexpr int GN_TS = 8;                  // steps per tile
 constexpr int GN_PITCH = GN_TS + 1;
 
 struct GivenArgs {
@@ -30,30 +32,43 @@ struct GivenArgs {
     int32_t need_z2, need_jump, record;
 };
 
-__device__ __forceinline__ void load_tile(double *tile, const double *__restrict__ src, int64_t path0, int64_t n_paths,
-                                          int n_steps, int s0, int lane)
+// lane (sub = lane >> 3, col = lane & 7) fetches element [path0 + 4 it + sub][s0 + col] for it = 0..7.  `rowptr` already
+// points at [path0 + sub][col] of the array, so the address of each load is one 64-bit add away (the full index
+// arithmetic per load costs more issue slots than the fp64 step itself).
+__device__ __forceinline__ void load_tile(double *tile, const double *__restrict__ rowptr, size_t stride4, int s0,
+                                          bool full, int rows_left, int cols_left, int lane)
 {
-    const int col = lane & 15, half = lane >> 4;
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-        const int row = 2 * it + half;
-        const int64_t p = path0 + row;
-        double val = 0.0;
-        if (p < n_paths && s0 + col < n_steps) val = __ldg(src + (size_t)p * n_steps + s0 + col);
-        tile[row * GN_PITCH + col] = val;
+    const int col = lane & 7, sub = lane >> 3;
+    const double *p = rowptr + s0;
+    if (full) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            tile[(4 * it + sub) * GN_PITCH + col] = __ldg(p);
+            p += stride4;
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int row = 4 * it + sub;
+            tile[row * GN_PITCH + col] = (row < rows_left && col < cols_left) ? __ldg(p) : 0.0;
+            p += stride4;
+        }
     }
 }
 
-__global__ void __launch_bounds__(GN_WARPS * 32)
+__global__ void __launch_bounds__(GN_WARPS * 32, 6)
 k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ Z1, const double *__restrict__ Z2,
                 const double *__restrict__ Zj, const double *__restrict__ Zjs, double *__restrict__ S_final,
                 double *__restrict__ v_final, double *__restrict__ all_paths)
 {
-    extern __shared__ __align__(16) double gn_tiles[];          // [GN_WARPS][5][32 * GN_PITCH]
+    extern __shared__ __align__(16) double gn_tiles[];          // [GN_WARPS][tiles in use][32 * GN_PITCH]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TILE = 32 * GN_PITCH;
-    double *t1 = gn_tiles + (size_t)warp * 5 * TILE, *t2 = t1 + TILE, *tj = t2 + TILE, *tjs = tj + TILE,
-           *tout = tjs + TILE;
+    const int ntile = 1 + a.need_z2 + 2 * a.need_jump + a.record;
+    double *t1 = gn_tiles + (size_t)warp * ntile * TILE;
+    double *t2 = t1 + TILE;                                   // valid only when need_z2
+    double *tj = t1 + (1 + a.need_z2) * TILE, *tjs = tj + TILE;   // valid only when need_jump
+    double *tout = t1 + (ntile - 1) * TILE;                   // valid only when record
     const int64_t n_groups = (a.n_paths + 31) / 32;
     for (int64_t g = (int64_t)blockIdx.x * GN_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * GN_WARPS) {
         const int64_t path0 = g * 32, me = path0 + lane;
@@ -61,13 +76,17 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
         if (a.record) {
             if (me < a.n_paths) all_paths[(size_t)me * (a.n_steps + 1)] = a.S0;  // :217
         }
+        const int rows_left = (int)((a.n_paths - path0) < 32 ? (a.n_paths - path0) : 32);
+        const size_t lane_off = (size_t)(path0 + (lane >> 3)) * a.n_steps + (lane & 7), stride4 = (size_t)4 * a.n_steps;
         for (int s0 = 0; s0 < a.n_steps; s0 += GN_TS) {
+            const int cols_left = a.n_steps - s0;
+            const bool full = rows_left == 32 && cols_left >= GN_TS;
             __syncwarp();
-            load_tile(t1, Z1, path0, a.n_paths, a.n_steps, s0, lane);
-            if (a.need_z2) load_tile(t2, Z2, path0, a.n_paths, a.n_steps, s0, lane);
+            load_tile(t1, Z1 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+            if (a.need_z2) load_tile(t2, Z2 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
             if (a.need_jump) {
-                load_tile(tj, Zj, path0, a.n_paths, a.n_steps, s0, lane);
-                load_tile(tjs, Zjs, path0, a.n_paths, a.n_steps, s0, lane);
+                load_tile(tj, Zj + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+                load_tile(tjs, Zjs + lane_off, stride4, s0, full, rows_left, cols_left, lane);
             }
             __syncwarp();
             const int ns = min(GN_TS, a.n_steps - s0);
@@ -76,9 +95,10 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
                 const double v_pos = fmax(v, 0.0);                               // :223
                 const double sqrt_v = sqrt(v_pos);                               // :224
                 const double dW1 = __dmul_rn(z1, a.sqrt_dt);                     // :226
-                double dW2 = __dmul_rn(__dmul_rn(a.rho, z1), a.sqrt_dt);         // :227
+                double dW2 = 0.0;                                                // :227 (unused when xi == 0)
                 if (a.need_z2)
-                    dW2 = __dadd_rn(dW2, __dmul_rn(__dmul_rn(a.sq1mr2, t2[lane * GN_PITCH + t]), a.sqrt_dt));
+                    dW2 = __dadd_rn(__dmul_rn(__dmul_rn(a.rho, z1), a.sqrt_dt),
+                                    __dmul_rn(__dmul_rn(a.sq1mr2, t2[lane * GN_PITCH + t]), a.sqrt_dt));
                 const double log_drift = __dmul_rn(__dadd_rn(a.drift_comp, -__dmul_rn(0.5, v_pos)), a.dt);   // :229
                 const double log_diff = __dmul_rn(sqrt_v, dW1);                  // :230
                 double jump = 0.0;                                               // :232
@@ -94,9 +114,10 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
             }
             if (a.record) {                                                      // :241, coalesced by rows
                 __syncwarp();
-                const int col = lane & 15, half = lane >> 4;
-                for (int it = 0; it < 16; ++it) {
-                    const int row = 2 * it + half;
+                const int col = lane & 7, sub = lane >> 3;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = 4 * it + sub;
                     const int64_t p = path0 + row;
                     if (p < a.n_paths && col < ns)
                         all_paths[(size_t)p * (a.n_steps + 1) + 1 + s0 + col] = tout[row * GN_PITCH + col];
@@ -202,9 +223,10 @@ static int launch_given(b200mc_handle *h, const GivenArgs &a, const double *Z1, 
     if (a.n_paths == 0) return 0;
     const int64_t groups = (a.n_paths + 31) / 32;
     int64_t grid = (groups + GN_WARPS - 1) / GN_WARPS;
-    const int64_t cap = (int64_t)h->sm_count * 8;
+    const int64_t cap = (int64_t)h->sm_count * 16;
     if (grid > cap) grid = cap;
-    const size_t smem = (size_t)GN_WARPS * 5 * 32 * GN_PITCH * sizeof(double);
+    const int ntile = 1 + a.need_z2 + 2 * a.need_jump + a.record;
+    const size_t smem = (size_t)GN_WARPS * ntile * 32 * GN_PITCH * sizeof(double);
     B200MC_CUDA(h, cudaFuncSetAttribute((const void *)k_given_normals, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     k_given_normals<<<(unsigned)grid, GN_WARPS * 32, smem, h->stream>>>(a, Z1, Z2, Zj, Zjs, S_final, v_final,
