@@ -13,6 +13,8 @@
 // Arrays the parameters make irrelevant (Z2 when xi == 0, the jump arrays when lambda_j <= 0) are never read and get
 // no tile: shared memory per warp is 2.3 KB per array in use, which is what sets the number of resident warps -- the
 // per-step fp64 chain (sqrt, exp, separately rounded products) has a latency of several hundred cycles and needs them.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -22,8 +24,6 @@
 namespace b200mc {
 
 constexpr int GN_WARPS = 4;
-constexpr int GN_TS = 8;                  // steps per tile
-constexpr int GN_PITCH = GN_TS + 1;
 
 struct GivenArgs {
     double S0, v0, dt, sqrt_dt, drift_comp, kappa, theta, xi, rho, sq1mr2, jump_thr, mu_j, sigma_j;
@@ -35,35 +35,38 @@ struct GivenArgs {
 // lane (sub = lane >> 3, col = lane & 7) fetches element [path0 + 4 it + sub][s0 + col] for it = 0..7.  `rowptr` already
 // points at [path0 + sub][col] of the array, so the address of each load is one 64-bit add away (the full index
 // arithmetic per load costs more issue slots than the fp64 step itself).
-__device__ __forceinline__ void load_tile(double *tile, const double *__restrict__ rowptr, size_t stride4, int s0,
+template <int TS>
+__device__ __forceinline__ void load_tile(double *tile, const double *__restrict__ rowptr, size_t stride_r, int s0,
                                           bool full, int rows_left, int cols_left, int lane)
 {
-    const int col = lane & 7, sub = lane >> 3;
+    constexpr int RPI = 32 / TS, PITCH = TS + 1;            // rows per load instruction
+    const int col = lane % TS, sub = lane / TS;
     const double *p = rowptr + s0;
     if (full) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            tile[(4 * it + sub) * GN_PITCH + col] = __ldg(p);
-            p += stride4;
+        for (int it = 0; it < TS; ++it) {
+            tile[(RPI * it + sub) * PITCH + col] = __ldg(p);
+            p += stride_r;
         }
     } else {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = 4 * it + sub;
-            tile[row * GN_PITCH + col] = (row < rows_left && col < cols_left) ? __ldg(p) : 0.0;
-            p += stride4;
+        for (int it = 0; it < TS; ++it) {
+            const int row = RPI * it + sub;
+            tile[row * PITCH + col] = (row < rows_left && col < cols_left) ? __ldg(p) : 0.0;
+            p += stride_r;
         }
     }
 }
 
-__global__ void __launch_bounds__(GN_WARPS * 32, 6)
+template <int GN_TS>
+__global__ void __launch_bounds__(GN_WARPS * 32, GN_TS == 8 ? 6 : 3)
 k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ Z1, const double *__restrict__ Z2,
                 const double *__restrict__ Zj, const double *__restrict__ Zjs, double *__restrict__ S_final,
                 double *__restrict__ v_final, double *__restrict__ all_paths)
 {
     extern __shared__ __align__(16) double gn_tiles[];          // [GN_WARPS][tiles in use][32 * GN_PITCH]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int TILE = 32 * GN_PITCH;
+    constexpr int GN_PITCH = GN_TS + 1, TILE = 32 * GN_PITCH;
     const int ntile = 1 + a.need_z2 + 2 * a.need_jump + a.record;
     double *t1 = gn_tiles + (size_t)warp * ntile * TILE;
     double *t2 = t1 + TILE;                                   // valid only when need_z2
@@ -77,16 +80,17 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
             if (me < a.n_paths) all_paths[(size_t)me * (a.n_steps + 1)] = a.S0;  // :217
         }
         const int rows_left = (int)((a.n_paths - path0) < 32 ? (a.n_paths - path0) : 32);
-        const size_t lane_off = (size_t)(path0 + (lane >> 3)) * a.n_steps + (lane & 7), stride4 = (size_t)4 * a.n_steps;
+        const size_t lane_off = (size_t)(path0 + lane / GN_TS) * a.n_steps + (lane % GN_TS),
+                     stride4 = (size_t)(32 / GN_TS) * a.n_steps;
         for (int s0 = 0; s0 < a.n_steps; s0 += GN_TS) {
             const int cols_left = a.n_steps - s0;
             const bool full = rows_left == 32 && cols_left >= GN_TS;
             __syncwarp();
-            load_tile(t1, Z1 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
-            if (a.need_z2) load_tile(t2, Z2 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+            load_tile<GN_TS>(t1, Z1 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+            if (a.need_z2) load_tile<GN_TS>(t2, Z2 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
             if (a.need_jump) {
-                load_tile(tj, Zj + lane_off, stride4, s0, full, rows_left, cols_left, lane);
-                load_tile(tjs, Zjs + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+                load_tile<GN_TS>(tj, Zj + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+                load_tile<GN_TS>(tjs, Zjs + lane_off, stride4, s0, full, rows_left, cols_left, lane);
             }
             __syncwarp();
             const int ns = min(GN_TS, a.n_steps - s0);
@@ -114,10 +118,10 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
             }
             if (a.record) {                                                      // :241, coalesced by rows
                 __syncwarp();
-                const int col = lane & 7, sub = lane >> 3;
+                const int col = lane % GN_TS, sub = lane / GN_TS;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int row = 4 * it + sub;
+                for (int it = 0; it < GN_TS; ++it) {
+                    const int row = (32 / GN_TS) * it + sub;
                     const int64_t p = path0 + row;
                     if (p < a.n_paths && col < ns)
                         all_paths[(size_t)p * (a.n_steps + 1) + 1 + s0 + col] = tout[row * GN_PITCH + col];
@@ -226,11 +230,16 @@ static int launch_given(b200mc_handle *h, const GivenArgs &a, const double *Z1, 
     const int64_t cap = (int64_t)h->sm_count * 16;
     if (grid > cap) grid = cap;
     const int ntile = 1 + a.need_z2 + 2 * a.need_jump + a.record;
-    const size_t smem = (size_t)GN_WARPS * ntile * 32 * GN_PITCH * sizeof(double);
-    B200MC_CUDA(h, cudaFuncSetAttribute((const void *)k_given_normals, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    k_given_normals<<<(unsigned)grid, GN_WARPS * 32, smem, h->stream>>>(a, Z1, Z2, Zj, Zjs, S_final, v_final,
-                                                                         all_paths);
+    // 8-step tiles (64-byte row segments, 2.3 KB of shared memory per warp and array => more resident warps) unless the
+    // run is memory heavy (jump arrays in use: 32 B per path-step) AND the rows are not 64-byte multiples: then 128-byte
+    // segments waste fewer sectors (measured, 1M x 250 SVJ: 2.0 -> 2.5 TB/s; 4M x 64: 3.4 vs 2.9 TB/s the other way)
+    const char *force = getenv("B200MC_GN_TILE");
+    const bool wide = force ? atoi(force) == 16 : (a.need_jump != 0 && (a.n_steps % 8) != 0);
+    const int ts = wide ? 16 : 8;
+    const size_t smem = (size_t)GN_WARPS * ntile * 32 * (ts + 1) * sizeof(double);
+    auto kern = wide ? k_given_normals<16> : k_given_normals<8>;
+    B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, GN_WARPS * 32, smem, h->stream>>>(a, Z1, Z2, Zj, Zjs, S_final, v_final, all_paths);
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
     return 0;
