@@ -58,35 +58,57 @@ k_terminal(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_g
     }
 }
 
-// ---------------------------------------------------------------------------------------------- path store
-template <int MODE, typename R, typename O> struct TileRec {
+// ---------------------------------------------------------------------------------------------- path store, Heston / SVJ
+// Stochastic variance makes a path sequential in time, so one lane owns one path for all its steps (the time-parallel
+// TMA tile of the deterministic-variance kernel is not available).  Rows of the reference layout start on arbitrary
+// element boundaries; storing fixed column tiles row by row leaves every 128-byte store straddling two lines (measured
+// 0.95 TB/s).  Here every row keeps a ring of two 64-byte windows in shared memory, positioned by the row's OWN
+// misalignment m_r = (address of the row start / sizeof(O)) mod A (A = elements per 64 bytes): window w of row r holds
+// the columns whose global addresses fall into the w-th 64-byte piece of that row.  After every A produced columns all
+// 32 rows have completed the same window index, and the warp writes them out: every store instruction covers full,
+// ALIGNED 32-byte sectors only (2 rows per instruction for fp32 output, 4 for fp64).
+template <int MODE, typename R, typename O> struct AlignedRec {
     static constexpr bool enabled = true;
-    O *tile;             // this warp's [32][33] tile
-    O *out;              // global matrix
-    const R *dtab;       // DETVAR: cumulative drift
-    int64_t path0, n_paths, ld;
-    int n_steps, lane;
+    static constexpr int A = 64 / (int)sizeof(O);       // window = 64 bytes = two full sectors (keeps the rings small)
+    O *ring;             // this warp's [32][pitch] rings (2 A elements each + padding)
+    int pitch, ncol, lane, m;    // m = misalignment of MY row, in elements
     R S0;
 
-    __device__ __noinline__ void flush(int s) const
+    __device__ __forceinline__ O &slot(int c) const { return ring[lane * pitch + ((m + c) & (2 * A - 1))]; }
+
+    // write window `w` (columns [w A - m_r, (w + 1) A - m_r) of row r) of all 32 rows.  `base` is the 64-byte aligned
+    // address this lane's OWN row is measured from (row start minus m elements); rows beyond n_rows carry base = nullptr.
+    O *base;
+    __device__ __noinline__ void flush(int w) const
     {
-        const int c0 = s & ~31, nc = (s & 31) + 1;
         __syncwarp();
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            const int64_t p = path0 + r;
-            if (p < n_paths && lane < nc) out[(size_t)p * ld + 1 + c0 + lane] = tile[r * 33 + lane];
+        constexpr int RPI = 32 / A;                     // rows per store instruction (2 for fp32, 4 for fp64)
+        const int j = lane % A, sub = lane / A;
+        const unsigned long long mine = (unsigned long long)(uintptr_t)base;
+        const int off = w * A + j;
+#pragma unroll 4
+        for (int it = 0; it < 32 / RPI; ++it) {
+            const int r = it * RPI + sub;
+            const int mr = __shfl_sync(0xffffffffu, m, r);
+            O *rb = reinterpret_cast<O *>((uintptr_t)__shfl_sync(0xffffffffu, mine, r));
+            const int c = off - mr;
+            if (rb != nullptr && c >= 0 && c < ncol) rb[off] = ring[r * pitch + ((w & 1) * A + j)];
         }
         __syncwarp();
     }
     __device__ __forceinline__ void operator()(int s, R x) const
     {
-        if constexpr (MODE == MODE_DETVAR) x += dtab[s];
         R S;
         if constexpr (sizeof(R) == 4) S = S0 * exp2f(x * LOG2E_F);
         else S = S0 * exp(x);
-        tile[lane * 33 + (s & 31)] = (O)S;
-        if ((s & 31) == 31 || s == n_steps - 1) flush(s);
+        const int c = s + 1;
+        slot(c) = (O)S;
+        if (((c + 1) & (A - 1)) == 0) flush((c + 1) / A - 1);       // (uniform across the warp: every lane is at column c)
+        if (c == ncol - 1) {        // last column: rows still hold a partial window k = floor(ncol / A), and those with a
+            const int w = ncol / A; // large misalignment also the start of window k + 1 (never k - 1: it shares a ring
+            flush(w);               // half with k + 1 and has been written out already)
+            flush(w + 1);
+        }
     }
 };
 
@@ -96,34 +118,29 @@ k_paths(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_g, c
         O *__restrict__ out)
 {
     using L = StateLayout<false, false>;
+    using Rec = AlignedRec<MODE, R, O>;
+    static_assert(MODE == MODE_HESTON || MODE == MODE_SVJ, "deterministic variance has its own kernels");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    O *tiles = reinterpret_cast<O *>(smem_raw);                                 // [8][32*33]
-    R *wtab = reinterpret_cast<R *>(tiles + (PT_THREADS / 32) * 32 * 33);       // [3][wld]
-    R *dtab = wtab + 3 * a.wld;                                                 // [wld]
-    if constexpr (MODE == MODE_DETVAR) {
-        for (int i = threadIdx.x; i < 3 * a.wld; i += PT_THREADS) wtab[i] = (R)wtab_g[i];
-        for (int i = threadIdx.x; i < a.wld; i += PT_THREADS) dtab[i] = (R)dtab_g[i];
-        __syncthreads();
-    }
+    const int pitch = 2 * Rec::A + (((a.ld & 1) != 0) ? 0 : 1);                 // (pitch + ld) odd: conflict-free fills
+    O *rings = reinterpret_cast<O *>(smem_raw);                                 // [8][32 * pitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_groups = (a.n_paths + 31) / 32;
     for (int64_t g = (int64_t)blockIdx.x * (PT_THREADS / 32) + warp; g < n_groups;
          g += (int64_t)gridDim.x * (PT_THREADS / 32)) {
-        TileRec<MODE, R, O> rec;
-        rec.tile = tiles + warp * 32 * 33;
-        rec.out = out;
-        rec.dtab = dtab;
-        rec.path0 = g * 32;
-        rec.n_paths = a.n_paths;
-        rec.ld = a.ld;
-        rec.n_steps = a.n_steps;
+        Rec rec;
+        rec.ring = rings + (size_t)warp * 32 * pitch;
+        rec.pitch = pitch;
+        rec.ncol = a.n_steps + 1;
         rec.lane = lane;
         rec.S0 = (R)a.m.S0;
-        int64_t me = rec.path0 + lane;
-        if (me < a.n_paths) out[(size_t)me * a.ld] = (O)a.m.S0;                 // column 0 = S0   (:217)
-        else me = a.n_paths - 1;   // idle lanes shadow the last path so the warp stays convergent in flush()
+        int64_t me = g * 32 + lane;
+        rec.m = (int)((((uintptr_t)out / sizeof(O)) + (uint64_t)me * (uint64_t)a.ld) % (uint64_t)Rec::A);
+        rec.base = me < a.n_paths ? out + (size_t)me * a.ld - rec.m : nullptr;
+        if (me >= a.n_paths) me = a.n_paths - 1;   // idle lanes shadow the last path so the warp stays convergent
+        __syncwarp();
+        rec.slot(0) = (O)a.m.S0;                                                // column 0 = S0   (:217)
         R xT[L::NS], vT[L::NS], sumz;
-        simulate_path<MODE, false, false, R>(a.m, a.key, a.path0 + (uint64_t)me, a.n_steps, wtab, a.wld, xT, vT, sumz,
+        simulate_path<MODE, false, false, R>(a.m, a.key, a.path0 + (uint64_t)me, a.n_steps, nullptr, a.wld, xT, vT, sumz,
                                              rec);
     }
 }
@@ -502,9 +519,7 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
         B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, (size_t)n_paths * ld * esz + 256));
         dO = h->d_stage;
     }
-    size_t smem = (size_t)(PT_THREADS / 32) * 32 * 33 * esz;
-    if (pr.mode == MODE_DETVAR) smem += (size_t)4 * pr.wld * (fp64 ? 8 : 4);
-    if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
+    size_t smem = (size_t)(PT_THREADS / 32) * 32 * (2 * (64 / esz) + 1) * esz;      // Heston / SVJ: ring of two windows per row
     int64_t grid = ((n_paths + 31) / 32 + PT_THREADS / 32 - 1) / (PT_THREADS / 32);
     const int64_t cap = (int64_t)h->sm_count * 8;
     if (grid > cap) grid = cap;
@@ -558,8 +573,13 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
 #undef TMA_CALL
         } else if (tab) DET_CALL(true); else DET_CALL(false);
 #undef DET_CALL
+        if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
+    } else if (pr.mode == MODE_HESTON) {
+        constexpr int M = MODE_HESTON;
+        PATH_CALL;
     } else {
-        DISPATCH_MODE(pr.mode, PATH_CALL);
+        constexpr int M = MODE_SVJ;
+        PATH_CALL;
     }
 #undef PATH_CALL
     B200MC_CUDA(h, cudaGetLastError());
