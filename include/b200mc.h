@@ -176,7 +176,11 @@ int b200mc_simulate_terminal(b200mc_handle *h, const b200mc_svj_params *p, doubl
 /* ---- a5 / path-storing mode ------------------------------------------------------------------------------
  * MonteCarloEngine.get_sample_paths (engine/monte_carlo.py:452-471) at scale: the full path matrix
  * [n_paths, n_steps + 1], row-major with leading dimension ld >= n_steps + 1 (elements), column 0 = S0
- * (:216-217,241).  Tiles are staged through shared memory and written with coalesced 128-bit stores. */
+ * (:216-217,241).  dtype selects the element type of `out` (B200MC_F32 / B200MC_F64), B200MC_FP64 the precision of
+ * the path state.  All variants stage tiles in shared memory.  Deterministic variance (GBM) with ld == n_steps + 1: a
+ * CTA owns 32 paths, its warps split the time axis, and the finished 32 x (n_steps + 1) tile -- which has exactly
+ * the global layout -- leaves with ONE TMA bulk store; padded rows: 128-bit row stores; Heston / SVJ: per-row rings
+ * of aligned 64-byte windows.  Only B200MC_FP64 and B200MC_FORCE_SVJ are accepted in flags. */
 int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
                           int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
                           uint32_t flags, int dtype, int on_device, void *out, int64_t ld);
