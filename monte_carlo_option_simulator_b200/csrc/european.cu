@@ -61,10 +61,12 @@ __device__ __forceinline__ void accumulate(A (&acc)[NACC], const EuroArgs &a, R 
         pay = (A)0.5 * (da + db);
     }
     acc[0] += da;
-    acc[1] += db;
     acc[2] += da * da;
-    acc[3] += db * db;
-    acc[4] += da * db;
+    if constexpr (ANTI) {          // without the twin these three stay exactly 0 (x + 0.0 is not folded by the compiler)
+        acc[1] += db;
+        acc[3] += db * db;
+        acc[4] += da * db;
+    }
     acc[5] += s_avg;
     acc[6] += s_avg * s_avg;
     acc[7] += pay * s_avg;
