@@ -474,6 +474,23 @@ def test_production_svj_within_3se_of_reference(golden, case):
     assert abs(r["price"] - c["result"]["price"]) <= 3 * math.hypot(r["std_error"], c["result"]["std_error"])
 
 
+@pytest.mark.parametrize("pname", ["svj_default", "heston", "jumpy"])
+def test_production_sv_modes_against_a_large_oracle_sample(golden, pname):
+    """Production mode for the stochastic-variance / jump kernels: 4e6 Philox paths on the GPU against 2e5 PCG64 paths
+    of the oracle (the reference's own estimator, antithetic, no CV) -- a 7x tighter band than the 4096-path goldens."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    p = SVJParams(**golden["params"][pname])
+    spot, T = 22500.0, 0.25
+    ours = MonteCarloEngine(p, 4_000_000, 252, seed=5, use_sobol=False, use_antithetic=True, use_control_variate=False,
+                            rng="philox")
+    ref = O.MonteCarloOracle(O.Params(**golden["params"][pname]), 200_000, 252, 42, False, True, False)
+    for K, is_call in ((21500.0, False), (22500.0, True), (23500.0, True)):
+        a = ours.price(spot, K, T, is_call)
+        b = ref.price(spot, K, T, is_call)
+        assert abs(a["price"] - b["price"]) <= 3.5 * math.hypot(a["std_error"], b["std_error"]), (pname, K, a, b)
+        assert a["std_error"] == pytest.approx(b["std_error"] * math.sqrt(200_000 / 4_000_000), rel=0.05)
+
+
 def test_pseudo_cv_formula_reproduced(golden):
     """Quirk 2: with antithetic off the reference's 'control variate' returns exactly bs_ref with SE 0; with it
     on, price = bs_ref + D*mean((b - a)/2).  Same dictionary keys as the reference."""
