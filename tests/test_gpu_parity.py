@@ -220,6 +220,42 @@ def test_fused_random_configurations(H, L, case):
     assert np.median(np.abs(S32 / So - 1)) < 2e-6
 
 
+@pytest.mark.parametrize("name", ["gbm", "detvar", "heston", "svj", "jumpy"])
+def test_fused_modes_against_the_reference_itself(H, L, name):
+    """The north star's deterministic mode, literally: the REFERENCE kernel (run in the dev container, fixtures in
+    tests/golden/fused_golden.npz) was fed the draws this library dumps; the fused kernels must (a) still produce those
+    draws bit for bit and (b) reproduce the reference's outputs: <= 1e-6 relative with the fp64 state (observed ~1e-14),
+    <= 1e-4 with the fp32 state."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from monte_carlo_option_simulator_b200 import SVJParams
+    c = json.load(open(os.path.join(GOLDEN, "fused_golden_cases.json")))[name]
+    d = dict(np.load(os.path.join(GOLDEN, "fused_golden.npz")))
+    p = SVJParams(**c["params"])
+    n, steps, T, S0, seed, off = c["n"], c["steps"], c["T"], c["S0"], c["seed"], c["path_offset"]
+    stream = L.select_stream(p, T, steps)
+    assert stream == int(d[f"{name}_stream"][0])
+    for i, w in enumerate(("Z1", "Z2", "Zj", "Zjs")):
+        got = H.dump_normals(seed, n, steps, stream, i, path_offset=off, jump_prob=p.lambda_j * (T / steps))
+        np.testing.assert_array_equal(got, d[f"{name}_{w}"])
+    S, A, V = H.simulate_terminal(p, S0, T, steps, n, seed, L.FP64 | L.ANTITHETIC, np.float64, off, True, True)
+    np.testing.assert_allclose(S, d[f"{name}_ref_S"], rtol=1e-6)
+    np.testing.assert_allclose(S, d[f"{name}_ref_S"], rtol=1e-10)            # what we actually achieve
+    np.testing.assert_allclose(A, d[f"{name}_ref_S_anti"], rtol=1e-10)
+    np.testing.assert_allclose(V, d[f"{name}_ref_v"], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(H.generate_paths(p, S0, T, steps, n, seed, L.FP64, np.float64, off), d[f"{name}_ref_paths"],
+                               rtol=1e-10)
+    S32, A32, _ = H.simulate_terminal(p, S0, T, steps, n, seed, L.ANTITHETIC, np.float32, off, True, False)
+    np.testing.assert_allclose(S32, d[f"{name}_ref_S"], rtol=1e-4)
+    np.testing.assert_allclose(A32, d[f"{name}_ref_S_anti"], rtol=1e-4)
+    np.testing.assert_allclose(H.generate_paths(p, S0, T, steps, n, seed, 0, np.float32, off), d[f"{name}_ref_paths"], rtol=1e-4)
+    bumps = L.Bumps(0.01, p.v0 + 0.01, max(p.v0 - 0.01, 0.001), p.r + 1e-4, max(p.r - 1e-4, 0))
+    row = H.price_european(p, S0, T, steps, n, seed, [S0], True, L.FP64 | L.GREEKS, bumps, path_offset=off)[0]
+    assert row[L.SUMS_FIELDS.index("sum_v0_up")] == pytest.approx(np.maximum(d[f"{name}_ref_S_v0up"] - S0, 0).sum(), rel=1e-9)
+    assert row[L.SUMS_FIELDS.index("sum_a")] == pytest.approx(np.maximum(d[f"{name}_ref_S"] - S0, 0).sum(), rel=1e-9)
+
+
 def test_fused_jumps_fire_like_reference(H, L, golden):
     """A jump-heavy parameter set: the integer jump test in the kernel must equal the reference's float compare."""
     p = P(golden, "jumpy")

@@ -197,3 +197,25 @@ def test_philox_block_words_layout():
             ctr[i, b] = (p & 0xFFFFFFFF, p >> 32, b, 1)
     key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32), (5, 3, 2))
     np.testing.assert_array_equal(w, O.philox4x32_10(ctr, key))
+
+
+def test_oracle_equals_reference_on_the_device_draws():
+    """tests/golden/fused_golden.npz: draws dumped from the GPU library, outputs computed by the REFERENCE kernel on them
+    (make_fused_golden.py).  Pins the oracle to the reference on exactly the inputs the fused-mode parity tests use."""
+    import json
+    import os
+    from conftest import GOLDEN
+    cases = json.load(open(os.path.join(GOLDEN, "fused_golden_cases.json")))
+    d = dict(np.load(os.path.join(GOLDEN, "fused_golden.npz")))
+    assert set(cases) == {"gbm", "detvar", "heston", "svj", "jumpy"}
+    for name, c in cases.items():
+        p = O.Params(**c["params"])
+        Z = [d[f"{name}_{w}"] for w in ("Z1", "Z2", "Zj", "Zjs")]
+        S, v, paths = O._sim(p, c["S0"], c["T"], *Z, c["steps"], record=True)
+        np.testing.assert_allclose(S, d[f"{name}_ref_S"], rtol=RTOL)
+        np.testing.assert_allclose(v, d[f"{name}_ref_v"], rtol=RTOL, atol=1e-18)
+        np.testing.assert_allclose(paths, d[f"{name}_ref_paths"], rtol=RTOL)
+        np.testing.assert_allclose(O._sim(p, c["S0"], c["T"], -Z[0], -Z[1], Z[2], -Z[3], c["steps"])[0],
+                                   d[f"{name}_ref_S_anti"], rtol=RTOL)
+        if name == "jumpy":
+            assert (Z[2] < p.lambda_j * (c["T"] / c["steps"])).sum() > 500          # the jumps really fire
