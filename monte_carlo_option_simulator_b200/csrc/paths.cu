@@ -10,6 +10,9 @@
 //                             and a 32x32 tile in shared memory; each lane fills its own row as the steps come out
 //                             of the recurrence, then the warp writes the tile out row by row so that every store
 //                             instruction covers 128 (fp32) or 256 (fp64) contiguous bytes.
+#include <algorithm>
+#include <type_traits>
+
 #include "prep.cuh"
 
 namespace b200mc {
@@ -366,49 +369,32 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <bool TAB, typename R, typename O>
-static void path_det_launch(const PathArgs &a, const double *wtab, const double *dtab, void *out, bool vec, unsigned grid,
-                            size_t smem, cudaStream_t st)
+// ---------------------------------------------------------------------------------------------- host side
+// Compile-time dispatch without macros: with_types / with_mode / with_bool call a generic lambda with tag values
+// whose TYPES carry the template arguments (float{} / double{}, std::integral_constant, std::bool_constant).
+template <typename F> static void with_types(bool fp64_state, int dtype, F &&f)
 {
-    if constexpr (sizeof(O) == 4) {
-        if (vec) {
-            auto k = k_paths_det<TAB, R, O, true>;
-            cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k<<<grid, PT_THREADS, smem, st>>>(a, wtab, dtab, (O *)out);
-            return;
-        }
+    if (fp64_state) { if (dtype == B200MC_F64) f(double{}, double{}); else f(double{}, float{}); }
+    else { if (dtype == B200MC_F64) f(float{}, double{}); else f(float{}, float{}); }
+}
+template <typename F> static void with_mode(int mode, F &&f)
+{
+    switch (mode) {
+    case MODE_GBM: f(std::integral_constant<int, MODE_GBM>{}); break;
+    case MODE_DETVAR: f(std::integral_constant<int, MODE_DETVAR>{}); break;
+    case MODE_HESTON: f(std::integral_constant<int, MODE_HESTON>{}); break;
+    default: f(std::integral_constant<int, MODE_SVJ>{}); break;
     }
-    auto k = k_paths_det<TAB, R, O, false>;
-    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, PT_THREADS, smem, st>>>(a, wtab, dtab, (O *)out);
 }
-
-using TermKernel = void (*)(const PathArgs, const double *, void *, void *, void *);
-
-template <int MODE, bool ANTI, typename R, typename O>
-static void term_launch(const PathArgs &a, const double *wtab, void *s, void *sa, void *v, unsigned grid, size_t smem,
-                        cudaStream_t st)
+template <typename F> static void with_bool(bool b, F &&f)
 {
-    auto k = k_terminal<MODE, ANTI, R, O>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, PT_THREADS, smem, st>>>(a, wtab, (O *)s, (O *)sa, (O *)v);
-}
-template <int MODE, typename R, typename O>
-static void path_launch(const PathArgs &a, const double *wtab, const double *dtab, void *out, unsigned grid, size_t smem,
-                        cudaStream_t st)
-{
-    auto k = k_paths<MODE, R, O>;
-    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, PT_THREADS, smem, st>>>(a, wtab, dtab, (O *)out);
+    if (b) f(std::true_type{}); else f(std::false_type{});
 }
 
-#define DISPATCH_MODE(mode, CALL)                       \
-    switch (mode) {                                     \
-    case MODE_GBM: { constexpr int M = MODE_GBM; CALL; } break;       \
-    case MODE_DETVAR: { constexpr int M = MODE_DETVAR; CALL; } break; \
-    case MODE_HESTON: { constexpr int M = MODE_HESTON; CALL; } break; \
-    default: { constexpr int M = MODE_SVJ; CALL; } break;             \
-    }
+template <typename K> static void allow_smem(K kernel, size_t smem)
+{
+    if (smem > 48 * 1024) cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
 
 static int upload_tables(b200mc_handle *h, const Prep &pr, const double **wtab_d, const double **dtab_d)
 {
@@ -468,21 +454,21 @@ extern "C" int b200mc_simulate_terminal(b200mc_handle *h, const b200mc_svj_param
         if (v_T) { dV = b; }
     }
     const size_t smem = pr.mode == MODE_DETVAR ? (size_t)3 * pr.wld * (fp64 ? 8 : 4) : 0;
+    if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
     int64_t grid = (n_paths + PT_THREADS - 1) / PT_THREADS;
     const int64_t cap = (int64_t)h->sm_count * 8;
     if (grid > cap) grid = cap;
-#define TERM_CALL                                                                                            \
-    do {                                                                                                     \
-        if (fp64) {                                                                                          \
-            if (dtype == B200MC_F64) { if (anti) term_launch<M, true, double, double>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); else term_launch<M, false, double, double>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); } \
-            else { if (anti) term_launch<M, true, double, float>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); else term_launch<M, false, double, float>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); } \
-        } else {                                                                                             \
-            if (dtype == B200MC_F64) { if (anti) term_launch<M, true, float, double>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); else term_launch<M, false, float, double>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); } \
-            else { if (anti) term_launch<M, true, float, float>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); else term_launch<M, false, float, float>(a, wtab_d, dS, dA, dV, (unsigned)grid, smem, h->stream); } \
-        }                                                                                                    \
-    } while (0)
-    DISPATCH_MODE(pr.mode, TERM_CALL);
-#undef TERM_CALL
+    with_mode(pr.mode, [&](auto mode) {
+        with_bool(anti, [&](auto twin) {
+            with_types(fp64, dtype, [&](auto r, auto o) {
+                using R = decltype(r);
+                using O = decltype(o);
+                auto k = k_terminal<decltype(mode)::value, decltype(twin)::value, R, O>;
+                allow_smem(k, smem);
+                k<<<(unsigned)grid, PT_THREADS, smem, h->stream>>>(a, wtab_d, (O *)dS, (O *)dA, (O *)dV);
+            });
+        });
+    });
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
     if (!on_device) {
@@ -508,7 +494,7 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
     B200MC_TRY(prepare(h, p, S0, T, n_steps, n_paths, seed, flags, nullptr, pr));
     B200MC_CUDA(h, cudaSetDevice(h->device));
     const bool fp64 = flags & B200MC_FP64;
-    const size_t esz = dtype == B200MC_F64 ? 8 : 4;
+    const size_t esz = dtype == B200MC_F64 ? 8 : 4, rsz = fp64 ? 8 : 4;
     const double *wtab_d, *dtab_d;
     B200MC_TRY(upload_tables(h, pr, &wtab_d, &dtab_d));
     PathArgs a;
@@ -519,69 +505,64 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
         B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, (size_t)n_paths * ld * esz + 256));
         dO = h->d_stage;
     }
-    size_t smem = (size_t)(PT_THREADS / 32) * 32 * (2 * (64 / esz) + 1) * esz;      // Heston / SVJ: ring of two windows per row
-    int64_t grid = ((n_paths + 31) / 32 + PT_THREADS / 32 - 1) / (PT_THREADS / 32);
-    const int64_t cap = (int64_t)h->sm_count * 8;
-    if (grid > cap) grid = cap;
-#define PATH_CALL                                                                                              \
-    do {                                                                                                       \
-        if (fp64) { if (dtype == B200MC_F64) path_launch<M, double, double>(a, wtab_d, dtab_d, dO, (unsigned)grid, smem, h->stream); \
-                    else path_launch<M, double, float>(a, wtab_d, dtab_d, dO, (unsigned)grid, smem, h->stream); }  \
-        else { if (dtype == B200MC_F64) path_launch<M, float, double>(a, wtab_d, dtab_d, dO, (unsigned)grid, smem, h->stream); \
-               else path_launch<M, float, float>(a, wtab_d, dtab_d, dO, (unsigned)grid, smem, h->stream); }         \
-    } while (0)
-    if (pr.mode == MODE_GBM || pr.mode == MODE_DETVAR) {
-        const bool tab = pr.mode == MODE_DETVAR;
-        const bool vec = dtype == B200MC_F32 && (ld % 4 == 0) && (((uintptr_t)dO) % 16 == 0);
-        smem = (size_t)(PT_THREADS / 32) * 32 * 33 * esz + (tab ? (size_t)2 * (pr.wld + 32) * (fp64 ? 8 : 4) : 0);
-#define DET_CALL(TAB)                                                                                              \
-        do {                                                                                                       \
-            if (fp64) { if (dtype == B200MC_F64) path_det_launch<TAB, double, double>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); \
-                        else path_det_launch<TAB, double, float>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); }  \
-            else { if (dtype == B200MC_F64) path_det_launch<TAB, float, double>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); \
-                   else path_det_launch<TAB, float, float>(a, wtab_d, dtab_d, dO, vec, (unsigned)grid, smem, h->stream); }         \
-        } while (0)
-        const size_t tma_smem = (((size_t)32 * (n_steps + 1) * esz + 127) & ~(size_t)127) + (size_t)((n_steps + 31) / 32) * 32 * (fp64 ? 8 : 4) +
-                                (tab ? (size_t)2 * (pr.wld + 32) * (fp64 ? 8 : 4) : 0);
+    constexpr int NW = PT_THREADS / 32;
+    const int64_t groups = (n_paths + 31) / 32;                       // 32 paths per warp (or per CTA in the TMA kernel)
+    const bool det = pr.mode == MODE_GBM || pr.mode == MODE_DETVAR;
+    const bool tab = pr.mode == MODE_DETVAR;
+    const size_t tab_bytes = tab ? (size_t)2 * (pr.wld + 32) * rsz : 0;
+
+    if (det) {
+        const int nch = (n_steps + 31) / 32;                          // TMA kernel: warps per CTA = chunks of 32 steps
+        const size_t tma_smem = (((size_t)32 * (n_steps + 1) * esz + 127) & ~(size_t)127) + (size_t)nch * 32 * rsz + tab_bytes;
+        const size_t row_smem = (size_t)NW * 32 * 33 * esz + tab_bytes;
         if (ld == (int64_t)n_steps + 1 && n_steps <= 1024 && tma_smem <= 200 * 1024) {
-            const int NCH = (n_steps + 31) / 32;                      // warps per CTA = chunks of 32 steps
-            const size_t rs = fp64 ? 8 : 4;
-            smem = (((size_t)32 * (n_steps + 1) * esz + 127) & ~(size_t)127) + (size_t)NCH * 32 * rs +
-                   (tab ? (size_t)2 * (pr.wld + 32) * rs : 0);
-            int64_t fgrid = (n_paths + 31) / 32;
-            const int64_t fcap = (int64_t)h->sm_count * 16;
-            if (fgrid > fcap) fgrid = fcap;
-#define TMA_CALL(TAB, RR, OO)                                                                                      \
-            do {                                                                                                   \
-                if (NCH <= 8) {                                                                                    \
-                    auto k = k_paths_tma<TAB, RR, OO, 256>;                                                        \
-                    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                    k<<<(unsigned)fgrid, 32 * NCH, smem, h->stream>>>(a, wtab_d, dtab_d, (OO *)dO);                \
-                } else {                                                                                           \
-                    auto k = k_paths_tma<TAB, RR, OO, 1024>;                                                       \
-                    cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                    k<<<(unsigned)fgrid, 32 * NCH, smem, h->stream>>>(a, wtab_d, dtab_d, (OO *)dO);                \
-                }                                                                                                  \
-            } while (0)
-            if (tab) {
-                if (fp64) { if (dtype == B200MC_F64) TMA_CALL(true, double, double); else TMA_CALL(true, double, float); }
-                else { if (dtype == B200MC_F64) TMA_CALL(true, float, double); else TMA_CALL(true, float, float); }
-            } else {
-                if (fp64) { if (dtype == B200MC_F64) TMA_CALL(false, double, double); else TMA_CALL(false, double, float); }
-                else { if (dtype == B200MC_F64) TMA_CALL(false, float, double); else TMA_CALL(false, float, float); }
-            }
-#undef TMA_CALL
-        } else if (tab) DET_CALL(true); else DET_CALL(false);
-#undef DET_CALL
-        if (smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
-    } else if (pr.mode == MODE_HESTON) {
-        constexpr int M = MODE_HESTON;
-        PATH_CALL;
+            // reference layout: CTA tile = 32 whole paths, one TMA bulk store per tile
+            const int64_t grid = std::min<int64_t>(groups, (int64_t)h->sm_count * 16);
+            with_bool(tab, [&](auto t) {
+                with_bool(nch > 8, [&](auto big) {
+                    with_types(fp64, dtype, [&](auto r, auto o) {
+                        using O = decltype(o);
+                        auto k = k_paths_tma<decltype(t)::value, decltype(r), O, decltype(big)::value ? 1024 : 256>;
+                        allow_smem(k, tma_smem);
+                        k<<<(unsigned)grid, 32 * nch, tma_smem, h->stream>>>(a, wtab_d, dtab_d, (O *)dO);
+                    });
+                });
+            });
+        } else {
+            // padded rows (or very long paths): row-tiled kernel, 128-bit stores when the rows allow them
+            if (row_smem > 200 * 1024) return fail(h, B200MC_EINVAL, "too many steps for the deterministic-variance tables");
+            const bool vec = dtype == B200MC_F32 && (ld % 4 == 0) && (((uintptr_t)dO) % 16 == 0);
+            const int64_t grid = std::min<int64_t>((groups + NW - 1) / NW, (int64_t)h->sm_count * 8);
+            with_bool(tab, [&](auto t) {
+                with_types(fp64, dtype, [&](auto r, auto o) {
+                    using O = decltype(o);
+                    if constexpr (sizeof(O) == 4) {
+                        if (vec) {
+                            auto k = k_paths_det<decltype(t)::value, decltype(r), O, true>;
+                            allow_smem(k, row_smem);
+                            k<<<(unsigned)grid, PT_THREADS, row_smem, h->stream>>>(a, wtab_d, dtab_d, (O *)dO);
+                            return;
+                        }
+                    }
+                    auto k = k_paths_det<decltype(t)::value, decltype(r), O, false>;
+                    allow_smem(k, row_smem);
+                    k<<<(unsigned)grid, PT_THREADS, row_smem, h->stream>>>(a, wtab_d, dtab_d, (O *)dO);
+                });
+            });
+        }
     } else {
-        constexpr int M = MODE_SVJ;
-        PATH_CALL;
+        // Heston / SVJ: one lane per path, per-row rings of two aligned 64-byte windows
+        const size_t smem = (size_t)NW * 32 * (2 * (64 / esz) + 1) * esz;
+        const int64_t grid = std::min<int64_t>((groups + NW - 1) / NW, (int64_t)h->sm_count * 8);
+        with_bool(pr.mode == MODE_SVJ, [&](auto jumps) {
+            with_types(fp64, dtype, [&](auto r, auto o) {
+                using O = decltype(o);
+                auto k = k_paths<decltype(jumps)::value ? MODE_SVJ : MODE_HESTON, decltype(r), O>;
+                allow_smem(k, smem);
+                k<<<(unsigned)grid, PT_THREADS, smem, h->stream>>>(a, wtab_d, dtab_d, (O *)dO);
+            });
+        });
     }
-#undef PATH_CALL
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
     if (!on_device) {
