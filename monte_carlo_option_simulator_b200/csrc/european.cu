@@ -165,32 +165,85 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g
         }
     }
 
-    // ---- fold slices -> one partial per (block, strike) ---------------------------------------------------
+    // ---- fold the CTA's threads -> one partial per (CTA, strike) ---------------------------------------------
+    // (a tree, not one thread walking 256 slots: that walk was 35 us of serial shared-memory latency per CTA -- the
+    // whole duration of a small launch and 2.4 % of a 10M-path one)
     __shared__ bool is_last;
+    if constexpr (SINGLE) {
+        const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int j = 0; j < NACC; ++j) {
-        red[tid] = acc[j];
-        __syncthreads();
-        if (tid < ks) {
-            double s = 0.0;
-            for (int sl = 0; sl < nslices; ++sl) s += red[sl * ks + tid];
-            partials[((size_t)blockIdx.x * ks + tid) * NACC + j] = s;
+        for (int j = 0; j < NACC; ++j) {
+            double v = acc[j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp * NACC + j] = v;
         }
         __syncthreads();
+        if (tid < NACC) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < EU_THREADS / 32; ++w) t += red[w * NACC + tid];
+            partials[(size_t)blockIdx.x * NACC + tid] = t;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            red[tid] = worker ? acc[j] : 0.0;
+            __syncthreads();
+            for (int st = 128; st >= 1; st >>= 1) {            // halving over the slices of a strike
+                if (worker && my_slice < st && my_slice + st < nslices) red[tid] += red[tid + st * ks];
+                __syncthreads();
+            }
+            if (tid < ks) partials[((size_t)blockIdx.x * ks + tid) * NACC + j] = red[tid];
+            __syncthreads();
+        }
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (is_last) {
+        // The last CTA adds the per-CTA partials.  A single thread per item walking all CTAs is a chain of gridDim.x
+        // dependent L2 round trips (measured: ~40 us of fixed latency per launch, visible in every small call and ~3 % of
+        // a 10M-path launch).  Here LANES threads share an item, each adds a strided subset of the CTAs with the loads
+        // of a subset issued back to back, and the subsets are folded in a fixed order: still bitwise reproducible
+        // for a given launch geometry.
         __threadfence();
         const int items = ks * NACC;
-        for (int it = tid; it < items; it += EU_THREADS) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * items + it];
-            const int k = it / NACC, j = it % NACC;
-            out[(size_t)k * (NACC + 1) + 1 + j] = s;
-            if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
+        if (items > 128) {              // many strikes: one thread per item already keeps 256+ independent chains in flight
+            for (int it = tid; it < items; it += EU_THREADS) {
+                double s = 0.0;
+                for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * items + it];
+                const int k = it / NACC, j = it % NACC;
+                out[(size_t)k * (NACC + 1) + 1 + j] = s;
+                if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
+            }
+        } else {
+            const int LANES = items <= 16 ? 16 : (items <= 32 ? 8 : (items <= 64 ? 4 : 2));
+            for (int it0 = 0; it0 < items; it0 += EU_THREADS / LANES) {      // a single pass (items <= 256 / LANES)
+                const int it = it0 + tid / LANES, sub = tid % LANES;
+                double s = 0.0;
+                if (it < items) {
+                    unsigned int b = sub;
+                    for (; b + 3 * LANES < gridDim.x; b += 4 * LANES) {
+                        const double p0 = partials[(size_t)b * items + it], p1 = partials[(size_t)(b + LANES) * items + it],
+                                     p2 = partials[(size_t)(b + 2 * LANES) * items + it],
+                                     p3 = partials[(size_t)(b + 3 * LANES) * items + it];
+                        s += p0; s += p1; s += p2; s += p3;
+                    }
+                    for (; b < gridDim.x; b += LANES) s += partials[(size_t)b * items + it];
+                }
+                __syncthreads();
+                red[tid] = s;
+                __syncthreads();
+                if (it < items && sub == 0) {
+                    double tot = 0.0;
+                    for (int q = 0; q < LANES; ++q) tot += red[tid + q];
+                    const int k = it / NACC, j = it % NACC;
+                    out[(size_t)k * (NACC + 1) + 1 + j] = tot;
+                    if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
+                }
+            }
         }
         if (tid == 0) *counter = 0u;   // re-arm for the next launch on this stream
     }
