@@ -116,10 +116,26 @@ __device__ __forceinline__ void block_finish(double (&v)[NV], double *smem, doub
     }
     __syncthreads();
     if (is_last) {
+        // every thread adds a strided subset of the CTA partials (loads issued back to back), then the subsets are
+        // folded warp by warp in a fixed order -- one thread walking gridDim.x dependent L2 round trips cost ~0.3 ms
         __threadfence();
+        double t[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) t[i] = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) t[i] += partials[(size_t)b * NV + i];
+        }
+        warp_reduce<NV>(t);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) smem[warp * NV + i] = t[i];
+        }
+        __syncthreads();
         if (threadIdx.x < NV) {
             double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NV + threadIdx.x];
+            for (int w = 0; w < nwarp; ++w) s += smem[w * NV + threadIdx.x];
             out[threadIdx.x] = s;
         }
         if (threadIdx.x == 0) *counter = 0u;   // re-arm for the next launch on this stream
