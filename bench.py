@@ -189,7 +189,7 @@ def instruction_roofline(h, achieved_path_steps_per_gpu, sm_mhz):
     binding = min(b_algo, key=b_algo.get)
     peak = b_algo[binding]
     return {"bound": binding, "achieved": achieved_path_steps_per_gpu, "peak": peak, "unit": UNIT,
-            "frac": achieved_path_steps_per_gpu / peak, "traffic": 38144,
+            "frac": achieved_path_steps_per_gpu / peak, "traffic": 23040,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture "
                               "profiles/r01_ncu_k_european_gbm_fp32_greeks.txt (algorithmic bytes: 0 per path-step)",
             "kernel": "k_european<GBM, fp32, greeks>", "kind": "instruction roofline (the kernel moves no data): "
