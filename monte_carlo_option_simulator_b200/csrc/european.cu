@@ -35,6 +35,8 @@ struct EuroArgs {
     int32_t n_strikes;
     int32_t is_call;
     int32_t wld;
+    int32_t fold_inside;                       // 1: the last CTA to finish adds the CTA partials; 0: k_fold_partials does
+    int32_t pad_;
     double up_mul, dn_mul, rup_mul, rdn_mul;   // S_T multipliers of the spot and rate bumps
     double sigmaT;                             // sqrt(v0) T        (pathwise vega, GBM only)
     double w_scale;                            // sqrt(dt) BM_SCALE (W_T = w_scale * sum raw z)
@@ -198,6 +200,7 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g
             __syncthreads();
         }
     }
+    if (!a.fold_inside) return;         // many strikes: a separate multi-CTA kernel adds the partials (k_fold_partials)
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
@@ -210,42 +213,59 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g
         // for a given launch geometry.
         __threadfence();
         const int items = ks * NACC;
-        if (items > 128) {              // many strikes: one thread per item already keeps 256+ independent chains in flight
-            for (int it = tid; it < items; it += EU_THREADS) {
-                double s = 0.0;
-                for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * items + it];
-                const int k = it / NACC, j = it % NACC;
-                out[(size_t)k * (NACC + 1) + 1 + j] = s;
-                if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
+        const int LANES = items <= 16 ? 16 : (items <= 32 ? 8 : (items <= 64 ? 4 : 2));
+        for (int it0 = 0; it0 < items; it0 += EU_THREADS / LANES) {      // a single pass (items <= 128)
+            const int it = it0 + tid / LANES, sub = tid % LANES;
+            double s = 0.0;
+            if (it < items) {
+                unsigned int b = sub;
+                for (; b + 3 * LANES < gridDim.x; b += 4 * LANES) {
+                    const double p0 = partials[(size_t)b * items + it], p1 = partials[(size_t)(b + LANES) * items + it],
+                                 p2 = partials[(size_t)(b + 2 * LANES) * items + it],
+                                 p3 = partials[(size_t)(b + 3 * LANES) * items + it];
+                    s += p0; s += p1; s += p2; s += p3;
+                }
+                for (; b < gridDim.x; b += LANES) s += partials[(size_t)b * items + it];
             }
-        } else {
-            const int LANES = items <= 16 ? 16 : (items <= 32 ? 8 : (items <= 64 ? 4 : 2));
-            for (int it0 = 0; it0 < items; it0 += EU_THREADS / LANES) {      // a single pass (items <= 256 / LANES)
-                const int it = it0 + tid / LANES, sub = tid % LANES;
-                double s = 0.0;
-                if (it < items) {
-                    unsigned int b = sub;
-                    for (; b + 3 * LANES < gridDim.x; b += 4 * LANES) {
-                        const double p0 = partials[(size_t)b * items + it], p1 = partials[(size_t)(b + LANES) * items + it],
-                                     p2 = partials[(size_t)(b + 2 * LANES) * items + it],
-                                     p3 = partials[(size_t)(b + 3 * LANES) * items + it];
-                        s += p0; s += p1; s += p2; s += p3;
-                    }
-                    for (; b < gridDim.x; b += LANES) s += partials[(size_t)b * items + it];
-                }
-                __syncthreads();
-                red[tid] = s;
-                __syncthreads();
-                if (it < items && sub == 0) {
-                    double tot = 0.0;
-                    for (int q = 0; q < LANES; ++q) tot += red[tid + q];
-                    const int k = it / NACC, j = it % NACC;
-                    out[(size_t)k * (NACC + 1) + 1 + j] = tot;
-                    if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
-                }
+            __syncthreads();
+            red[tid] = s;
+            __syncthreads();
+            if (it < items && sub == 0) {
+                double tot = 0.0;
+                for (int q = 0; q < LANES; ++q) tot += red[tid + q];
+                const int k = it / NACC, j = it % NACC;
+                out[(size_t)k * (NACC + 1) + 1 + j] = tot;
+                if (j == 0) out[(size_t)k * (NACC + 1)] = (double)a.n_paths;
             }
         }
         if (tid == 0) *counter = 0u;   // re-arm for the next launch on this stream
+    }
+}
+
+// Sum of the CTA partials for launches with many strikes (items = n_strikes * 16 > 128): one CTA reading
+// gridDim.x * items doubles is limited by the bandwidth of a single SM (4.8 MB for 64 strikes: ~70 us), so this runs as
+// its own small grid, 64 items per CTA, 4 lanes per item over the CTA index, folded in a fixed order.
+__global__ void __launch_bounds__(256)
+k_fold_partials(const double *__restrict__ partials, int n_ctas, int items, double n_paths, double *__restrict__ out)
+{
+    const int it = blockIdx.x * 64 + (threadIdx.x >> 2), sub = threadIdx.x & 3;
+    double s = 0.0;
+    if (it < items) {
+        int b = sub;
+        for (; b + 12 < n_ctas; b += 16) {
+            const double p0 = partials[(size_t)b * items + it], p1 = partials[(size_t)(b + 4) * items + it],
+                         p2 = partials[(size_t)(b + 8) * items + it], p3 = partials[(size_t)(b + 12) * items + it];
+            s += p0; s += p1; s += p2; s += p3;
+        }
+        for (; b < n_ctas; b += 4) s += partials[(size_t)b * items + it];
+    }
+    const double s1 = __shfl_down_sync(0xffffffffu, s, 1), s2 = __shfl_down_sync(0xffffffffu, s, 2),
+                 s3 = __shfl_down_sync(0xffffffffu, s, 3);
+    if (it < items && sub == 0) {
+        const double tot = ((s + s1) + s2) + s3;
+        const int k = it / NACC, j = it % NACC;
+        out[(size_t)k * (NACC + 1) + 1 + j] = tot;
+        if (j == 0) out[(size_t)k * (NACC + 1)] = n_paths;
     }
 }
 
@@ -292,6 +312,7 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
     a.n_strikes = n_strikes;
     a.is_call = is_call ? 1 : 0;
     a.wld = pr.wld;
+    a.fold_inside = (n_strikes * NACC <= 128) ? 1 : 0;
     if (greeks) {
         a.up_mul = 1.0 + bumps->spot_bump;
         a.dn_mul = 1.0 - bumps->spot_bump;
@@ -348,6 +369,13 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
                                                           out_dev);
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
+    if (!a.fold_inside) {
+        const int items = n_strikes * NACC;
+        k_fold_partials<<<(items + 63) / 64, 256, 0, h->stream>>>((const double *)(sc + off_p), (int)grid, items,
+                                                                 (double)n_paths, out_dev);
+        B200MC_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    }
     return 0;
 }
 
