@@ -165,6 +165,27 @@ int b200mc_price_european_async(b200mc_handle *h, const b200mc_svj_params *p, do
                                 const double *strikes, int32_t n_strikes, int is_call, uint32_t flags,
                                 const b200mc_bumps *bumps, b200mc_sums *out_dev);
 
+/* ---- a11 / SURVEY 8(f)-1,2: many independent pricing problems in one launch over a (cell x path) grid ------
+ * The reference prices scenario ladders and optimiser candidates as loops of MonteCarloEngine.price():
+ * StressTestEngine (engine/risk.py:33-111, 13 calls), the premium of every HedgingBacktest scenario
+ * (engine/risk.py:264-273, num_scenarios calls), the calibration objectives (engine/calibration.py:78-89,
+ * 119-130).  A cell is one such call: its own parameters, spot, maturity, steps, paths, seed, option type.
+ * All cells of a call share n_strikes and flags (ANTITHETIC, FP64, FORCE_SVJ; GREEKS is rejected);
+ * strikes is [n_cells][n_strikes] (host), out is [n_cells][n_strikes] b200mc_sums (host, or device memory when
+ * on_device != 0: then the call is asynchronous on the handle's stream).  Cell i's sums equal those of
+ * b200mc_price_european(cell i's arguments, strikes[i], ...) -- same draws, same per-path arithmetic -- up to the
+ * order of the fp64 additions; the Greek fields are 0. */
+typedef struct b200mc_cell {
+    b200mc_svj_params params;
+    double S0, T;
+    int64_t n_paths;
+    uint64_t seed, path_offset;
+    int32_t n_steps;
+    int32_t is_call;
+} b200mc_cell;
+int b200mc_price_cells(b200mc_handle *h, const b200mc_cell *cells, int32_t n_cells, const double *strikes,
+                       int32_t n_strikes, uint32_t flags, int on_device, b200mc_sums *out);
+
 /* Terminal values of the fused simulation (deterministic-mode parity of the fused kernels, and the terminal
  * P&L vector for compute_risk_metrics, engine/risk.py:117).  S_T / S_T_anti / v_T are [n_paths] of `dtype`
  * (B200MC_F32 / B200MC_F64); any may be NULL.  on_device != 0: pointers are device memory. */

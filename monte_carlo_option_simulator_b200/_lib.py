@@ -42,6 +42,41 @@ class Bumps(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("spot_bump", "v0_up", "v0_dn", "r_up", "r_dn")]
 
 
+class Cell(C.Structure):
+    """b200mc_cell -- one pricing problem of a b200mc_price_cells launch."""
+    _fields_ = [("params", SvjParams), ("S0", C.c_double), ("T", C.c_double), ("n_paths", C.c_int64),
+                ("seed", C.c_uint64), ("path_offset", C.c_uint64), ("n_steps", C.c_int32), ("is_call", C.c_int32)]
+
+
+PARAM_FIELDS = tuple(n for n, _ in SvjParams._fields_)
+# numpy mirror of b200mc_cell (same layout as the ctypes struct above): lets callers fill thousands of cells vectorised
+CELL_DTYPE = np.dtype([(n, "<f8") for n in PARAM_FIELDS] +
+                      [("S0", "<f8"), ("T", "<f8"), ("n_paths", "<i8"), ("seed", "<u8"), ("path_offset", "<u8"),
+                       ("n_steps", "<i4"), ("is_call", "<i4")])
+assert CELL_DTYPE.itemsize == C.sizeof(Cell)
+
+
+def make_cells(params, S0, T, n_steps, n_paths, seed, path_offset=0, is_call=True) -> np.ndarray:
+    """Structured array of b200mc_cell.  Every argument is a scalar or a sequence (broadcast to the longest);
+    `params` is one parameter object (shared by all cells) or a sequence of them."""
+    cols = dict(S0=np.atleast_1d(np.asarray(S0, dtype=np.float64)), T=np.atleast_1d(np.asarray(T, dtype=np.float64)),
+                n_paths=np.atleast_1d(np.asarray(n_paths, dtype=np.int64)),
+                n_steps=np.atleast_1d(np.asarray(n_steps, dtype=np.int32)),
+                is_call=np.atleast_1d(np.asarray(is_call)).astype(np.int32),
+                path_offset=np.atleast_1d(np.array(path_offset, dtype=np.uint64)))
+    sd = np.atleast_1d(np.asarray(seed))
+    cols["seed"] = np.array([int(x) & (2 ** 64 - 1) for x in sd.tolist()], dtype=np.uint64) if sd.dtype == object \
+        else sd.astype(np.int64).view(np.uint64) if sd.dtype.kind == "i" else sd.astype(np.uint64)
+    plist = list(params) if isinstance(params, (list, tuple)) else [params]
+    n = max([len(plist)] + [c.size for c in cols.values()])
+    out = np.zeros(n, dtype=CELL_DTYPE)
+    for f in PARAM_FIELDS:
+        out[f] = np.array([float(getattr(p, f)) for p in plist]) if len(plist) > 1 else float(getattr(plist[0], f))
+    for k, c in cols.items():
+        out[k] = c if c.size > 1 else c[0]
+    return out
+
+
 SUMS_FIELDS = ("n", "sum_a", "sum_b", "sum_aa", "sum_bb", "sum_ab", "sum_s", "sum_ss", "sum_ps",
                "sum_pw_delta", "sum_spot_up", "sum_spot_dn", "sum_v0_up", "sum_v0_dn", "sum_r_up", "sum_r_dn",
                "sum_pw_vega")
@@ -76,6 +111,7 @@ _PROTOS = {
                                          _vp, _i32, C.c_int, _u32, C.POINTER(Bumps), _vp]),
     "b200mc_price_european_async": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                                _vp, _i32, C.c_int, _u32, C.POINTER(Bumps), _vp]),
+    "b200mc_price_cells": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _u32, C.c_int, _vp]),
     "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                             _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
@@ -260,6 +296,34 @@ class Handle:
             return None
         out = np.empty((strikes.size, NSUMS), dtype=np.float64)
         self._check(self.lib.b200mc_price_european(*args, out.ctypes.data))
+        return out
+
+    def price_cells(self, cells, strikes, flags=0, out_dev: Optional[int] = None):
+        """cells: a structured array from make_cells(), or a sequence of dicts / objects with params, S0, T, n_steps,
+        n_paths, seed[, path_offset, is_call]; strikes: [n_cells, n_strikes] (or [n_cells]).  Returns float64
+        [n_cells, n_strikes, NSUMS], or None when `out_dev` is given (asynchronous)."""
+        if not (isinstance(cells, np.ndarray) and cells.dtype == CELL_DTYPE):
+            if not len(cells):
+                raise B200MCError(EINVAL, "cells must hold at least one cell")
+            get = (lambda c, k, d=None: c.get(k, d)) if isinstance(cells[0], dict) else \
+                  (lambda c, k, d=None: getattr(c, k, d))
+            cells = make_cells([get(c, "params") for c in cells], [get(c, "S0") for c in cells],
+                               [get(c, "T") for c in cells], [get(c, "n_steps") for c in cells],
+                               [get(c, "n_paths") for c in cells], [get(c, "seed") for c in cells],
+                               [get(c, "path_offset", 0) or 0 for c in cells],
+                               [bool(get(c, "is_call", True)) for c in cells])
+        cells = np.ascontiguousarray(cells)
+        n = cells.size
+        if not n:
+            raise B200MCError(EINVAL, "cells must hold at least one cell")
+        ks = np.ascontiguousarray(strikes, dtype=np.float64).reshape(n, -1)
+        if out_dev is not None:
+            self._check(self.lib.b200mc_price_cells(self.h, cells.ctypes.data, n, ks.ctypes.data, ks.shape[1],
+                                                     int(flags), 1, _vp(out_dev)))
+            return None
+        out = np.empty((n, ks.shape[1], NSUMS), dtype=np.float64)
+        self._check(self.lib.b200mc_price_cells(self.h, cells.ctypes.data, n, ks.ctypes.data, ks.shape[1], int(flags), 0,
+                                                 out.ctypes.data))
         return out
 
     def simulate_terminal(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,

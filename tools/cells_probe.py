@@ -1,0 +1,40 @@
+"""(cell x path) grid launch vs a loop of single-problem launches: the hedging-backtest premiums (1000 scenarios x 50k
+paths x 63 steps, engine/risk.py:264-273) and the 13 scenarios of a stress report (200k paths)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from monte_carlo_option_simulator_b200 import SVJParams, _lib  # noqa: E402
+
+h = _lib.Handle(0)
+for name, p in (("gbm", SVJParams.gbm(0.3, r=0.065)), ("svj", SVJParams())):
+    for n_cells, n_paths, steps in ((1000, 50_000, 63), (13, 200_000, 63), (64, 1_000_000, 250)):
+        cells = _lib.make_cells(p, 22500.0, steps / 252, steps, n_paths, 42 + np.arange(n_cells))
+        ks = np.full(n_cells, 22500.0)
+        out = h.malloc(n_cells * 17 * 8)
+        best_b = best_l = best_w = 1e9
+        for r in range(4):
+            t0 = time.perf_counter()
+            h.timer_begin()
+            h.price_cells(cells, ks, _lib.ANTITHETIC, out_dev=out)
+            ms = h.timer_end()
+            w = (time.perf_counter() - t0) * 1e3
+            if r:
+                best_b, best_w = min(best_b, ms), min(best_w, w)
+        for r in range(3):
+            h.timer_begin()
+            for i in range(n_cells):
+                h.price_european(p, 22500.0, steps / 252, steps, n_paths, 42 + i, [22500.0], True, _lib.ANTITHETIC,
+                                 out_dev=out + i * 17 * 8)
+            ms = h.timer_end()
+            if r:
+                best_l = min(best_l, ms)
+        h.free(out)
+        work = n_cells * n_paths * steps
+        print(f"{name} {n_cells:5d} cells x {n_paths:8d} paths x {steps:3d}: one launch {best_b:8.3f} ms "
+              f"({work / best_b / 1e9:6.3f}e12 path-steps/s, wall {best_w:7.2f} ms)   "
+              f"loop of launches {best_l:8.3f} ms", flush=True)
+h.close()
