@@ -61,6 +61,7 @@ extern "C" {
 #define B200MC_STREAM_GBM    0u
 #define B200MC_STREAM_HESTON 1u
 #define B200MC_STREAM_SVJ    2u
+#define B200MC_STREAM_HEDGE  3u   /* b200mc_hedge_walk: GBM layout, counter path = scenario index */
 
 /* which array b200mc_dump_normals returns */
 #define B200MC_Z1         0
@@ -185,6 +186,18 @@ typedef struct b200mc_cell {
 } b200mc_cell;
 int b200mc_price_cells(b200mc_handle *h, const b200mc_cell *cells, int32_t n_cells, const double *strikes,
                        int32_t n_strikes, uint32_t flags, int on_device, b200mc_sums *out);
+
+/* The daily delta-hedging walk of HedgingBacktest.run_backtest (engine/risk.py:278-316) for n_scenarios scenarios:
+ * Black-Scholes delta at sigma = sqrt(v0) (engine/monte_carlo.py:45-55), rebalancing cost |trade| S cost_bps / 10000
+ * with cost_bps = txn_cost_bps + slippage_bps, one GBM step per day, settlement against the option payoff; fp64 in the
+ * reference's operation order.  premiums: [n_scenarios] cash received at t = 0 (risk.py:271-273; NULL = 0).
+ * Z: [n_scenarios][n_days] standard normals (HOST; the reference's default_rng(seed).standard_normal() sequence) or
+ * NULL: then the normals are Philox draws, counter = (scenario_offset + i, day / 8, B200MC_STREAM_HEDGE), key = seed,
+ * exactly what b200mc_dump_normals(seed, scenario_offset, n, n_days, B200MC_STREAM_HEDGE, B200MC_Z1) returns.
+ * Outputs (HOST): final_pnl[n_scenarios]; txn_cost[n_scenarios] total rebalancing cost (may be NULL). */
+int b200mc_hedge_walk(b200mc_handle *h, const b200mc_svj_params *p, double S0, double strike, double T, int is_call,
+                      int32_t n_days, int64_t n_scenarios, double cost_bps, const double *premiums, const double *Z,
+                      uint64_t seed, uint64_t scenario_offset, double *final_pnl, double *txn_cost);
 
 /* Terminal values of the fused simulation (deterministic-mode parity of the fused kernels, and the terminal
  * P&L vector for compute_risk_metrics, engine/risk.py:117).  S_T / S_T_anti / v_T are [n_paths] of `dtype`

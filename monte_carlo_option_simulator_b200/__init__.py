@@ -5,8 +5,9 @@ from .models import SVJParams                                   # noqa: F401
 from .monte_carlo import (MonteCarloEngine, bs_delta, bs_price,  # noqa: F401
                           _simulate_svj_paths_numba, brownian_bridge_reorder, generate_sobol_normals)
 from .greeks import GreeksEngine                                # noqa: F401
-from .risk import compute_risk_metrics                          # noqa: F401
+from .risk import (HedgingBacktest, LiquidityStress, StressTestEngine,  # noqa: F401
+                   compute_risk_metrics)
 from .patch import patch_reference                              # noqa: F401
 
-__all__ = ["SVJParams", "MonteCarloEngine", "GreeksEngine", "compute_risk_metrics", "bs_price", "bs_delta",
-           "patch_reference"]
+__all__ = ["SVJParams", "MonteCarloEngine", "GreeksEngine", "compute_risk_metrics", "StressTestEngine", "LiquidityStress",
+           "HedgingBacktest", "bs_price", "bs_delta", "patch_reference"]

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libb200mc.so")
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM = 0, 1, 2, 3, 4
 ANTITHETIC, GREEKS, FP64, FORCE_SVJ = 0x1, 0x2, 0x4, 0x8
-STREAM_GBM, STREAM_HESTON, STREAM_SVJ = 0, 1, 2
+STREAM_GBM, STREAM_HESTON, STREAM_SVJ, STREAM_HEDGE = 0, 1, 2, 3
 Z1, Z2, ZJUMP_U, ZJUMP_SIZE = 0, 1, 2, 3
 F32, F64 = 0, 1
 
@@ -112,6 +112,8 @@ _PROTOS = {
     "b200mc_price_european_async": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                                _vp, _i32, C.c_int, _u32, C.POINTER(Bumps), _vp]),
     "b200mc_price_cells": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _u32, C.c_int, _vp]),
+    "b200mc_hedge_walk": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _dbl, C.c_int, _i32, _i64, _dbl, _vp, _vp,
+                                     _u64, _u64, _vp, _vp]),
     "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                             _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
@@ -325,6 +327,27 @@ class Handle:
         self._check(self.lib.b200mc_price_cells(self.h, cells.ctypes.data, n, ks.ctypes.data, ks.shape[1], int(flags), 0,
                                                  out.ctypes.data))
         return out
+
+    def hedge_walk(self, params, S0, strike, T, is_call, n_days, n_scenarios, cost_bps, premiums=None, Z=None, seed=0,
+                   scenario_offset=0):
+        """The delta-hedging walk of engine/risk.py:278-316 for all scenarios: returns (final_pnl, txn_cost), float64
+        [n_scenarios].  Z: [n_scenarios, n_days] host normals, or None for Philox draws (STREAM_HEDGE) keyed by seed."""
+        n = int(n_scenarios)
+        prem = None if premiums is None else np.ascontiguousarray(premiums, dtype=np.float64).ravel()
+        if prem is not None and prem.size != n:
+            raise B200MCError(EINVAL, "premiums must hold one value per scenario")
+        z = None
+        if Z is not None:
+            z = np.ascontiguousarray(Z, dtype=np.float64)
+            if z.shape != (n, int(n_days)):
+                raise B200MCError(EINVAL, "Z must be [n_scenarios, n_days]")
+        pnl, cost = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        sp = to_params(params)
+        self._check(self.lib.b200mc_hedge_walk(self.h, C.byref(sp), float(S0), float(strike), float(T), int(bool(is_call)),
+                                                int(n_days), n, float(cost_bps), _ptr(prem), _ptr(z),
+                                                int(seed) & (2 ** 64 - 1), int(scenario_offset), pnl.ctypes.data,
+                                                cost.ctypes.data))
+        return pnl, cost
 
     def simulate_terminal(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,
                           want_anti=False, want_v=False, dev_ptrs=None):

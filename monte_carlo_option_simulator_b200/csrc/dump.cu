@@ -26,7 +26,8 @@ __global__ void k_dump_philox(PhiloxKey key, uint64_t path0, int64_t n_paths, in
 __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_steps, uint32_t stream, int which,
                                double jump_prob, double *__restrict__ out)
 {
-    const int per = stream == B200MC_STREAM_GBM ? 8 : (stream == B200MC_STREAM_HESTON ? 4 : 2);
+    const bool gbm_layout = stream == B200MC_STREAM_GBM || stream == B200MC_STREAM_HEDGE;
+    const int per = gbm_layout ? 8 : (stream == B200MC_STREAM_HESTON ? 4 : 2);
     const int n_blocks = (n_steps + per - 1) / per;
     const int64_t total = n_paths * n_blocks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -38,7 +39,7 @@ __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, i
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
         const double neutral = which == B200MC_ZJUMP_U ? 1.0 : 0.0;
         double vals[8];
-        if (stream == B200MC_STREAM_GBM) {
+        if (gbm_layout) {
             for (int t = 0; t < 4; ++t) {
                 const BM2 b = box_muller_word(ww[t]);
                 vals[2 * t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rc : neutral;
@@ -143,7 +144,7 @@ extern "C" int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t pat
 {
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
     if (!out || n_paths <= 0 || n_steps <= 0) return fail(h, B200MC_EINVAL, "bad argument");
-    if (stream > B200MC_STREAM_SVJ) return fail(h, B200MC_EINVAL, "unknown stream");
+    if (stream > B200MC_STREAM_HEDGE) return fail(h, B200MC_EINVAL, "unknown stream");
     if (which < B200MC_Z1 || which > B200MC_ZJUMP_SIZE) return fail(h, B200MC_EINVAL, "unknown array selector");
     B200MC_CUDA(h, cudaSetDevice(h->device));
     const size_t bytes = (size_t)n_paths * n_steps * 8;

@@ -256,9 +256,12 @@ class MonteCarloEngine:
         """Price a European option; same keys as monte_carlo.py:345-373."""
         if self.rng == "reference":
             return self._price_reference(spot, strike, T, is_call)
-        p = self.params
         steps = steps_for(self.num_steps, T)                                   # :287
         row = self._sums(spot, [float(strike)], T, is_call, steps)[0]
+        return self._result(row, self.params, spot, strike, T, is_call, steps)
+
+    def _result(self, row, p, spot, strike, T, is_call, steps) -> Dict[str, float]:
+        """The dict of price() from one b200mc_sums row."""
         n, mean, var, mean_a, dvar = self._moments(row, self.use_antithetic)
         discount = math.exp(-p.r * T)                                          # :327
         raw_price = discount * mean                                            # :342
@@ -272,13 +275,52 @@ class MonteCarloEngine:
             result["bs_ref"] = bs_ref
             result["raw_mc_price"] = raw_price
             result["std_error"] = discount * math.sqrt(dvar) / math.sqrt(n)
-        result.update(self._spot_cv(row, spot, T, discount))
+        result.update(self._spot_cv(row, spot, T, discount, p))
         return result
 
-    def _spot_cv(self, row, spot, T, discount) -> Dict[str, float]:
+    def price_many(self, spots, strikes, Ts, is_call=True, *, params=None, seeds=None) -> List[Dict[str, float]]:
+        """NEW: many independent price() problems in ONE launch over a (cell x path) grid
+        (b200mc_price_cells).  spots / strikes / Ts / is_call / params / seeds are scalars or sequences (broadcast);
+        problem i returns exactly what MonteCarloEngine(params_i, num_paths, num_steps, seeds_i, <flags of self>)
+        .price(spot_i, strike_i, T_i, is_call_i) returns (same draws, sums equal up to the order of the fp64 additions).
+        This is what the loops of engine/risk.py:33-111 (stress ladders) and :264-273 (premium of every hedging
+        scenario) become.  With a communicator the paths of every cell are sharded and the sums all-reduced once."""
+        def seq(x, n=None):
+            return list(x) if isinstance(x, (list, tuple, np.ndarray)) else None
+        cols = [seq(spots), seq(strikes), seq(Ts), seq(is_call), seq(params), seq(seeds)]
+        m = max([len(c) for c in cols if c is not None] or [1])
+        defaults = [spots, strikes, Ts, is_call, params if params is not None else self.params,
+                    seeds if seeds is not None else self.seed]
+        cols = [c if c is not None else [d] * m for c, d in zip(cols, defaults)]
+        if any(len(c) != m for c in cols):
+            raise ValueError("price_many: sequences must have a common length")
+        sp, ks, ts, calls, ps, sds = cols
+        if self.rng == "reference":
+            return [MonteCarloEngine(ps[i], self.num_paths, self.num_steps, sds[i], self.use_sobol, self.use_antithetic,
+                                     self.use_control_variate, rng="reference", precision=self.precision,
+                                     handle=self._handle, comm=self.comm).price(sp[i], ks[i], ts[i], calls[i])
+                    for i in range(m)]
+        steps = [steps_for(self.num_steps, float(T)) for T in ts]
+        n, lo = int(self.num_paths), 0
+        world = self.comm.world if self.comm is not None else 1
+        if world > 1:
+            from .dist import shard_range
+            lo, hi = shard_range(n, self.comm.rank, world)
+            n = hi - lo
+        if n > 0:
+            cells = _lib.make_cells(ps if isinstance(params, (list, tuple)) else ps[0], [float(x) for x in sp],
+                                    [float(x) for x in ts], steps, n, sds, lo, [bool(c) for c in calls])
+            sums = self.handle.price_cells(cells, np.asarray(ks, dtype=np.float64), self._flags())[:, 0, :]
+        else:
+            sums = np.zeros((m, len(SUMS_FIELDS)))
+        if world > 1:
+            sums = self.comm.allreduce_sum(sums).reshape(m, len(SUMS_FIELDS))
+        return [self._result(sums[i], ps[i], sp[i], ks[i], ts[i], calls[i], steps[i]) for i in range(m)]
+
+    def _spot_cv(self, row, spot, T, discount, p=None) -> Dict[str, float]:
         """NEW keys: regression control variate on S_T, whose mean S0 e^{(r-q)T} is known for every SVJ
         parameter set (the jump drift is compensated, monte_carlo.py:209-210)."""
-        p = self.params
+        p = p or self.params
         n = row[_COL["n"]]
         anti = self.use_antithetic
         pay_mean = (0.5 * (row[_COL["sum_a"]] + row[_COL["sum_b"]]) if anti else row[_COL["sum_a"]]) / n

@@ -57,9 +57,12 @@ def _batched_objectives(calib):
     return _heston_objective, _svj_objective
 
 
-def patch_reference(package: str = "engine", batch_calibration: bool = True) -> List[str]:
+def patch_reference(package: str = "engine", batch_calibration: bool = True, batch_scenarios: bool = True) -> List[str]:
     """Returns the list of 'module.attribute' names that were rebound.  batch_calibration: also replace the two
-    calibration objectives by versions that price all strikes of a candidate in one launch."""
+    calibration objectives by versions that price all strikes of a candidate in one launch.
+    batch_scenarios: also replace StressTestEngine / HedgingBacktest / LiquidityStress (engine/risk.py:23-337) by the
+    mirrors that price all scenarios of a report in one launch; with False the reference's own
+    classes keep running, one price() call per scenario, on the rebound MonteCarloEngine."""
     done = []
 
     def rebind(modname, attr, obj):
@@ -81,6 +84,9 @@ def patch_reference(package: str = "engine", batch_calibration: bool = True) -> 
     rebind(f"{package}.greeks", "GreeksEngine", _g.GreeksEngine)
     rebind(f"{package}.risk", "MonteCarloEngine", _mc.MonteCarloEngine)
     rebind(f"{package}.risk", "compute_risk_metrics", _r.compute_risk_metrics)
+    if batch_scenarios:
+        for attr in ("StressTestEngine", "LiquidityStress", "HedgingBacktest"):
+            rebind(f"{package}.risk", attr, getattr(_r, attr))
     rebind(f"{package}.calibration", "MonteCarloEngine", _mc.MonteCarloEngine)
     calib = sys.modules.get(f"{package}.calibration")
     if batch_calibration and calib is not None and all(hasattr(calib, a) for a in
@@ -89,6 +95,10 @@ def patch_reference(package: str = "engine", batch_calibration: bool = True) -> 
         h_obj, s_obj = _batched_objectives(calib)
         rebind(f"{package}.calibration", "_heston_objective", h_obj)
         rebind(f"{package}.calibration", "_svj_objective", s_obj)
-    for attr, obj in (("MonteCarloEngine", _mc.MonteCarloEngine), ("GreeksEngine", _g.GreeksEngine)):
+    app = [("MonteCarloEngine", _mc.MonteCarloEngine), ("GreeksEngine", _g.GreeksEngine),
+           ("compute_risk_metrics", _r.compute_risk_metrics)]
+    if batch_scenarios:
+        app += [(a, getattr(_r, a)) for a in ("StressTestEngine", "LiquidityStress", "HedgingBacktest")]
+    for attr, obj in app:
         rebind(f"{package}.app", attr, obj)
     return done

@@ -1,15 +1,26 @@
-"""Host mirror of the path-based tail metrics of engine/risk.py (compute_risk_metrics :117-155, Hill :158-173).
+"""Host mirror of engine/risk.py: the path-based tail metrics (compute_risk_metrics :117-155, Hill :158-173) and the
+callers built on MonteCarloEngine.price -- StressTestEngine (:23-111), LiquidityStress (:178-222), HedgingBacktest
+(:228-337).
 
 The reference sorts the whole P&L vector on the host; here the vector goes to the GPU once (or already lives there)
-and the order statistics come from an exact radix select (csrc/risk.cu).  Same keys, same index conventions."""
+and the order statistics come from an exact radix select (csrc/risk.cu).  Same keys, same index conventions.
+The reference prices every stress scenario and every hedging scenario's premium with its own price() call; here all
+scenarios of a report go out as one (cell x path) launch (MonteCarloEngine.price_many -> b200mc_price_cells) and the
+hedging walk runs as one kernel over the scenarios (b200mc_hedge_walk)."""
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional
+from typing import Dict, List, Optional
 
 import numpy as np
 
 from . import _lib
+from .models import SVJParams, copy_with
+from .monte_carlo import MonteCarloEngine
+
+SPOT_SHOCKS = [-0.08, -0.05, -0.02, 0.02, 0.05, 0.08]     # engine/config.py:134
+VOL_SHOCKS = [-0.05, 0.05]                                # engine/config.py:135  (+-5 vol points)
+JUMP_SCENARIO_SIZE = 0.04                                 # engine/config.py:136
 
 KEYS = ("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std")
 
@@ -112,3 +123,124 @@ def terminal_pnl_metrics(params, spot: float, strike: float, T: float, n_paths: 
     res = {k: float(v) for k, v in zip(KEYS, out)}
     res["premium"] = float(premium)
     return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# a11: the callers of engine/risk.py
+# ------------------------------------------------------------------------------------------------------------
+class StressTestEngine:
+    """Mirror of StressTestEngine (engine/risk.py:23-111): same constructor, methods, keys and numbers as the reference
+    run on this package's MonteCarloEngine with the reference's default flags; every ladder (and the whole report) is
+    ONE launch.  Keyword-only extras: rng, precision, handle, comm (as MonteCarloEngine)."""
+
+    def __init__(self, params, num_paths: int = 200_000, seed: int = 42, *, rng=None, precision="fp32", handle=None,
+                 comm=None):
+        self.params = params
+        self.num_paths = num_paths
+        self.seed = seed
+        self._kw = dict(rng=rng, precision=precision, handle=handle, comm=comm)
+
+    def _engine(self) -> MonteCarloEngine:
+        return MonteCarloEngine(self.params, num_paths=self.num_paths, seed=self.seed, **self._kw)   # :36,56,85
+
+    def _vol_shocked(self, shock: float) -> SVJParams:
+        p = self.params                                                                            # :61-68
+        return copy_with(p, v0=max(p.v0 + 2 * np.sqrt(p.v0) * shock, 0.001), theta=max(p.theta + shock ** 2, 0.001))
+
+    # every method lists its scenarios, prices them in one launch and formats the reference's dicts
+    def _prices(self, spots, params, strike, T, is_call) -> List[float]:
+        res = self._engine().price_many(spots, strike, T, is_call, params=params)
+        return [r["price"] for r in res]
+
+    @staticmethod
+    def _spot_rows(spot, base, prices):
+        return [{"shock_pct": sh * 100, "spot": spot * (1 + sh), "price": pr, "pnl": pr - base,
+                 "pnl_pct": (pr - base) / max(base, 1e-6) * 100} for sh, pr in zip(SPOT_SHOCKS, prices)]   # :42-49
+
+    def spot_shock_ladder(self, spot: float, strike: float, T: float, is_call: bool = True) -> List[Dict]:
+        pr = self._prices([spot] + [spot * (1 + sh) for sh in SPOT_SHOCKS], [self.params] * 7, strike, T, is_call)
+        return self._spot_rows(spot, pr[0], pr[1:])
+
+    def _vol_rows(self, base, shocked, prices):
+        return [{"vol_shock": sh * 100, "v0": sp.v0, "price": pr, "pnl": pr - base}                 # :71-76
+                for sh, sp, pr in zip(VOL_SHOCKS, shocked, prices)]
+
+    def vol_shock_ladder(self, spot: float, strike: float, T: float, is_call: bool = True) -> List[Dict]:
+        shocked = [self._vol_shocked(sh) for sh in VOL_SHOCKS]
+        pr = self._prices([spot] * (1 + len(shocked)), [self.params] + shocked, strike, T, is_call)
+        return self._vol_rows(pr[0], shocked, pr[1:])
+
+    @staticmethod
+    def _jump_dict(base, dn, up, gap_size):
+        return {"base_price": base, "gap_down_price": dn, "gap_down_pnl": dn - base, "gap_up_price": up,
+                "gap_up_pnl": up - base, "gap_size_pct": gap_size * 100}                            # :96-103
+
+    def jump_scenario(self, spot: float, strike: float, T: float, is_call: bool = True,
+                      gap_size: float = JUMP_SCENARIO_SIZE) -> Dict:
+        pr = self._prices([spot, spot * (1 - gap_size), spot * (1 + gap_size)], [self.params] * 3, strike, T, is_call)
+        return self._jump_dict(pr[0], pr[1], pr[2], gap_size)
+
+    def full_stress_report(self, spot: float, strike: float, T: float, is_call: bool = True) -> Dict:
+        """All scenarios of the three ladders (:105-111) as one launch; the base price (the reference recomputes it,
+        identically, for every ladder) is priced once."""
+        shocked = [self._vol_shocked(sh) for sh in VOL_SHOCKS]
+        g = JUMP_SCENARIO_SIZE
+        spots = [spot] + [spot * (1 + sh) for sh in SPOT_SHOCKS] + [spot] * len(shocked) + [spot * (1 - g), spot * (1 + g)]
+        params = [self.params] * 7 + shocked + [self.params] * 2
+        pr = self._prices(spots, params, strike, T, is_call)
+        ns = len(SPOT_SHOCKS)
+        return {"spot_shocks": self._spot_rows(spot, pr[0], pr[1:1 + ns]),
+                "vol_shocks": self._vol_rows(pr[0], shocked, pr[1 + ns:1 + ns + len(shocked)]),
+                "jump_scenario": self._jump_dict(pr[0], pr[-2], pr[-1], g)}
+
+
+class LiquidityStress:
+    """Mirror of LiquidityStress (engine/risk.py:178-222): closed-form parameter transforms, no simulation."""
+
+    @staticmethod
+    def bid_ask_widening(base_spread: float, widening_factor: float = 3.0) -> Dict:
+        stressed = base_spread * widening_factor
+        return {"base_spread": base_spread, "stressed_spread": stressed, "slippage_increase": stressed - base_spread}
+
+    @staticmethod
+    def vol_gap_no_spot_move(params, vol_jump: float = 0.05) -> SVJParams:
+        return copy_with(params, v0=params.v0 + 2 * np.sqrt(params.v0) * vol_jump + vol_jump ** 2)      # :201
+
+    @staticmethod
+    def expiry_vol_crush(params, crush_pct: float = 0.30) -> SVJParams:
+        return copy_with(params, theta=max(params.theta * (1 - crush_pct * 0.5), 0.001),              # :214-221
+                            v0=max(params.v0 * (1 - crush_pct), 0.001))
+
+
+class HedgingBacktest:
+    """Mirror of HedgingBacktest (engine/risk.py:228-337).  The premiums of all scenarios are one (cell x path) launch
+    (cell s: seed + s, the reference's default engine flags), the daily walk is one kernel over the scenarios.
+    rng="reference": premiums from the reference's own draws (Sobol front end on the host) and the walk on
+    default_rng(seed) normals -- reproduces the reference's numbers; rng="philox" (default): device draws."""
+
+    def __init__(self, params, seed: int = 42, *, rng=None, precision="fp32", handle=None):
+        self.params = params
+        self.seed = seed
+        self.rng = rng
+        self._kw = dict(rng=rng, precision=precision, handle=handle)
+
+    def run_backtest(self, spot: float, strike: float, T: float, is_call: bool = True, num_days: int = None,
+                     txn_cost_bps: float = 5.0, slippage_bps: float = 2.0, num_scenarios: int = 1000,
+                     num_mc_paths: int = 50_000) -> Dict:
+        if num_days is None:
+            num_days = max(int(T * 252), 1)                                                        # :255-256
+        p = self.params
+        engine = MonteCarloEngine(p, num_paths=num_mc_paths, seed=self.seed, **self._kw)
+        h = engine.handle
+        seeds = [self.seed + s for s in range(num_scenarios)]                                      # :271
+        premiums = np.array([r["price"] for r in engine.price_many(spot, strike, T, is_call, seeds=seeds)])   # :272-273
+        Z = None
+        if engine.rng == "reference":                                                              # :262,292
+            Z = np.random.default_rng(self.seed).standard_normal((num_scenarios, num_days))
+        pnl, cost = h.hedge_walk(p, spot, strike, T, is_call, num_days, num_scenarios, txn_cost_bps + slippage_bps,
+                                 premiums, Z, seed=self.seed)
+        metrics = compute_risk_metrics(pnl, confidence=0.99, handle=h)                             # :319
+        return {"mean_pnl": float(np.mean(pnl)), "std_pnl": float(np.std(pnl)),
+                "pnl_percentiles": {f"{q}%": float(np.percentile(pnl, q)) for q in (1, 5, 25, 50, 75, 95, 99)},
+                "risk_metrics": metrics, "num_scenarios": num_scenarios,
+                "total_txn_cost_avg": float(cost[-1])}      # :336: the reference reports the LAST scenario's total

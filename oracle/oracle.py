@@ -470,6 +470,118 @@ def risk_metrics(returns: np.ndarray, confidence: float = 0.99) -> Dict[str, flo
 
 
 # --------------------------------------------------------------------------------------------
+# a11: the callers of engine/risk.py -- stress ladders (:33-111) and the delta-hedging backtest (:238-337)
+# --------------------------------------------------------------------------------------------
+SPOT_SHOCKS = [-0.08, -0.05, -0.02, 0.02, 0.05, 0.08]     # engine/config.py:134
+VOL_SHOCKS = [-0.05, 0.05]                                # engine/config.py:135
+JUMP_SCENARIO_SIZE = 0.04                                 # engine/config.py:136
+
+
+def vol_shocked_params(p: Params, shock: float) -> Params:
+    """risk.py:61-68."""
+    return Params(kappa=p.kappa, theta=max(p.theta + shock ** 2, 0.001), xi=p.xi, rho=p.rho,
+                  v0=max(p.v0 + 2 * np.sqrt(p.v0) * shock, 0.001), lambda_j=p.lambda_j, mu_j=p.mu_j,
+                  sigma_j=p.sigma_j, r=p.r, q=p.q)
+
+
+class StressOracle:
+    """Restates StressTestEngine (risk.py:23-111).  `engine_kw` are extra MonteCarloOracle arguments (the reference
+    uses the engine defaults: Sobol, antithetic, control variate)."""
+
+    def __init__(self, params, num_paths=200_000, seed=42, **engine_kw):
+        self.p, self.n, self.seed, self.kw = as_params(params), num_paths, seed, engine_kw
+
+    def _engine(self, p=None):
+        return MonteCarloOracle(p or self.p, num_paths=self.n, seed=self.seed, **self.kw)
+
+    def spot_shock_ladder(self, spot, strike, T, is_call=True):
+        eng = self._engine()
+        base = eng.price(spot, strike, T, is_call)["price"]
+        out = []
+        for shock in SPOT_SHOCKS:                                          # :40-49
+            s = spot * (1 + shock)
+            pr = eng.price(s, strike, T, is_call)["price"]
+            out.append({"shock_pct": shock * 100, "spot": s, "price": pr, "pnl": pr - base,
+                        "pnl_pct": (pr - base) / max(base, 1e-6) * 100})
+        return out
+
+    def vol_shock_ladder(self, spot, strike, T, is_call=True):
+        base = self._engine().price(spot, strike, T, is_call)["price"]
+        out = []
+        for shock in VOL_SHOCKS:                                           # :60-77
+            sp = vol_shocked_params(self.p, shock)
+            pr = self._engine(sp).price(spot, strike, T, is_call)["price"]
+            out.append({"vol_shock": shock * 100, "v0": sp.v0, "price": pr, "pnl": pr - base})
+        return out
+
+    def jump_scenario(self, spot, strike, T, is_call=True, gap_size=JUMP_SCENARIO_SIZE):
+        eng = self._engine()
+        base = eng.price(spot, strike, T, is_call)["price"]
+        dn = eng.price(spot * (1 - gap_size), strike, T, is_call)["price"]   # :89-90
+        up = eng.price(spot * (1 + gap_size), strike, T, is_call)["price"]   # :93-94
+        return {"base_price": base, "gap_down_price": dn, "gap_down_pnl": dn - base, "gap_up_price": up,
+                "gap_up_pnl": up - base, "gap_size_pct": gap_size * 100}
+
+    def full_stress_report(self, spot, strike, T, is_call=True):
+        return {"spot_shocks": self.spot_shock_ladder(spot, strike, T, is_call),
+                "vol_shocks": self.vol_shock_ladder(spot, strike, T, is_call),
+                "jump_scenario": self.jump_scenario(spot, strike, T, is_call)}
+
+
+def hedge_walk(p, spot, strike, T, is_call, num_days, txn_cost_bps, slippage_bps, premiums, Z):
+    """The daily delta-hedging walk of HedgingBacktest.run_backtest (risk.py:278-316), vectorised over the
+    scenarios (rows of Z: one standard normal per scenario and day, the order the reference draws them in).
+    Returns (final_pnl[n], total_txn_cost[n])."""
+    from scipy.stats import norm
+    p = as_params(p)
+    Z = np.asarray(Z, dtype=np.float64)
+    n = Z.shape[0]
+    dt = T / num_days                                                      # :258
+    sigma = np.sqrt(p.v0)                                                  # :260
+    S = np.full(n, float(spot))
+    cash = np.array(premiums, dtype=np.float64).copy()                     # :273
+    hedge = np.zeros(n)
+    total_cost = np.zeros(n)
+    t_rem = T
+    for day in range(num_days):
+        if t_rem <= 0:                                                     # :279-280
+            break
+        d1 = (np.log(S / strike) + (p.r - p.q + 0.5 * sigma ** 2) * t_rem) / (sigma * np.sqrt(t_rem))
+        delta = np.exp(-p.q * t_rem) * norm.cdf(d1) if is_call else np.exp(-p.q * t_rem) * (norm.cdf(d1) - 1.0)
+        trade = delta - hedge                                              # :286
+        cost = np.abs(trade) * S * (txn_cost_bps + slippage_bps) / 10000   # :287
+        total_cost += cost
+        cash -= trade * S + cost                                           # :289
+        hedge = delta
+        S = S * np.exp((p.r - p.q - 0.5 * p.v0) * dt + np.sqrt(p.v0 * dt) * Z[:, day])   # :293-294
+        t_rem -= dt                                                        # :308
+    payoff = np.maximum(S - strike, 0) if is_call else np.maximum(strike - S, 0)
+    return cash + hedge * S - payoff, total_cost                           # :316
+
+
+class HedgingOracle:
+    """Restates HedgingBacktest.run_backtest (risk.py:238-337): premium of every scenario from a fresh engine seeded
+    seed + scenario (default engine flags), the walk above on default_rng(seed) normals drawn scenario by scenario."""
+
+    def __init__(self, params, seed=42, **engine_kw):
+        self.p, self.seed, self.kw = as_params(params), seed, engine_kw
+
+    def run_backtest(self, spot, strike, T, is_call=True, num_days=None, txn_cost_bps=5.0, slippage_bps=2.0,
+                     num_scenarios=1000, num_mc_paths=50_000):
+        if num_days is None:
+            num_days = max(int(T * 252), 1)                                # :255-256
+        Z = np.random.default_rng(self.seed).standard_normal((num_scenarios, num_days))   # :262,292 (same stream)
+        prem = [MonteCarloOracle(self.p, num_paths=num_mc_paths, seed=self.seed + s, **self.kw)
+                .price(spot, strike, T, is_call)["price"] for s in range(num_scenarios)]  # :271-273
+        pnl, cost = hedge_walk(self.p, spot, strike, T, is_call, num_days, txn_cost_bps, slippage_bps, prem, Z)
+        pct = {f"{q}%": float(np.percentile(pnl, q)) for q in (1, 5, 25, 50, 75, 95, 99)}
+        return {"mean_pnl": float(np.mean(pnl)), "std_pnl": float(np.std(pnl)), "pnl_percentiles": pct,
+                "risk_metrics": risk_metrics(pnl, 0.99), "num_scenarios": num_scenarios,
+                "total_txn_cost_avg": float(cost[-1]),                    # :336: the LAST scenario's total, not a mean
+                "_pnl": pnl, "_cost": cost}
+
+
+# --------------------------------------------------------------------------------------------
 # Philox4x32-10 (not in the reference; the generator of the CUDA path).  NumPy mirror for KATs and
 # for checking the device's raw words bit for bit.
 # --------------------------------------------------------------------------------------------

@@ -36,6 +36,30 @@ def garr():
     return dict(np.load(os.path.join(GOLDEN, "golden_arrays.npz")))
 
 
+@pytest.fixture(scope="session")
+def risk_golden():
+    """StressTestEngine / HedgingBacktest outputs of the reference (tests/golden/make_risk_callers_golden.py)."""
+    with open(os.path.join(GOLDEN, "risk_callers_golden.json")) as f:
+        return json.load(f)
+
+
+def assert_tree_close(got, want, rel=1e-9, abs_=1e-9, path=""):
+    """Nested dicts / lists of floats, NaN == NaN; keys starting with '_' in `got` are ignored."""
+    import math
+    if isinstance(want, dict):
+        assert set(k for k in got if not k.startswith("_")) == set(want), path
+        for k in want:
+            assert_tree_close(got[k], want[k], rel, abs_, f"{path}.{k}")
+    elif isinstance(want, list):
+        assert len(got) == len(want), path
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert_tree_close(g, w, rel, abs_, f"{path}[{i}]")
+    elif isinstance(want, float) and math.isnan(want):
+        assert math.isnan(got), path
+    else:
+        assert got == pytest.approx(want, rel=rel, abs=abs_), path
+
+
 def unnan(d):
     """golden.json stores NaN as the string 'nan' (strict JSON)."""
     return {k: (float("nan") if v == "nan" else v) for k, v in d.items()}

@@ -57,6 +57,27 @@ class OracleBackedHandle:
             rows.append(row)
         return np.array(rows, dtype=np.float64)
 
+    def price_cells(self, cells, strikes, flags=0, out_dev=None):
+        """Every cell through price_european above (cells: the structured array of _lib.make_cells)."""
+        ks = np.asarray(strikes, dtype=np.float64).reshape(len(cells), -1)
+        out = []
+        for c, k in zip(cells, ks):
+            p = O.Params(**{f: float(c[f]) for f in _lib.PARAM_FIELDS})
+            out.append(self.price_european(p, float(c["S0"]), float(c["T"]), int(c["n_steps"]), int(c["n_paths"]),
+                                           int(c["seed"]), k, bool(c["is_call"]), flags, None, int(c["path_offset"])))
+        return np.array(out)
+
+    def hedge_walk(self, params, S0, strike, T, is_call, n_days, n_scenarios, cost_bps, premiums=None, Z=None, seed=0,
+                   scenario_offset=0):
+        if Z is None:       # stand-in for the device's Philox draws
+            Z = np.random.default_rng(seed + 12345).standard_normal((scenario_offset + n_scenarios, n_days))[scenario_offset:]
+        return O.hedge_walk(params, S0, strike, T, is_call, n_days, cost_bps, 0.0,
+                            premiums if premiums is not None else np.zeros(n_scenarios), Z)
+
+    def risk_metrics(self, pnl, confidence=0.99, n=None, dtype=None):
+        r = O.risk_metrics(np.asarray(pnl, dtype=np.float64), confidence)
+        return np.array([r[k] for k in ("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std")])
+
 
 def test_bs_closed_forms_match_golden(golden):
     b = golden["cases"]["bs"]
@@ -169,9 +190,10 @@ def test_patch_reference_rebinds_import_by_name_sites():
     mods = {}
     for name, attrs in {"monte_carlo": ["_simulate_svj_paths_numba", "MonteCarloEngine", "bs_price", "bs_delta"],
                         "greeks": ["_simulate_svj_paths_numba", "MonteCarloEngine", "GreeksEngine"],
-                        "risk": ["MonteCarloEngine", "compute_risk_metrics"],
+                        "risk": ["MonteCarloEngine", "compute_risk_metrics", "StressTestEngine", "HedgingBacktest",
+                                 "LiquidityStress"],
                         "calibration": ["MonteCarloEngine"],
-                        "app": ["MonteCarloEngine", "GreeksEngine", "StressTestEngine"]}.items():
+                        "app": ["MonteCarloEngine", "GreeksEngine", "StressTestEngine", "HedgingBacktest"]}.items():
         m = types.ModuleType(f"fakeengine.{name}")
         for a in attrs:
             setattr(m, a, object())
@@ -179,15 +201,21 @@ def test_patch_reference_rebinds_import_by_name_sites():
         sys.modules[f"fakeengine.{name}"] = m
     sys.modules["fakeengine"] = pkg
     try:
+        from monte_carlo_option_simulator_b200 import risk as R
+        done = patch_reference("fakeengine", batch_scenarios=False)
+        assert not isinstance(mods["app"].StressTestEngine, type)       # caller classes: left alone on request
+        assert not isinstance(mods["risk"].HedgingBacktest, type)
+        assert len(done) == 12          # (no calibration objectives in this stub module)
         done = patch_reference("fakeengine")
+        assert mods["risk"].StressTestEngine is R.StressTestEngine and mods["app"].HedgingBacktest is R.HedgingBacktest
+        assert mods["risk"].LiquidityStress is R.LiquidityStress
+        assert len(done) == 17
         assert mods["monte_carlo"].MonteCarloEngine is MonteCarloEngine
         assert mods["greeks"]._simulate_svj_paths_numba is MC._simulate_svj_paths_numba
         assert mods["greeks"].GreeksEngine is GreeksEngine
         assert mods["risk"].MonteCarloEngine is MonteCarloEngine
         assert mods["calibration"].MonteCarloEngine is MonteCarloEngine
         assert mods["app"].GreeksEngine is GreeksEngine
-        assert not isinstance(mods["app"].StressTestEngine, type)       # caller class: left alone
-        assert len(done) == 12          # (no calibration objectives in this stub module)
     finally:
         for k in list(sys.modules):
             if k.startswith("fakeengine"):
@@ -291,3 +319,97 @@ def test_batched_calibration_objectives_equal_the_per_strike_loop(golden, monkey
         for k in list(sys.modules):
             if k.startswith("fakecal"):
                 del sys.modules[k]
+
+
+# ---------------------------------------------------------------------------------------------- a11: risk.py callers
+def test_price_many_equals_a_loop_of_price(golden):
+    """price_many builds the cells (params, spot, T -> steps, seed per problem) and the reference's dicts from the sums:
+    same dicts as separate engines' price() calls."""
+    p, p2 = P(golden, "svj_default"), P(golden, "gbm_cfg1")
+    h = OracleBackedHandle()
+    eng = MonteCarloEngine(p, 700, 252, 5, use_sobol=False, handle=h, rng="philox")
+    spots, ks, Ts = [22500.0, 21000.0, 22500.0], [22500.0, 22000.0, 23000.0], [0.25, 0.1, 0.02]
+    got = eng.price_many(spots, ks, Ts, [True, False, True], params=[p, p2, p], seeds=[5, 6, 7])
+    assert h.calls == 3
+    for i, g in enumerate(got):
+        e = MonteCarloEngine([p, p2, p][i], 700, 252, [5, 6, 7][i], use_sobol=False, handle=OracleBackedHandle(), rng="philox")
+        want = e.price(spots[i], ks[i], Ts[i], [True, False, True][i])
+        assert g == pytest.approx(want, rel=1e-12, abs=1e-12)
+    # scalars broadcast, and a mismatch in lengths is an error
+    assert len(eng.price_many(22500.0, [22000.0, 23000.0], 0.25)) == 2
+    with pytest.raises(ValueError):
+        eng.price_many([1.0, 2.0], [1.0, 2.0, 3.0], 0.25)
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_stress_engine_keys_and_formulas(risk_golden, idx):
+    """StressTestEngine on the stand-in handle: same structure and keys as the reference's report, every number equal to
+    the reference's formulas applied to this engine's own price() results."""
+    from monte_carlo_option_simulator_b200.risk import StressTestEngine, SPOT_SHOCKS, VOL_SHOCKS
+    from conftest import assert_tree_close
+    c = risk_golden["stress"][idx]
+    p = O.Params(**risk_golden["params"][c["params"]])
+    h = OracleBackedHandle()
+    st = StressTestEngine(p, num_paths=400, seed=c["seed"], rng="philox", handle=h)
+    rep = st.full_stress_report(c["spot"], c["strike"], c["T"], c["is_call"])
+    assert h.calls == 11                                  # 1 base + 6 spot + 2 vol + 2 gap cells, one price_cells call
+
+    def price(params, spot):
+        return MonteCarloEngine(params, 400, seed=c["seed"], rng="philox", handle=OracleBackedHandle()).price(
+            spot, c["strike"], c["T"], c["is_call"])["price"]
+    base = price(p, c["spot"])
+    want = {"spot_shocks": [], "vol_shocks": [], "jump_scenario": None}
+    for sh in SPOT_SHOCKS:
+        pr = price(p, c["spot"] * (1 + sh))
+        want["spot_shocks"].append({"shock_pct": sh * 100, "spot": c["spot"] * (1 + sh), "price": pr, "pnl": pr - base,
+                                    "pnl_pct": (pr - base) / max(base, 1e-6) * 100})
+    for sh in VOL_SHOCKS:
+        sp = O.vol_shocked_params(p, sh)
+        pr = price(sp, c["spot"])
+        want["vol_shocks"].append({"vol_shock": sh * 100, "v0": sp.v0, "price": pr, "pnl": pr - base})
+    dn, up = price(p, c["spot"] * 0.96), price(p, c["spot"] * 1.04)
+    want["jump_scenario"] = {"base_price": base, "gap_down_price": dn, "gap_down_pnl": dn - base, "gap_up_price": up,
+                             "gap_up_pnl": up - base, "gap_size_pct": 4.0}
+    assert_tree_close(rep, want, rel=1e-12, abs_=1e-10)
+    assert_tree_close(st.spot_shock_ladder(c["spot"], c["strike"], c["T"], c["is_call"]), want["spot_shocks"], 1e-12, 1e-10)
+    assert_tree_close(st.vol_shock_ladder(c["spot"], c["strike"], c["T"], c["is_call"]), want["vol_shocks"], 1e-12, 1e-10)
+    assert_tree_close(st.jump_scenario(c["spot"], c["strike"], c["T"], c["is_call"]), want["jump_scenario"], 1e-12, 1e-10)
+    # same keys as the reference's own report
+    assert set(rep) == set(c["report"]) and set(rep["spot_shocks"][0]) == set(c["report"]["spot_shocks"][0])
+    assert set(rep["vol_shocks"][0]) == set(c["report"]["vol_shocks"][0])
+    assert set(rep["jump_scenario"]) == set(c["report"]["jump_scenario"])
+
+
+def test_liquidity_stress_transforms():
+    from monte_carlo_option_simulator_b200.risk import LiquidityStress
+    p = O.Params(kappa=3.0, theta=0.04, xi=0.5, rho=-0.7, v0=0.04, lambda_j=1.0, mu_j=-0.05, sigma_j=0.1, r=0.065, q=0.012)
+    assert LiquidityStress.bid_ask_widening(2.0) == {"base_spread": 2.0, "stressed_spread": 6.0, "slippage_increase": 4.0}
+    g = LiquidityStress.vol_gap_no_spot_move(p, 0.05)
+    assert g.v0 == pytest.approx(0.04 + 2 * 0.2 * 0.05 + 0.0025) and g.theta == p.theta and g.rho == p.rho
+    c = LiquidityStress.expiry_vol_crush(p, 0.30)
+    assert c.v0 == pytest.approx(0.028) and c.theta == pytest.approx(0.034) and c.kappa == p.kappa
+    assert LiquidityStress.expiry_vol_crush(p, 1.0).v0 == 0.001
+
+
+def test_hedging_backtest_host_logic(risk_golden):
+    """HedgingBacktest on the stand-in handle == the oracle's walk on the same premiums and normals; keys and the
+    'last scenario' quirk of total_txn_cost_avg as in the reference."""
+    from monte_carlo_option_simulator_b200.risk import HedgingBacktest
+    c = risk_golden["hedge"][1]
+    p = O.Params(**risk_golden["params"][c["params"]])
+    h = OracleBackedHandle()
+    bt = HedgingBacktest(p, seed=3, rng="philox", handle=h)
+    got = bt.run_backtest(c["spot"], c["strike"], c["T"], c["is_call"], num_days=c["num_days"], txn_cost_bps=3.0,
+                          slippage_bps=1.0, num_scenarios=15, num_mc_paths=300)
+    prem = [MonteCarloEngine(p, 300, seed=3 + s, rng="philox", handle=OracleBackedHandle()).price(
+        c["spot"], c["strike"], c["T"], c["is_call"])["price"] for s in range(15)]
+    Z = np.random.default_rng(3 + 12345).standard_normal((15, c["num_days"]))
+    pnl, cost = O.hedge_walk(p, c["spot"], c["strike"], c["T"], c["is_call"], c["num_days"], 3.0, 1.0, prem, Z)
+    assert set(got) == set(c["result"])
+    assert got["mean_pnl"] == pytest.approx(pnl.mean(), rel=1e-10) and got["std_pnl"] == pytest.approx(pnl.std(), rel=1e-10)
+    assert got["total_txn_cost_avg"] == pytest.approx(cost[-1], rel=1e-12)
+    assert got["pnl_percentiles"]["5%"] == pytest.approx(np.percentile(pnl, 5), rel=1e-10)
+    assert got["risk_metrics"]["var"] == pytest.approx(O.risk_metrics(pnl)["var"], rel=1e-10)
+    # default day count: max(int(T * 252), 1)
+    got = bt.run_backtest(c["spot"], c["strike"], 0.003, True, num_scenarios=4, num_mc_paths=50)
+    assert got["num_scenarios"] == 4

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import unnan
+from conftest import assert_tree_close, unnan
 from oracle import oracle as O
 
 PNAMES = ["svj_default", "gbm_cfg1", "heston", "jumpy"]
@@ -219,3 +219,20 @@ def test_oracle_equals_reference_on_the_device_draws():
                                    d[f"{name}_ref_S_anti"], rtol=RTOL)
         if name == "jumpy":
             assert (Z[2] < p.lambda_j * (c["T"] / c["steps"])).sum() > 500          # the jumps really fire
+
+
+# ---------------------------------------------------------------------------------------------- a11: risk.py callers
+@pytest.mark.parametrize("idx", [0, 1])
+def test_stress_report_against_the_reference(risk_golden, idx):
+    c = risk_golden["stress"][idx]
+    o = O.StressOracle(O.Params(**risk_golden["params"][c["params"]]), num_paths=c["num_paths"], seed=c["seed"])
+    assert_tree_close(o.full_stress_report(c["spot"], c["strike"], c["T"], c["is_call"]), c["report"], rel=1e-9, abs_=1e-8)
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_hedging_backtest_against_the_reference(risk_golden, idx):
+    c = risk_golden["hedge"][idx]
+    o = O.HedgingOracle(O.Params(**risk_golden["params"][c["params"]]), seed=c["seed"])
+    got = o.run_backtest(c["spot"], c["strike"], c["T"], c["is_call"], c["num_days"], c["txn_cost_bps"], c["slippage_bps"],
+                         c["num_scenarios"], c["num_mc_paths"])
+    assert_tree_close(got, c["result"], rel=1e-9, abs_=1e-7)

@@ -37,4 +37,21 @@ for name, p in (("gbm", SVJParams.gbm(0.3, r=0.065)), ("svj", SVJParams())):
         print(f"{name} {n_cells:5d} cells x {n_paths:8d} paths x {steps:3d}: one launch {best_b:8.3f} ms "
               f"({work / best_b / 1e9:6.3f}e12 path-steps/s, wall {best_w:7.2f} ms)   "
               f"loop of launches {best_l:8.3f} ms", flush=True)
+
+# the two callers end to end (wall clock, Python included)
+from monte_carlo_option_simulator_b200.risk import HedgingBacktest, StressTestEngine  # noqa: E402
+for name, p in (("gbm", SVJParams.gbm(0.3, r=0.065)), ("svj", SVJParams())):
+    st = StressTestEngine(p, num_paths=200_000, seed=42, handle=h)
+    bt = HedgingBacktest(p, seed=42, handle=h)
+    st.full_stress_report(22500.0, 22500.0, 0.25)
+    bt.run_backtest(22500.0, 22500.0, 0.25, num_scenarios=10, num_mc_paths=1000)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        st.full_stress_report(22500.0, 22500.0, 0.25)
+    t_st = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    res = bt.run_backtest(22500.0, 22500.0, 0.25)
+    t_bt = time.perf_counter() - t0
+    print(f"{name}: full_stress_report (11 cells x 200k paths x 63) {t_st * 1e3:.2f} ms;  run_backtest (1000 scenarios x 50k paths "
+          f"x 63 + walk) {t_bt * 1e3:.1f} ms  mean_pnl {res['mean_pnl']:.2f} std {res['std_pnl']:.2f}", flush=True)
 h.close()
