@@ -58,7 +58,7 @@ assert CELL_DTYPE.itemsize == C.sizeof(Cell)
 
 def make_cells(params, S0, T, n_steps, n_paths, seed, path_offset=0, is_call=True) -> np.ndarray:
     """Structured array of b200mc_cell.  Every argument is a scalar or a sequence (broadcast to the longest);
-    `params` is one parameter object (shared by all cells) or a sequence of them."""
+    `params` is one parameter object (shared by all cells), a sequence of them, or a dict field -> scalar / array."""
     cols = dict(S0=np.atleast_1d(np.asarray(S0, dtype=np.float64)), T=np.atleast_1d(np.asarray(T, dtype=np.float64)),
                 n_paths=np.atleast_1d(np.asarray(n_paths, dtype=np.int64)),
                 n_steps=np.atleast_1d(np.asarray(n_steps, dtype=np.int32)),
@@ -67,11 +67,15 @@ def make_cells(params, S0, T, n_steps, n_paths, seed, path_offset=0, is_call=Tru
     sd = np.atleast_1d(np.asarray(seed))
     cols["seed"] = np.array([int(x) & (2 ** 64 - 1) for x in sd.tolist()], dtype=np.uint64) if sd.dtype == object \
         else sd.astype(np.int64).view(np.uint64) if sd.dtype.kind == "i" else sd.astype(np.uint64)
-    plist = list(params) if isinstance(params, (list, tuple)) else [params]
-    n = max([len(plist)] + [c.size for c in cols.values()])
+    if isinstance(params, dict):
+        pcols = {f: np.atleast_1d(np.asarray(params[f], dtype=np.float64)) for f in PARAM_FIELDS}
+    else:
+        plist = list(params) if isinstance(params, (list, tuple)) else [params]
+        pcols = {f: np.array([float(getattr(p, f)) for p in plist]) for f in PARAM_FIELDS}
+    n = max([c.size for c in pcols.values()] + [c.size for c in cols.values()])
     out = np.zeros(n, dtype=CELL_DTYPE)
-    for f in PARAM_FIELDS:
-        out[f] = np.array([float(getattr(p, f)) for p in plist]) if len(plist) > 1 else float(getattr(plist[0], f))
+    for f, c in pcols.items():
+        out[f] = c if c.size > 1 else c[0]
     for k, c in cols.items():
         out[k] = c if c.size > 1 else c[0]
     return out

@@ -317,6 +317,39 @@ class MonteCarloEngine:
             sums = self.comm.allreduce_sum(sums).reshape(m, len(SUMS_FIELDS))
         return [self._result(sums[i], ps[i], sp[i], ks[i], ts[i], calls[i], steps[i]) for i in range(m)]
 
+    def price_population(self, param_cols: Dict[str, np.ndarray], spot: float, strikes, T: float,
+                         is_call: bool = True) -> np.ndarray:
+        """NEW: price_batch for a whole POPULATION of parameter sets in one launch.  param_cols maps
+        the ten SVJParams fields to scalars or arrays [S]; returns the prices [S, n_strikes] -- row s is what
+        MonteCarloEngine(params_s, <this engine's settings>).price_batch(spot, strikes, T, is_call) reports as "price"
+        (paths shared across the strikes of a candidate, same seed for every candidate as in the reference's
+        objectives, engine/calibration.py:78-85).  Philox draws only."""
+        if self.rng != "philox":
+            raise ValueError("price_population draws on the device (rng='philox')")
+        ks = np.ascontiguousarray(np.asarray(strikes, dtype=np.float64).ravel())
+        steps = steps_for(self.num_steps, T)
+        cells = _lib.make_cells(param_cols, float(spot), float(T), steps, int(self.num_paths), self.seed, 0, bool(is_call))
+        S = cells.size
+        sums = self.handle.price_cells(cells, np.tile(ks, (S, 1)), self._flags())             # [S, K, NSUMS]
+        n = sums[:, :, _COL["n"]]
+        sa, sb = sums[:, :, _COL["sum_a"]], sums[:, :, _COL["sum_b"]]
+        r, q, v0 = cells["r"][:, None], cells["q"][:, None], cells["v0"][:, None]
+        discount = np.exp(-r * T)
+        mean = (0.5 * (sa + sb) if self.use_antithetic else sa) / n
+        price = discount * mean
+        if self.use_control_variate:                                            # monte_carlo.py:443-448
+            from scipy.special import ndtr
+            sig = np.sqrt(v0)
+            sT = sig * math.sqrt(T)
+            d1 = (np.log(float(spot) / ks[None, :]) + (r - q + 0.5 * sig ** 2) * T) / sT
+            d2 = d1 - sT
+            if is_call:
+                bs_ref = float(spot) * np.exp(-q * T) * ndtr(d1) - ks[None, :] * discount * ndtr(d2)
+            else:
+                bs_ref = ks[None, :] * discount * ndtr(-d2) - float(spot) * np.exp(-q * T) * ndtr(-d1)
+            price = price - (discount * sa / n - bs_ref)
+        return price
+
     def _spot_cv(self, row, spot, T, discount, p=None) -> Dict[str, float]:
         """NEW keys: regression control variate on S_T, whose mean S0 e^{(r-q)T} is known for every SVJ
         parameter set (the jump drift is compensated, monte_carlo.py:209-210)."""

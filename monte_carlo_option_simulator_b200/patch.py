@@ -54,15 +54,73 @@ def _batched_objectives(calib):
         total = _sum_sq(engine, spot, strikes, T, market_prices, weights, is_call)
         return total + calib.REGULARIZATION["lambda_j"] * lambda_j ** 2
 
+    # ---- population forms (second half): x is [n_params, S], the return value [S] ------------------
+    def _population_sum_sq(cols, spot, strikes, T, market_prices, weights, is_call, num_paths, num_steps):
+        S = max(np.size(v) for v in cols.values())
+        try:
+            engine = calib.MonteCarloEngine(calib.SVJParams(), num_paths=num_paths, num_steps=num_steps, use_sobol=True,
+                                            use_antithetic=True, use_control_variate=True)
+            prices = engine.price_population(cols, spot, np.asarray(strikes, dtype=float), T, is_call)
+        except Exception:
+            return np.full(S, float(len(strikes)))
+        err = (prices - np.asarray(market_prices, dtype=float)[None, :]) ** 2 * np.asarray(weights, dtype=float)[None, :]
+        bad = ~np.isfinite(err)                                  # a strike that "failed" counts 1.0 (:88-89)
+        return np.where(bad, 1.0, err).sum(axis=1)
+
+    def _heston_population(x, spot, strikes, T, market_prices, weights, r, q, is_call, num_paths=100_000, num_steps=100):
+        x = np.asarray(x, dtype=float)
+        if x.ndim == 1:
+            return _heston_objective(x, spot, strikes, T, market_prices, weights, r, q, is_call, num_paths, num_steps)
+        kappa, theta, xi, rho, v0 = x
+        viol = xi ** 2 - 2 * kappa * theta
+        feller_penalty = np.where(2.0 * kappa * theta > xi * xi, 0.0, 10.0 * viol ** 2)
+        cols = dict(kappa=kappa, theta=theta, xi=xi, rho=rho, v0=v0, lambda_j=0.0, mu_j=0.0, sigma_j=0.01, r=r, q=q)
+        total = _population_sum_sq(cols, spot, strikes, T, market_prices, weights, is_call, num_paths, num_steps)
+        return total + calib.REGULARIZATION["xi"] * xi ** 2 + calib.REGULARIZATION["rho"] * rho ** 2 + feller_penalty
+
+    def _svj_population(x_jump, heston_params, spot, strikes, T, market_prices, weights, r, q, is_call,
+                        num_paths=100_000, num_steps=100):
+        x_jump = np.asarray(x_jump, dtype=float)
+        if x_jump.ndim == 1:
+            return _svj_objective(x_jump, heston_params, spot, strikes, T, market_prices, weights, r, q, is_call,
+                                  num_paths, num_steps)
+        lambda_j, mu_j, sigma_j = x_jump
+        kappa, theta, xi, rho, v0 = heston_params
+        cols = dict(kappa=kappa, theta=theta, xi=xi, rho=rho, v0=v0, lambda_j=lambda_j, mu_j=mu_j, sigma_j=sigma_j, r=r, q=q)
+        total = _population_sum_sq(cols, spot, strikes, T, market_prices, weights, is_call, num_paths, num_steps)
+        return total + calib.REGULARIZATION["lambda_j"] * lambda_j ** 2
+
+    _heston_objective.population = _heston_population
+    _svj_objective.population = _svj_population
     return _heston_objective, _svj_objective
 
 
-def patch_reference(package: str = "engine", batch_calibration: bool = True, batch_scenarios: bool = True) -> List[str]:
+def _population_de(scipy_de):
+    """differential_evolution wrapper for engine/calibration.py:195-226: objectives that carry a `.population` form are
+    run with vectorized=True / updating='deferred' (SciPy stays the optimiser; one launch per generation instead of one
+    per candidate).  Everything else goes to SciPy untouched."""
+    def differential_evolution(func, bounds, args=(), **kw):
+        pop = getattr(func, "population", None)
+        if pop is None:
+            return scipy_de(func, bounds, args=args, **kw)
+        kw.pop("workers", None)
+        kw["vectorized"], kw["updating"] = True, "deferred"
+        return scipy_de(pop, bounds, args=args, **kw)
+    differential_evolution._b200mc_inner = scipy_de
+    return differential_evolution
+
+
+def patch_reference(package: str = "engine", batch_calibration: bool = True, batch_scenarios: bool = True,
+                    batch_population: bool = False) -> List[str]:
     """Returns the list of 'module.attribute' names that were rebound.  batch_calibration: also replace the two
     calibration objectives by versions that price all strikes of a candidate in one launch.
     batch_scenarios: also replace StressTestEngine / HedgingBacktest / LiquidityStress (engine/risk.py:23-337) by the
     mirrors that price all scenarios of a report in one launch; with False the reference's own
-    classes keep running, one price() call per scenario, on the rebound MonteCarloEngine."""
+    classes keep running, one price() call per scenario, on the rebound MonteCarloEngine.
+    batch_population (opt-in, needs batch_calibration): also wrap engine.calibration.differential_evolution so that a
+    whole DE generation is ONE launch (SciPy's vectorized=True, updating='deferred').  This changes the optimiser's
+    update rule from SciPy's default 'immediate' to 'deferred', so the calibrated parameters differ from the reference's
+    run (both are noisy optimisers of the same objective); hence not the default."""
     done = []
 
     def rebind(modname, attr, obj):
@@ -95,6 +153,9 @@ def patch_reference(package: str = "engine", batch_calibration: bool = True, bat
         h_obj, s_obj = _batched_objectives(calib)
         rebind(f"{package}.calibration", "_heston_objective", h_obj)
         rebind(f"{package}.calibration", "_svj_objective", s_obj)
+        if batch_population and hasattr(calib, "differential_evolution"):
+            de = getattr(calib.differential_evolution, "_b200mc_inner", calib.differential_evolution)
+            rebind(f"{package}.calibration", "differential_evolution", _population_de(de))
     app = [("MonteCarloEngine", _mc.MonteCarloEngine), ("GreeksEngine", _g.GreeksEngine),
            ("compute_risk_metrics", _r.compute_risk_metrics)]
     if batch_scenarios:

@@ -315,6 +315,31 @@ def test_batched_calibration_objectives_equal_the_per_strike_loop(golden, monkey
         calib._svj_objective(np.array([1.0, -0.05, 0.1]), np.array([3.0, 0.04, 0.5, -0.7, 0.04]), 22500.0, ks, 0.25, mkt, w,
                              0.065, 0.012, True, num_paths=600, num_steps=80)
         assert handle.calls == calls + 1                   # ONE launch for the three strikes
+        # population forms (8f-2, second half): column s of x == the scalar objective at x[:, s]
+        X = np.array([[3.0, 0.04, 0.5, -0.7, 0.04], [1.0, 0.02, 0.6, -0.3, 0.05], [5.0, 0.09, 0.2, -0.1, 0.01]]).T
+        got = calib._heston_objective.population(X, 22500.0, ks, 0.25, mkt, w, 0.065, 0.012, True, 600, 80)
+        want = [calib._heston_objective(X[:, s], 22500.0, ks, 0.25, mkt, w, 0.065, 0.012, True, 600, 80) for s in range(3)]
+        np.testing.assert_allclose(got, want, rtol=1e-10)
+        XJ = np.array([[1.0, -0.05, 0.1], [4.0, 0.02, 0.3]]).T
+        hp = np.array([3.0, 0.04, 0.5, -0.7, 0.04])
+        got = calib._svj_objective.population(XJ, hp, 22500.0, ks, 0.25, mkt, w, 0.065, 0.012, False, 600, 80)
+        want = [calib._svj_objective(XJ[:, s], hp, 22500.0, ks, 0.25, mkt, w, 0.065, 0.012, False, 600, 80) for s in range(2)]
+        np.testing.assert_allclose(got, want, rtol=1e-10)
+        # the DE wrapper: objectives with a population form run vectorised / deferred, anything else goes through
+        seen = {}
+
+        def fake_de(func, bounds, args=(), **kw):
+            seen.update(kw, func=func)
+            return "result"
+        calib.differential_evolution = fake_de
+        done = patch_reference("fakecal", batch_population=True)
+        assert "fakecal.calibration.differential_evolution" in done
+        assert calib.differential_evolution(calib._heston_objective, [(0, 1)] * 5, args=(1,), workers=1, seed=42) == "result"
+        assert seen["vectorized"] is True and seen["updating"] == "deferred" and "workers" not in seen and seen["seed"] == 42
+        assert seen["func"] is calib._heston_objective.population
+        seen.clear()
+        calib.differential_evolution(len, [(0, 1)], workers=1)
+        assert seen["func"] is len and "vectorized" not in seen and seen["workers"] == 1
     finally:
         for k in list(sys.modules):
             if k.startswith("fakecal"):

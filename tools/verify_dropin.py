@@ -96,4 +96,18 @@ from engine.risk import StressTestEngine  # noqa: E402
 t0 = time.time()
 rep = StressTestEngine(svj, num_paths=200_000).full_stress_report(22500.0, 22500.0, 0.08, True)
 print(f"[stress] full_stress_report: {time.time() - t0:.2f} s, sections {list(rep.keys())}")
+
+from engine.risk import HedgingBacktest  # noqa: E402
+t0 = time.time()
+bt = HedgingBacktest(svj).run_backtest(22500.0, 22500.0, 0.08, True)          # defaults: 1000 scenarios x 50k paths
+print(f"[hedge] run_backtest (1000 scenarios x 50k paths): {time.time() - t0:.3f} s, mean_pnl {bt['mean_pnl']:.2f}, "
+      f"std_pnl {bt['std_pnl']:.2f}, VaR99 {bt['risk_metrics']['var']:.2f}")
+
+# opt-in: one launch per DE generation (vectorized / deferred updating)
+patch_reference("engine", batch_population=True)
+t0 = time.time()
+cal2 = engine.calibration.CalibrationEngine().calibrate(22500.0, ks, 0.08, mkt, True, num_paths=20_000)
+print(f"[calibration] population-batched calibrate: {time.time() - t0:.1f} s, "
+      f"stage1 nit={cal2['stage1_result']['nit']} err={cal2['stage1_result']['error']:.4g}, "
+      f"stage2 nit={cal2['stage2_result']['nit']} err={cal2['stage2_result']['error']:.4g}, v0={cal2['params'].v0:.4f}")
 print("DROP-IN OK")
