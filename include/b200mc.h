@@ -199,6 +199,18 @@ int b200mc_hedge_walk(b200mc_handle *h, const b200mc_svj_params *p, double S0, d
                       int32_t n_days, int64_t n_scenarios, double cost_bps, const double *premiums, const double *Z,
                       uint64_t seed, uint64_t scenario_offset, double *final_pnl, double *txn_cost);
 
+/* Black-Scholes implied volatilities of n options in one launch -- the double loop of
+ * extract_iv_surface (engine/surface.py:69-126) and the smile loop of engine/app.py:226-234, whose every iteration is
+ * implied_vol(price, S, K, T, r, q, is_call, lo = 0.001, hi = 5.0) = brentq on bs_call_price / bs_put_price
+ * (engine/surface.py:22-66, xtol 1e-8).  prices, strikes, maturities: [n] float64; is_call: [n] int32 (HOST).
+ * out_iv[n]: the root in [lo, hi] (bracketed Newton, converged to ~1e-13; brentq's answer lies within its xtol of it),
+ * NaN where the reference returns None (price(lo) - p and price(hi) - p of the same sign, or NaN inputs).  Where p
+ * equals price(lo) or price(hi) to fp64 rounding that sign test hangs on the last bit of the normal CDF (SciPy's ndtr
+ * there, CUDA's normcdf here). */
+int b200mc_implied_vol(b200mc_handle *h, int64_t n, const double *prices, const double *strikes,
+                       const double *maturities, const int32_t *is_call, double S, double r, double q,
+                       double lo, double hi, double *out_iv);
+
 /* Terminal values of the fused simulation (deterministic-mode parity of the fused kernels, and the terminal
  * P&L vector for compute_risk_metrics, engine/risk.py:117).  S_T / S_T_anti / v_T are [n_paths] of `dtype`
  * (B200MC_F32 / B200MC_F64); any may be NULL.  on_device != 0: pointers are device memory. */

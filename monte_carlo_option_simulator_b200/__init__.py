@@ -7,7 +7,8 @@ from .monte_carlo import (MonteCarloEngine, bs_delta, bs_price,  # noqa: F401
 from .greeks import GreeksEngine                                # noqa: F401
 from .risk import (HedgingBacktest, LiquidityStress, StressTestEngine,  # noqa: F401
                    compute_risk_metrics)
+from .surface import extract_iv_surface, implied_vol           # noqa: F401
 from .patch import patch_reference                              # noqa: F401
 
 __all__ = ["SVJParams", "MonteCarloEngine", "GreeksEngine", "compute_risk_metrics", "StressTestEngine", "LiquidityStress",
-           "HedgingBacktest", "bs_price", "bs_delta", "patch_reference"]
+           "HedgingBacktest", "implied_vol", "extract_iv_surface", "bs_price", "bs_delta", "patch_reference"]

@@ -118,6 +118,7 @@ _PROTOS = {
     "b200mc_price_cells": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _u32, C.c_int, _vp]),
     "b200mc_hedge_walk": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _dbl, C.c_int, _i32, _i64, _dbl, _vp, _vp,
                                      _u64, _u64, _vp, _vp]),
+    "b200mc_implied_vol": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _dbl, _vp]),
     "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                             _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
@@ -352,6 +353,23 @@ class Handle:
                                                 int(seed) & (2 ** 64 - 1), int(scenario_offset), pnl.ctypes.data,
                                                 cost.ctypes.data))
         return pnl, cost
+
+    def implied_vol(self, prices, S, strikes, maturities, r, q, is_call=True, lo=0.001, hi=5.0) -> np.ndarray:
+        """Black-Scholes implied volatilities (engine/surface.py:48-66) of a whole chain: prices, strikes, maturities and
+        is_call broadcast against each other; returns float64 of the broadcast shape, NaN where the reference gives None."""
+        pr, ks, ts, cl = np.broadcast_arrays(np.asarray(prices, dtype=np.float64), np.asarray(strikes, dtype=np.float64),
+                                             np.asarray(maturities, dtype=np.float64), np.asarray(is_call))
+        shape = pr.shape
+        out = np.empty(shape, dtype=np.float64)
+        if out.size == 0:
+            return out
+        pr, ks, ts = (np.ascontiguousarray(a).ravel() for a in (pr, ks, ts))
+        cl = np.ascontiguousarray(cl.astype(bool).astype(np.int32)).ravel()
+        flat = out.reshape(-1)
+        self._check(self.lib.b200mc_implied_vol(self.h, flat.size, pr.ctypes.data, ks.ctypes.data, ts.ctypes.data,
+                                                 cl.ctypes.data, float(S), float(r), float(q), float(lo), float(hi),
+                                                 flat.ctypes.data))
+        return out
 
     def simulate_terminal(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,
                           want_anti=False, want_v=False, dev_ptrs=None):

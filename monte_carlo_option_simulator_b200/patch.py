@@ -13,6 +13,7 @@ from typing import List
 from . import greeks as _g
 from . import monte_carlo as _mc
 from . import risk as _r
+from . import surface as _s
 
 
 def _batched_objectives(calib):
@@ -156,6 +157,8 @@ def patch_reference(package: str = "engine", batch_calibration: bool = True, bat
         if batch_population and hasattr(calib, "differential_evolution"):
             de = getattr(calib.differential_evolution, "_b200mc_inner", calib.differential_evolution)
             rebind(f"{package}.calibration", "differential_evolution", _population_de(de))
+    for attr in ("implied_vol", "extract_iv_surface"):       # one launch per chain
+        rebind(f"{package}.surface", attr, getattr(_s, attr))
     app = [("MonteCarloEngine", _mc.MonteCarloEngine), ("GreeksEngine", _g.GreeksEngine),
            ("compute_risk_metrics", _r.compute_risk_metrics)]
     if batch_scenarios:

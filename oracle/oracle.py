@@ -582,6 +582,70 @@ class HedgingOracle:
 
 
 # --------------------------------------------------------------------------------------------
+# 8(f)-3: implied volatility, engine/surface.py:22-126.  The root finder itself is SciPy's brentq (scipy.optimize, the
+# reference's requirements.txt pins no version; 1.18.1 in this image) -- called here exactly as the reference calls it.
+# --------------------------------------------------------------------------------------------
+def bs_call_price(S, K, T, r, q, sigma):
+    """surface.py:22-28."""
+    from scipy.stats import norm
+    if T <= 1e-10 or sigma <= 1e-10:
+        return max(S * np.exp(-q * T) - K * np.exp(-r * T), 0.0)
+    d1 = (np.log(S / K) + (r - q + 0.5 * sigma ** 2) * T) / (sigma * np.sqrt(T))
+    d2 = d1 - sigma * np.sqrt(T)
+    return S * np.exp(-q * T) * norm.cdf(d1) - K * np.exp(-r * T) * norm.cdf(d2)
+
+
+def bs_put_price(S, K, T, r, q, sigma):
+    """surface.py:31-37."""
+    from scipy.stats import norm
+    if T <= 1e-10 or sigma <= 1e-10:
+        return max(K * np.exp(-r * T) - S * np.exp(-q * T), 0.0)
+    d1 = (np.log(S / K) + (r - q + 0.5 * sigma ** 2) * T) / (sigma * np.sqrt(T))
+    d2 = d1 - sigma * np.sqrt(T)
+    return K * np.exp(-r * T) * norm.cdf(-d2) - S * np.exp(-q * T) * norm.cdf(-d1)
+
+
+def implied_vol(price, S, K, T, r, q, is_call=True, lo=0.001, hi=5.0):
+    """surface.py:48-66."""
+    from scipy.optimize import brentq
+    pricer = bs_call_price if is_call else bs_put_price
+    try:
+        f = lambda sigma: pricer(S, K, T, r, q, sigma) - price                    # noqa: E731
+        if f(lo) * f(hi) > 0:
+            return None
+        return brentq(f, lo, hi, xtol=1e-8, maxiter=200)
+    except (ValueError, RuntimeError):
+        return None
+
+
+def extract_iv_surface(spot, r, q, strikes, maturities, call_prices, put_prices, bid_ask_spreads=None,
+                       max_spread_pct=0.10):
+    """surface.py:69-126."""
+    n_mat, n_k = call_prices.shape
+    iv_call = np.full((n_mat, n_k), np.nan)
+    iv_put = np.full((n_mat, n_k), np.nan)
+    valid = np.ones((n_mat, n_k), dtype=bool)
+    for i in range(n_mat):
+        for j in range(n_k):
+            if bid_ask_spreads is not None:                                       # :98-103
+                mid = 0.5 * (call_prices[i, j] + put_prices[i, j])
+                if mid > 0 and bid_ask_spreads[i, j] / mid > max_spread_pct:
+                    valid[i, j] = False
+                    continue
+            c = implied_vol(call_prices[i, j], spot, strikes[j], maturities[i], r, q, True)
+            p = implied_vol(put_prices[i, j], spot, strikes[j], maturities[i], r, q, False)
+            if c is not None:
+                iv_call[i, j] = c
+            else:
+                valid[i, j] = False
+            if p is not None:
+                iv_put[i, j] = p
+            else:
+                valid[i, j] = False
+    return {"iv_call": iv_call, "iv_put": iv_put, "valid_mask": valid, "strikes": strikes, "maturities": maturities}
+
+
+# --------------------------------------------------------------------------------------------
 # Philox4x32-10 (not in the reference; the generator of the CUDA path).  NumPy mirror for KATs and
 # for checking the device's raw words bit for bit.
 # --------------------------------------------------------------------------------------------

@@ -43,6 +43,12 @@ def risk_golden():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def iv_golden():
+    """Implied-volatility surface written by the reference's extract_iv_surface (tests/golden/make_iv_golden.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "iv_golden.npz")))
+
+
 def assert_tree_close(got, want, rel=1e-9, abs_=1e-9, path=""):
     """Nested dicts / lists of floats, NaN == NaN; keys starting with '_' in `got` are ignored."""
     import math

@@ -236,3 +236,17 @@ def test_hedging_backtest_against_the_reference(risk_golden, idx):
     got = o.run_backtest(c["spot"], c["strike"], c["T"], c["is_call"], c["num_days"], c["txn_cost_bps"], c["slippage_bps"],
                          c["num_scenarios"], c["num_mc_paths"])
     assert_tree_close(got, c["result"], rel=1e-9, abs_=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------- 8(f)-3: implied vol
+def test_iv_surface_against_the_reference(iv_golden):
+    g = iv_golden
+    for spreads, tag in ((g["spreads"], ""), (None, "_ns")):
+        s = O.extract_iv_surface(float(g["spot"]), float(g["r"]), float(g["q"]), g["strikes"], g["maturities"], g["calls"],
+                                 g["puts"], spreads)
+        np.testing.assert_array_equal(s["valid_mask"], g["valid" + tag])
+        np.testing.assert_allclose(s["iv_call"], g["iv_call" + tag], rtol=0, atol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(s["iv_put"], g["iv_put" + tag], rtol=0, atol=1e-12, equal_nan=True)
+    for price, K, T, call, lo, hi, want in g["scalar"]:
+        got = O.implied_vol(price, float(g["spot"]), K, T, float(g["r"]), float(g["q"]), bool(call), lo, hi)
+        assert (got is None and np.isnan(want)) or got == pytest.approx(want, abs=1e-12)
