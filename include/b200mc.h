@@ -211,6 +211,27 @@ int b200mc_implied_vol(b200mc_handle *h, int64_t n, const double *prices, const 
                        const double *maturities, const int32_t *is_call, double S, double r, double q,
                        double lo, double hi, double *out_iv);
 
+/* ---- a working quasi-Monte Carlo front end (new; the reference's own use_sobol path is degenerate and
+ * stays reproducible on the host) ---------------------------------------------------------------------
+ * Scrambled Sobol points generated on the device, bitwise those of scipy.stats.qmc.Sobol(d, scramble=True, seed): the
+ * caller passes that engine's scrambled direction numbers sv[n_dims][bits] and digital shift[n_dims] (uint32, HOST);
+ * point n = shift ^ XOR over the set bits b of gray(n) of sv[.][b]; u = clip(x 2^-bits, 1e-10, 1 - 1e-10),
+ * z = normcdfinv(u) (engine/monte_carlo.py:80-84).  Dimension layout, s = n_steps: [0, s) Z1 and [s, 2s) Z2 in
+ * Brownian-bridge order (dimension 0 = W_T, then interval midpoints breadth first: a correct bridge), [2s, 3s) jump
+ * sizes and [3s, 4s) jump uniforms in time order; n_dims must cover the blocks the parameters need (s if xi == 0 and
+ * lambda_j == 0, 2s if lambda_j == 0, else 4s).  Paths [path_offset, path_offset + n_paths) of the sequence.
+ * b200mc_qmc_normals: the step normals / uniforms of one block, float64 [n_paths][n_steps] on the HOST (which =
+ * B200MC_Z1 | Z2 | ZJUMP_U | ZJUMP_SIZE), for checks against SciPy.
+ * b200mc_price_european_qmc: those draws, device resident, through the fp64 recurrence of
+ * b200mc_simulate_given_normals_dev, terminal values reduced on the device; flags: ANTITHETIC only; out[n_strikes]
+ * with the price sums of b200mc_sums (Greek fields 0). */
+int b200mc_qmc_normals(b200mc_handle *h, int64_t n_paths, uint64_t path_offset, int32_t n_steps, const uint32_t *sv,
+                       const uint32_t *shift, int32_t n_dims, int32_t bits, int which, double *out);
+int b200mc_price_european_qmc(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T, int32_t n_steps,
+                              int64_t n_paths, uint64_t path_offset, const uint32_t *sv, const uint32_t *shift,
+                              int32_t n_dims, int32_t bits, const double *strikes, int32_t n_strikes, int is_call,
+                              uint32_t flags, b200mc_sums *out);
+
 /* Terminal values of the fused simulation (deterministic-mode parity of the fused kernels, and the terminal
  * P&L vector for compute_risk_metrics, engine/risk.py:117).  S_T / S_T_anti / v_T are [n_paths] of `dtype`
  * (B200MC_F32 / B200MC_F64); any may be NULL.  on_device != 0: pointers are device memory. */

@@ -119,6 +119,9 @@ _PROTOS = {
     "b200mc_hedge_walk": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _dbl, C.c_int, _i32, _i64, _dbl, _vp, _vp,
                                      _u64, _u64, _vp, _vp]),
     "b200mc_implied_vol": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _dbl, _vp]),
+    "b200mc_qmc_normals": (C.c_int, [_vp, _i64, _u64, _i32, _vp, _vp, _i32, _i32, C.c_int, _vp]),
+    "b200mc_price_european_qmc": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _vp, _vp, _i32, _i32,
+                                             _vp, _i32, C.c_int, _u32, _vp]),
     "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                             _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
@@ -173,6 +176,16 @@ def select_stream(params, T: float, n_steps: int, flags: int = 0, bumps: Optiona
     if rc != OK:
         raise B200MCError(rc, (load().b200mc_last_error(None) or b"").decode())
     return int(out.value)
+
+
+def sobol_tables(n_dims: int, seed: int):
+    """(sv, shift, bits) of scipy.stats.qmc.Sobol(d=n_dims, scramble=True, seed=seed): the scrambled direction numbers
+    and the digital shift the device generator needs to reproduce SciPy's points bit for bit."""
+    from scipy.stats.qmc import Sobol
+    eng = Sobol(d=int(n_dims), scramble=True, seed=seed)
+    sv = np.ascontiguousarray(eng._sv, dtype=np.uint32)
+    shift = np.ascontiguousarray(eng._shift, dtype=np.uint32)
+    return sv, shift, int(eng.bits)
 
 
 def to_params(p) -> SvjParams:
@@ -369,6 +382,27 @@ class Handle:
         self._check(self.lib.b200mc_implied_vol(self.h, flat.size, pr.ctypes.data, ks.ctypes.data, ts.ctypes.data,
                                                  cl.ctypes.data, float(S), float(r), float(q), float(lo), float(hi),
                                                  flat.ctypes.data))
+        return out
+
+    # -- quasi-Monte Carlo ------------------------------------------------------------------
+    def qmc_normals(self, sobol, n_paths, n_steps, which, path_offset=0) -> np.ndarray:
+        """Step normals / uniforms of one block of the device Sobol front end, float64 [n_paths, n_steps].
+        sobol = (sv [n_dims, bits] uint32, shift [n_dims] uint32, bits), see sobol_tables()."""
+        sv, shift, bits = sobol
+        out = np.empty((int(n_paths), int(n_steps)), dtype=np.float64)
+        self._check(self.lib.b200mc_qmc_normals(self.h, int(n_paths), int(path_offset), int(n_steps), sv.ctypes.data,
+                                                 shift.ctypes.data, sv.shape[0], int(bits), int(which), out.ctypes.data))
+        return out
+
+    def price_european_qmc(self, params, S0, T, n_steps, n_paths, sobol, strikes, is_call=True, flags=0, path_offset=0):
+        sv, shift, bits = sobol
+        strikes = np.ascontiguousarray(np.atleast_1d(strikes), dtype=np.float64)
+        out = np.empty((strikes.size, NSUMS), dtype=np.float64)
+        sp = to_params(params)
+        self._check(self.lib.b200mc_price_european_qmc(self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths),
+                                                        int(path_offset), sv.ctypes.data, shift.ctypes.data, sv.shape[0],
+                                                        int(bits), strikes.ctypes.data, strikes.size, int(bool(is_call)),
+                                                        int(flags), out.ctypes.data))
         return out
 
     def simulate_terminal(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,

@@ -182,7 +182,9 @@ def _default_rng() -> str:
 class MonteCarloEngine:
     """Mirror of the reference's MonteCarloEngine (monte_carlo.py:249-471).
 
-    Extra keyword-only arguments (not in the reference): ``rng`` ("philox" | "reference"), ``precision``
+    Extra keyword-only arguments (not in the reference): ``rng`` ("philox" | "reference" | "sobol": a WORKING
+    quasi-Monte Carlo front end -- SciPy's scrambled Sobol points generated on the device and a correct Brownian bridge,
+    SURVEY.md 8f-4; the reference's own degenerate use_sobol path is what rng="reference" reproduces), ``precision``
     ("fp32" | "fp64": arithmetic of the path state in the fused kernels), ``handle`` (a ``_lib.Handle``),
     ``comm`` (a ``dist.Comm``: paths are sharded over its ranks and the sums all-reduced).
     """
@@ -199,8 +201,8 @@ class MonteCarloEngine:
         self.use_antithetic = use_antithetic
         self.use_control_variate = use_control_variate
         self.rng = rng or _default_rng()
-        if self.rng not in ("philox", "reference"):
-            raise ValueError("rng must be 'philox' or 'reference'")
+        if self.rng not in ("philox", "reference", "sobol"):
+            raise ValueError("rng must be 'philox', 'reference' or 'sobol'")
         if precision not in ("fp32", "fp64"):
             raise ValueError("precision must be 'fp32' or 'fp64'")
         self.precision = precision
@@ -225,9 +227,33 @@ class MonteCarloEngine:
     def _flags(self) -> int:
         return (ANTITHETIC if self.use_antithetic else 0) | (FP64 if self.precision == "fp64" else 0)
 
+    def _sobol(self, steps: int, T: float):
+        """Scrambled direction numbers of SciPy's Sobol engine for the dimensions this run needs (cached)."""
+        p = self.params
+        nb = 4 if p.lambda_j * (T / steps) > 0.0 else (2 if p.xi != 0.0 else 1)
+        key = (nb * steps, self.seed)
+        cache = getattr(self, "_sobol_cache", None)
+        if cache is None or cache[0] != key:
+            self._sobol_cache = cache = (key, _lib.sobol_tables(nb * steps, self.seed))
+        return cache[1]
+
     def _sums(self, spot, strikes, T, is_call, steps, flags=None, bumps=None) -> np.ndarray:
         flags = self._flags() if flags is None else flags
         n = int(self.num_paths)
+        if self.rng == "sobol":
+            if bumps is not None or (flags & _lib.GREEKS):
+                raise ValueError("rng='sobol' has no Greek sums")
+            lo, hi = 0, n
+            world = self.comm.world if self.comm is not None else 1
+            if world > 1:
+                from .dist import shard_range
+                lo, hi = shard_range(n, self.comm.rank, world)
+            ks = np.atleast_1d(np.asarray(strikes, dtype=np.float64))
+            rows = np.zeros((ks.size, len(SUMS_FIELDS)))
+            if hi > lo:
+                rows = self.handle.price_european_qmc(self.params, float(spot), float(T), steps, hi - lo, self._sobol(steps, T),
+                                                      ks, is_call, flags & ANTITHETIC, path_offset=lo)
+            return self.comm.allreduce_sum(rows).reshape(ks.size, -1) if world > 1 else rows
         if self.comm is not None and self.comm.world > 1:
             from .dist import sharded_sums
             return sharded_sums(self.handle, self.comm, self.params, float(spot), float(T), steps, n, self.seed,
@@ -295,9 +321,9 @@ class MonteCarloEngine:
         if any(len(c) != m for c in cols):
             raise ValueError("price_many: sequences must have a common length")
         sp, ks, ts, calls, ps, sds = cols
-        if self.rng == "reference":
+        if self.rng != "philox":
             return [MonteCarloEngine(ps[i], self.num_paths, self.num_steps, sds[i], self.use_sobol, self.use_antithetic,
-                                     self.use_control_variate, rng="reference", precision=self.precision,
+                                     self.use_control_variate, rng=self.rng, precision=self.precision,
                                      handle=self._handle, comm=self.comm).price(sp[i], ks[i], ts[i], calls[i])
                     for i in range(m)]
         steps = [steps_for(self.num_steps, float(T)) for T in ts]
@@ -407,8 +433,8 @@ class MonteCarloEngine:
         Philox counter ranges: path_offset = cell * num_paths), one launch per cell; with a communicator the CELLS are
         dealt round-robin to the ranks and no path-level collective is needed (only the final gather of the sums).
         All launches are queued on the stream before one synchronisation and one device->host copy."""
-        if self.rng == "reference":
-            rows = [self._price_batch_reference(spot, strikes, float(T), is_call) for T in maturities]
+        if self.rng != "philox":
+            rows = [self.price_batch(spot, strikes, float(T), is_call) for T in maturities]
             steps = [steps_for(self.num_steps, float(T)) for T in maturities]
         else:
             from ._lib import NSUMS

@@ -646,6 +646,54 @@ def extract_iv_surface(spot, r, q, strikes, maturities, call_prices, put_prices,
 
 
 # --------------------------------------------------------------------------------------------
+# 8(f)-4: the WORKING quasi-Monte Carlo front end of the CUDA path (not in the reference, whose bridge is degenerate --
+# see bb_reorder above).  Sobol points are SciPy's own; the bridge is the textbook construction.
+# --------------------------------------------------------------------------------------------
+def qmc_bridge_nodes(n: int):
+    """[(t, l, r, wl, wr, sd)] in construction order: the endpoint, then interval midpoints breadth first; unit time
+    steps, W[0] = 0.  W[t] = wl W[l] + wr W[r] + sd z_k."""
+    nodes = [(n, 0, 0, 0.0, 0.0, math.sqrt(n))]
+    cur = [(0, n)]
+    while cur:
+        nxt = []
+        for l, r in cur:
+            if r - l <= 1:
+                continue
+            m = (l + r) // 2
+            nodes.append((m, l, r, (r - m) / (r - l), (m - l) / (r - l), math.sqrt((m - l) * (r - m) / (r - l))))
+            nxt += [(l, m), (m, r)]
+        cur = nxt
+    return nodes
+
+
+def qmc_bridge(z: np.ndarray) -> np.ndarray:
+    """z [n_paths, steps] in bridge order -> unit-variance step normals [n_paths, steps]."""
+    n = z.shape[1]
+    W = np.zeros((z.shape[0], n + 1))
+    for k, (t, l, r, wl, wr, sd) in enumerate(qmc_bridge_nodes(n)):
+        W[:, t] = wl * W[:, l] + wr * W[:, r] + sd * z[:, k]
+    return np.diff(W, axis=1)
+
+
+def qmc_draws(seed: int, n_paths: int, steps: int, n_blocks: int, path_offset: int = 0):
+    """(Z1, Z2, Z_jump, Z_jump_size) of the device front end: scrambled Sobol (SciPy), clip, norm.ppf, blocks
+    [Z1 bridged][Z2 bridged][jump sizes][jump uniforms]; blocks beyond n_blocks come back as neutral arrays."""
+    from scipy.stats import norm
+    from scipy.stats.qmc import Sobol
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)          # "balance properties require n to be a power of 2"
+        pts = Sobol(d=n_blocks * steps, scramble=True, seed=seed).random(path_offset + n_paths)[path_offset:]
+    u = np.clip(pts, 1e-10, 1 - 1e-10)
+    blk = lambda b: u[:, b * steps:(b + 1) * steps]                               # noqa: E731
+    Z1 = qmc_bridge(norm.ppf(blk(0)))
+    Z2 = qmc_bridge(norm.ppf(blk(1))) if n_blocks >= 2 else np.zeros_like(Z1)
+    Zjs = norm.ppf(blk(2)) if n_blocks >= 4 else np.zeros_like(Z1)
+    Zj = blk(3).copy() if n_blocks >= 4 else np.ones_like(Z1)
+    return Z1, Z2, Zj, Zjs
+
+
+# --------------------------------------------------------------------------------------------
 # Philox4x32-10 (not in the reference; the generator of the CUDA path).  NumPy mirror for KATs and
 # for checking the device's raw words bit for bit.
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,114 @@
+"""GPU tests of the working quasi-Monte Carlo front end: device Sobol points bitwise SciPy's, the
+correct Brownian bridge, the sums against the oracle recurrence on the same draws, and the point of it all -- an error
+far below plain Monte Carlo's at equal path counts."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from monte_carlo_option_simulator_b200 import _lib
+    return _lib
+
+
+@pytest.fixture(scope="module")
+def H(L):
+    h = L.Handle(0)
+    yield h
+    h.close()
+
+
+GBM = O.Params(kappa=0.0, theta=0.09, xi=0.0, rho=0.0, v0=0.09, lambda_j=0.0, mu_j=0.0, sigma_j=0.01, r=0.065, q=0.0)
+HES = O.Params(kappa=3.0, theta=0.04, xi=0.5, rho=-0.7, v0=0.04, lambda_j=0.0, mu_j=0.0, sigma_j=0.01, r=0.065, q=0.012)
+SVJ = O.Params(kappa=3.0, theta=0.04, xi=0.5, rho=-0.7, v0=0.04, lambda_j=2.0, mu_j=-0.05, sigma_j=0.10, r=0.065, q=0.012)
+
+
+@pytest.mark.parametrize("steps,n,off", [(1, 5, 0), (7, 100, 3), (63, 257, 0), (250, 64, 1000), (64, 1000, 12345)])
+def test_device_draws_equal_scipy_plus_textbook_bridge(H, L, steps, n, off):
+    tables = L.sobol_tables(4 * steps, 11)
+    Z1, Z2, Zj, Zjs = O.qmc_draws(11, n, steps, 4, path_offset=off)
+    for which, want in ((L.Z1, Z1), (L.Z2, Z2), (L.ZJUMP_U, Zj), (L.ZJUMP_SIZE, Zjs)):
+        got = H.qmc_normals(tables, n, steps, which, path_offset=off)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    # the uniforms ARE SciPy's points (bitwise, away from the clip)
+    import warnings
+    from scipy.stats.qmc import Sobol
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        pts = Sobol(d=4 * steps, scramble=True, seed=11).random(off + n)[off:, 3 * steps:]
+    np.testing.assert_array_equal(H.qmc_normals(tables, n, steps, L.ZJUMP_U, path_offset=off), np.clip(pts, 1e-10, 1 - 1e-10))
+
+
+def test_bridge_is_not_degenerate(H, L):
+    """W_T = sum of the step normals has variance n_steps (the reference's bridge gives exactly 0), and it
+    is carried by dimension 0 alone."""
+    steps, n = 63, 4096
+    Z1 = H.qmc_normals(L.sobol_tables(steps, 42), n, steps, L.Z1)
+    wT = Z1.sum(axis=1)
+    assert wT.var() == pytest.approx(steps, rel=5e-3) and abs(wT.mean()) < 0.02
+    assert np.abs(Z1.var(axis=0) - 1).max() < 0.05
+
+
+@pytest.mark.parametrize("p,name", [(GBM, "gbm"), (HES, "heston"), (SVJ, "svj")])
+@pytest.mark.parametrize("anti", [False, True])
+def test_sums_vs_oracle_on_the_same_draws(H, L, p, name, anti):
+    steps, n, off, T, S0 = 40, 777, 5, 0.25, 22500.0
+    nb = 4 if p.lambda_j > 0 else (2 if p.xi != 0 else 1)
+    tables = L.sobol_tables(nb * steps, 7)
+    ks = [21000.0, 22500.0, 24000.0]
+    got = H.price_european_qmc(p, S0, T, steps, n, tables, ks, False, L.ANTITHETIC if anti else 0, path_offset=off)
+    Z1, Z2, Zj, Zjs = O.qmc_draws(7, n, steps, nb, path_offset=off)
+    S = O._sim(p, S0, T, Z1, Z2, Zj, Zjs, steps)[0]
+    A = O._sim(p, S0, T, -Z1, -Z2, Zj, -Zjs, steps)[0] if anti else None
+    for K, row in zip(ks, got):
+        a = np.maximum(K - S, 0.0)
+        b = np.maximum(K - A, 0.0) if anti else np.zeros_like(a)
+        s_avg = 0.5 * (S + A) if anti else S
+        want = [n, a.sum(), b.sum(), (a * a).sum(), (b * b).sum(), (a * b).sum(), s_avg.sum(), (s_avg ** 2).sum(),
+                ((0.5 * (a + b) if anti else a) * s_avg).sum()]
+        np.testing.assert_allclose(row[:9], want, rtol=1e-9, atol=1e-6)
+        assert not row[9:].any()
+
+
+def test_engine_sobol_mode_beats_plain_monte_carlo(H, L):
+    """GBM call, 16384 paths x 64 steps: the QMC error against Black-Scholes is far below the Monte Carlo standard error
+    at the same path count; chunked and sharded ranges add up; errors are reported."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    p = SVJParams.gbm(0.3, r=0.065)
+    bs = O.bs_price(2500.0, 2500.0, 1.0, 0.065, 0.0, 0.3, True)
+    errs = []
+    for seed in (1, 2, 3):
+        q = MonteCarloEngine(p, 16384, 64, seed, use_antithetic=False, use_control_variate=False, rng="sobol", handle=H)
+        errs.append(abs(q.price(2500.0, 2500.0, 1.0)["price"] - bs))
+    mc = MonteCarloEngine(p, 16384, 64, 1, use_antithetic=False, use_control_variate=False, handle=H).price(2500.0, 2500.0, 1.0)
+    assert max(errs) < 0.1 * mc["std_error"], (errs, mc["std_error"])
+    # price_batch / price_grid run through the same front end
+    q = MonteCarloEngine(p, 8192, 64, 5, rng="sobol", handle=H)
+    rows = q.price_batch(2500.0, [2300.0, 2500.0, 2700.0], 0.5)
+    for r_ in rows:
+        assert r_["price"] == pytest.approx(O.bs_price(2500.0, r_["strike"], 0.5, 0.065, 0.0, 0.3, True), rel=2e-3)
+    # path ranges add (the multi-GPU sharding rule)
+    tables = L.sobol_tables(64, 5)
+    whole = H.price_european_qmc(p, 2500.0, 1.0, 64, 5000, tables, [2500.0])
+    a = H.price_european_qmc(p, 2500.0, 1.0, 64, 2000, tables, [2500.0])
+    b = H.price_european_qmc(p, 2500.0, 1.0, 64, 3000, tables, [2500.0], path_offset=2000)
+    np.testing.assert_allclose(a + b, whole, rtol=1e-12)
+    with pytest.raises(L.B200MCError):
+        H.price_european_qmc(p, 2500.0, 1.0, 64, 100, L.sobol_tables(32, 5), [2500.0])        # too few dimensions
+    with pytest.raises(L.B200MCError, match="Greek"):
+        H.price_european_qmc(p, 2500.0, 1.0, 64, 100, tables, [2500.0], flags=L.GREEKS)
+    with pytest.raises(L.B200MCError):
+        H.price_european_qmc(p, 2500.0, 1.0, 64, 100, tables, [2500.0], path_offset=2 ** 30)  # beyond the sequence
+
+
+def test_heston_qmc_within_mc_error_of_plain_mc(H, L):
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine
+    mc = MonteCarloEngine(HES, 4_000_000, 63, 3, use_control_variate=False, handle=H).price(22500.0, 22500.0, 0.25)
+    q = MonteCarloEngine(HES, 65536, 63, 3, use_control_variate=False, rng="sobol", handle=H).price(22500.0, 22500.0, 0.25)
+    assert abs(q["price"] - mc["price"]) < 4 * mc["std_error"] + 0.002 * mc["price"]

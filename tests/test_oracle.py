@@ -1,6 +1,7 @@
 """CPU: pin the oracle (oracle/) against fixtures produced by running the reference itself."""
 import ctypes
 import hashlib
+import math
 
 import numpy as np
 import pytest
@@ -250,3 +251,22 @@ def test_iv_surface_against_the_reference(iv_golden):
     for price, K, T, call, lo, hi, want in g["scalar"]:
         got = O.implied_vol(price, float(g["spot"]), K, T, float(g["r"]), float(g["q"]), bool(call), lo, hi)
         assert (got is None and np.isnan(want)) or got == pytest.approx(want, abs=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- 8(f)-4: working QMC front end
+@pytest.mark.parametrize("n", [1, 2, 7, 16, 63, 250])
+def test_qmc_bridge_is_an_orthogonal_map(n):
+    """Independent N(0,1) draws in bridge order -> independent N(0,1) step normals: the linear map is orthogonal, and
+    its first column (dimension 0) carries the whole of W_T.  (The reference's own bridge fails this: bb_reorder above.)"""
+    B = O.qmc_bridge(np.eye(n))                    # row k = image of unit draw k
+    np.testing.assert_allclose(B @ B.T, np.eye(n), atol=1e-12)
+    np.testing.assert_allclose(B.sum(axis=1), [math.sqrt(n)] + [0.0] * (n - 1), atol=1e-12)
+    assert sorted(t for t, *_ in O.qmc_bridge_nodes(n)) == list(range(1, n + 1))
+
+
+def test_qmc_draws_blocks():
+    Z1, Z2, Zj, Zjs = O.qmc_draws(3, 64, 10, 4)
+    assert Z1.shape == Z2.shape == Zj.shape == Zjs.shape == (64, 10)
+    assert 0 < Zj.min() and Zj.max() < 1
+    Z1b, Z2b, Zjb, Zjsb = O.qmc_draws(3, 64, 10, 1)
+    assert not Z2b.any() and (Zjb == 1).all() and not Zjsb.any()
