@@ -226,6 +226,7 @@ static int launch_cells(b200mc_handle *h, const b200mc_cell *cells, int32_t n_ce
     std::vector<int> mode((size_t)n_cells);
     std::vector<double> tabs;
     int64_t max_paths[4] = {0, 0, 0, 0};
+    int32_t max_steps[4] = {0, 0, 0, 0};
     int wld_max = 0, count[4] = {0, 0, 0, 0};
     Prep pr;
     for (int32_t i = 0; i < n_cells; ++i) {
@@ -249,6 +250,7 @@ static int launch_cells(b200mc_handle *h, const b200mc_cell *cells, int32_t n_ce
         mode[(size_t)i] = pr.mode;
         count[pr.mode] += 1;
         max_paths[pr.mode] = std::max<int64_t>(max_paths[pr.mode], cl.n_paths);
+        max_steps[pr.mode] = std::max(max_steps[pr.mode], cl.n_steps);
     }
     std::vector<int32_t> order;
     order.reserve((size_t)n_cells);
@@ -302,11 +304,13 @@ static int launch_cells(b200mc_handle *h, const b200mc_cell *cells, int32_t n_ce
             h->occ_smem[slot] = smem;
             h->occ_val[slot] = occ;
         }
-        // CTAs per cell: enough CTAs for ~4 waves of the resident capacity (tail < 25 % of a wave's worth of one CTA's
-        // work), never more than the cell's 256-path batches
+        // CTAs per cell: a CTA should carry ~2^18 path-steps (~90 us of GBM work: the launch then ends within a few
+        // per cent of its ideal time whatever the mix of cell sizes) and the group should fill ~4 waves of resident
+        // CTAs; never more CTAs than the cell has 256-path batches.  (A CTA costs ~2 us of prologue and fold.)
         const int64_t need = (max_paths[md] + CL_THREADS - 1) / CL_THREADS;
-        const int64_t want = ((int64_t)4 * h->sm_count * occ + g[md].slots - 1) / g[md].slots;
-        int64_t cpc = std::min(need, std::max<int64_t>(want, 1));
+        const int64_t by_work = (max_paths[md] * (int64_t)max_steps[md] + (1 << 18) - 1) >> 18;
+        const int64_t by_fill = ((int64_t)4 * h->sm_count * occ + g[md].slots - 1) / g[md].slots;
+        int64_t cpc = std::min(need, std::max<int64_t>(std::max(by_work, by_fill), 1));
         while ((int64_t)g[md].slots * cpc > 0x7fffffff / 2) cpc = (cpc + 1) / 2;
         g[md].cpc = (int)cpc;
         g[md].poff = ptotal;

@@ -26,7 +26,7 @@ extern "C" int b200mc_simulate_given_normals_dev(b200mc_handle *h, const b200mc_
 
 namespace b200mc {
 
-constexpr int QMC_PT = 32;          // paths per CTA tile
+constexpr int QMC_PT_MAX = 32;      // paths per CTA tile: 32, 16 or 8 (the largest whose tile leaves >= 4 CTAs per SM)
 constexpr int QMC_THREADS = 256;
 
 struct BridgeNode {                 // node k of the construction: W[t] = wl W[l] + wr W[r] + sd z_k
@@ -62,7 +62,7 @@ static std::vector<BridgeNode> bridge_table(int n)
 struct QmcArgs {
     uint64_t path0;
     int64_t n_paths;
-    int32_t n_steps, bits, pitch, n_levels;
+    int32_t n_steps, bits, pitch, n_levels, pt, pad_;
     double sign;                    // +1, or -1 for the antithetic pass (normals negated, uniforms kept)
     double scale;                   // 2^-bits
 };
@@ -83,16 +83,16 @@ k_qmc_block(const __grid_constant__ QmcArgs a, int which, const uint32_t *__rest
             const BridgeNode *__restrict__ nodes, const int32_t *__restrict__ level_start, double *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *zb = reinterpret_cast<double *>(smem_raw);              // [QMC_PT][pitch]  draws, dimension-major per path
-    double *W = zb + (size_t)QMC_PT * a.pitch;                      // [QMC_PT][pitch]  bridge values (which == 0)
+    double *zb = reinterpret_cast<double *>(smem_raw);              // [pt][pitch]  draws, dimension-major per path
     const int tid = threadIdx.x;
-    const int s = a.n_steps;
-    for (int64_t tile = blockIdx.x; tile * QMC_PT < a.n_paths; tile += gridDim.x) {
-        const int64_t base = tile * QMC_PT;
-        const int np = (int)min((int64_t)QMC_PT, a.n_paths - base);
+    const int s = a.n_steps, PT = a.pt;
+    double *W = zb + (size_t)PT * a.pitch;                          // [pt][pitch]  bridge values (which == 0)
+    for (int64_t tile = blockIdx.x; tile * PT < a.n_paths; tile += gridDim.x) {
+        const int64_t base = tile * PT;
+        const int np = (int)min((int64_t)PT, a.n_paths - base);
         // ---- draws: item = (dimension j, path p), p fastest so that a warp shares sv[j][.] ------------------------
-        for (int it = tid; it < s * QMC_PT; it += QMC_THREADS) {
-            const int j = it / QMC_PT, p = it % QMC_PT;
+        for (int it = tid; it < s * PT; it += QMC_THREADS) {
+            const int j = it / PT, p = it % PT;
             if (p < np) {
                 const uint32_t x = sobol_point(sv + (size_t)j * a.bits, shift[j], a.bits, a.path0 + (uint64_t)(base + p));
                 double u = (double)x * a.scale;
@@ -105,8 +105,8 @@ k_qmc_block(const __grid_constant__ QmcArgs a, int which, const uint32_t *__rest
             // ---- bridge, level by level: item = (node of the level, path) ---------------------------------------
             for (int lv = 0; lv < a.n_levels; ++lv) {
                 const int k0 = level_start[lv], k1 = level_start[lv + 1];
-                for (int it = tid; it < (k1 - k0) * QMC_PT; it += QMC_THREADS) {
-                    const int k = k0 + it / QMC_PT, p = it % QMC_PT;
+                for (int it = tid; it < (k1 - k0) * PT; it += QMC_THREADS) {
+                    const int k = k0 + it / PT, p = it % PT;
                     if (p < np) {
                         const BridgeNode nd = nodes[k];
                         double *w = W + (size_t)p * a.pitch;
@@ -166,7 +166,7 @@ static int upload(b200mc_handle *h, void *dst, const void *src, size_t bytes)
 }
 
 struct QmcPlan {
-    int n_steps, bits, pitch, n_levels, n_blocks;      // n_blocks: 1 (Z1), 2 (+Z2) or 4 (+ jump sizes and uniforms)
+    int n_steps, bits, pitch, n_levels, n_blocks, pt;      // n_blocks: 1 (Z1), 2 (+Z2) or 4 (+ jump sizes and uniforms)
     size_t smem;
     uint32_t *d_sv, *d_shift;
     BridgeNode *d_nodes;
@@ -182,7 +182,9 @@ static int qmc_prepare(b200mc_handle *h, int32_t n_steps, const uint32_t *sv, co
     if (n_dims < n_blocks * n_steps) return fail(h, B200MC_EINVAL, "the point set has fewer dimensions than the run needs");
     pl.n_steps = n_steps; pl.bits = bits; pl.n_blocks = n_blocks;
     pl.pitch = (n_steps + 1) | 1;                       // odd pitch (in doubles): conflict-free with lanes over paths
-    pl.smem = (size_t)2 * QMC_PT * pl.pitch * sizeof(double);
+    pl.pt = QMC_PT_MAX;                                 // 128 KB tiles (1 CTA per SM) were latency bound: 0.62 ms per 64k x 250
+    while (pl.pt > 8 && (size_t)2 * pl.pt * pl.pitch * sizeof(double) > 56 * 1024) pl.pt >>= 1;
+    pl.smem = (size_t)2 * pl.pt * pl.pitch * sizeof(double);
     if (pl.smem > (size_t)h->smem_optin - 1024) return fail(h, B200MC_EINVAL, "too many steps for the bridge tile");
     std::vector<BridgeNode> nodes = bridge_table(n_steps);
     std::vector<int32_t> levels;
@@ -216,11 +218,12 @@ static int qmc_block(b200mc_handle *h, const QmcPlan &pl, int b, uint64_t path0,
 {
     QmcArgs a;
     a.path0 = path0; a.n_paths = n; a.n_steps = pl.n_steps; a.bits = pl.bits; a.pitch = pl.pitch; a.n_levels = pl.n_levels;
+    a.pt = pl.pt; a.pad_ = 0;
     a.sign = sign;
     a.scale = ldexp(1.0, -pl.bits);
     const int which = b <= 1 ? 0 : (b == 2 ? 1 : 2);
-    const int64_t tiles = (n + QMC_PT - 1) / QMC_PT;
-    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)h->sm_count * 8);
+    const int64_t tiles = (n + pl.pt - 1) / pl.pt;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)h->sm_count * 16);
     k_qmc_block<<<grid, QMC_THREADS, pl.smem, h->stream>>>(a, which, pl.d_sv + (size_t)b * pl.n_steps * pl.bits,
                                                            pl.d_shift + (size_t)b * pl.n_steps, pl.d_nodes, pl.d_levels, out);
     B200MC_CUDA(h, cudaGetLastError());
@@ -277,7 +280,7 @@ extern "C" int b200mc_price_european_qmc(b200mc_handle *h, const b200mc_svj_para
     const int nb = blocks_needed(p, T, n_steps);
 
     // chunks of paths so that the step normals stay below ~2 GiB per block
-    int64_t chunk = std::max<int64_t>(QMC_PT, ((int64_t)1 << 28) / n_steps);
+    int64_t chunk = std::max<int64_t>(QMC_PT_MAX, ((int64_t)1 << 28) / n_steps);
     chunk = std::min(chunk, n_paths);
     const size_t zbytes = (size_t)chunk * n_steps * 8;
     const int grid_r = (int)std::min<int64_t>((chunk + 255) / 256, (int64_t)h->sm_count * 4);

@@ -38,6 +38,22 @@ for name, p in (("gbm", SVJParams.gbm(0.3, r=0.065)), ("svj", SVJParams())):
               f"({work / best_b / 1e9:6.3f}e12 path-steps/s, wall {best_w:7.2f} ms)   "
               f"loop of launches {best_l:8.3f} ms", flush=True)
 
+# BASELINE cfg3, benchmark reading (64 strikes x 16 expiries, 1M paths per cell, own draws per cell) as ONE launch
+p = SVJParams.gbm(0.3, r=0.065)
+Ts = np.repeat(np.arange(1, 17) / 8.0, 64)
+steps = np.maximum((250 * Ts).astype(int), 10)
+order = np.argsort(-steps, kind="stable")                     # longest cells first
+cells = _lib.make_cells(p, 2500.0, Ts, steps, 1_000_000, 42, np.arange(1024) * 1_000_000)[order]
+ks = np.tile(np.linspace(0.7, 1.3, 64) * 2500.0, 16)[order]
+out = h.malloc(1024 * 17 * 8)
+best = 1e9
+for r in range(3):
+    h.timer_begin()
+    h.price_cells(cells, ks, _lib.ANTITHETIC, out_dev=out)
+    best = min(best, h.timer_end())
+h.free(out)
+print(f"cfg3 independent cells as one launch: {best:.2f} ms = {float(steps.sum()) * 1e6 / best / 1e9:.3f}e12 path-steps/s", flush=True)
+
 # the two callers end to end (wall clock, Python included)
 from monte_carlo_option_simulator_b200.risk import HedgingBacktest, StressTestEngine  # noqa: E402
 for name, p in (("gbm", SVJParams.gbm(0.3, r=0.065)), ("svj", SVJParams())):
