@@ -40,7 +40,11 @@ def _worker(rank, world, port, q):
         x = np.random.default_rng(3).standard_t(3, size=20_001) * 0.01
         lo, hi = shard_range(x.size, rank, world)
         risk = compute_risk_metrics_sharded(x[lo:hi], 0.99, comm=comm, handle=NumpyRiskHandle())
-        q.put((rank, got, price, delta, shard_range(n, rank, world), risk))
+        # scenario ladders over sharded paths: every cell's paths are split, the sums all-reduced once
+        from monte_carlo_option_simulator_b200.risk import StressTestEngine
+        many = eng.price_many([22500.0, 21000.0], [22500.0, 22000.0], 0.25, [True, False])
+        stress = StressTestEngine(p, num_paths=n, seed=5, rng="philox", handle=h, comm=comm).jump_scenario(22500.0, 22500.0, 0.25)
+        q.put((rank, got, price, delta, shard_range(n, rank, world), risk, many, stress))
     finally:
         dist.destroy_process_group()
 
@@ -71,7 +75,14 @@ def test_two_rank_sharding_matches_single_process():
     delta = GreeksEngine(p, 1001, 252, 5, rng="philox", handle=h).delta(22500.0, 22500.0, 0.25, True)
     assert results[0][4] == (0, 501) and results[1][4] == (501, 1001)
     want_risk = O.risk_metrics(np.random.default_rng(3).standard_t(3, size=20_001) * 0.01, 0.99)
-    for rank, got, pr_, dl, _, risk in results:
+    eng1 = MonteCarloEngine(p, 1001, 252, 5, use_sobol=False, rng="philox", handle=h)
+    want_many = [eng1.price(22500.0, 22500.0, 0.25, True), eng1.price(21000.0, 22000.0, 0.25, False)]
+    from monte_carlo_option_simulator_b200.risk import StressTestEngine
+    want_stress = StressTestEngine(p, num_paths=1001, seed=5, rng="philox", handle=h).jump_scenario(22500.0, 22500.0, 0.25)
+    for rank, got, pr_, dl, _, risk, many, stress in results:
+        for g_, w_ in zip(many, want_many):
+            assert g_ == pytest.approx(w_, rel=1e-10, abs=1e-9)
+        assert stress == pytest.approx(want_stress, rel=1e-9, abs=1e-8)
         for k, w in want_risk.items():
             assert risk[k] == pytest.approx(w, rel=1e-10, abs=1e-13), k
         np.testing.assert_allclose(got, whole, rtol=1e-12)
