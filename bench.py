@@ -407,6 +407,47 @@ def run_b200(args):
                                  "reading": "price_batch semantics: paths shared across the 64 strikes of an expiry",
                                  "atm_1y_price": float(grid["prices"][7, 32])}
             line["extras_path_steps_per_s"] = extras
+            # the callers of SURVEY 8(f): scenario grids, hedging backtest, implied-vol chain, quasi-Monte Carlo
+            try:
+                from monte_carlo_option_simulator_b200.risk import HedgingBacktest, StressTestEngine
+                nxt = {}
+                cells = _lib.make_cells(p, 22500.0, 0.25, 63, 50_000, 42 + np.arange(1000))
+                outc = torch.zeros(1000 * _lib.NSUMS, dtype=torch.float64, device="cuda")
+                best = None
+                for r in range(4):
+                    h.timer_begin()
+                    h.price_cells(cells, np.full(1000, 22500.0), _lib.ANTITHETIC, out_dev=outc.data_ptr())
+                    ms_ = h.timer_end()
+                    if r:
+                        best = ms_ if best is None else min(best, ms_)
+                nxt["cells_1000x50k_paths_x63_steps"] = {"ms": best, "path_steps_per_s": 1000 * 50_000 * 63 / (best * 1e-3)}
+                st = StressTestEngine(SVJParams(), num_paths=200_000, seed=42, handle=h)
+                bt = HedgingBacktest(SVJParams(), seed=42, handle=h)
+                st.full_stress_report(22500.0, 22500.0, 0.25)
+                bt.run_backtest(22500.0, 22500.0, 0.25, num_scenarios=10, num_mc_paths=1000)
+                t0 = time.perf_counter()
+                st.full_stress_report(22500.0, 22500.0, 0.25)
+                nxt["svj_full_stress_report_200k_paths_s"] = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                bt.run_backtest(22500.0, 22500.0, 0.25)
+                nxt["svj_hedging_backtest_1000x50k_paths_s"] = time.perf_counter() - t0
+                g = np.random.default_rng(1)
+                kk, tt = 22500.0 * g.uniform(0.8, 1.2, 2048), g.uniform(0.05, 1.0, 2048)
+                h.implied_vol(np.full(2048, 900.0), 22500.0, kk, tt, 0.065, 0.012)
+                t0 = time.perf_counter()
+                h.implied_vol(np.full(2048, 900.0), 22500.0, kk, tt, 0.065, 0.012)
+                nxt["implied_vol_2048_options_s"] = time.perf_counter() - t0
+                qe = MonteCarloEngine(p, 1 << 20, N_STEPS, 42, use_antithetic=False, use_control_variate=False, rng="sobol",
+                                      handle=h)
+                qe.price(SPOT, STRIKE, T)
+                t0 = time.perf_counter()
+                qp = qe.price(SPOT, STRIKE, T)
+                from monte_carlo_option_simulator_b200 import bs_price
+                nxt["qmc_1M_paths_x250"] = {"seconds": time.perf_counter() - t0,
+                                            "abs_error_vs_black_scholes": abs(qp["price"] - bs_price(SPOT, STRIKE, T, p.r, p.q, 0.3, True))}
+                line["next_rows"] = nxt
+            except Exception as e:  # noqa: BLE001
+                line["next_rows"] = {"error": str(e)}
             v, cores, dt = cpu_reference_steps(2, 1, 50_000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "50000 paths x 250 steps: price + delta + vega + gamma per step, 2 steps "

@@ -218,10 +218,11 @@ class HedgingBacktest:
     rng="reference": premiums from the reference's own draws (Sobol front end on the host) and the walk on
     default_rng(seed) normals -- reproduces the reference's numbers; rng="philox" (default): device draws."""
 
-    def __init__(self, params, seed: int = 42, *, rng=None, precision="fp32", handle=None):
+    def __init__(self, params, seed: int = 42, *, rng=None, precision="fp32", handle=None, comm=None):
         self.params = params
         self.seed = seed
         self.rng = rng
+        self.comm = comm            # scenarios are sharded over its ranks (contiguous ranges), P&Ls gathered once
         self._kw = dict(rng=rng, precision=precision, handle=handle)
 
     def run_backtest(self, spot: float, strike: float, T: float, is_call: bool = True, num_days: int = None,
@@ -232,13 +233,24 @@ class HedgingBacktest:
         p = self.params
         engine = MonteCarloEngine(p, num_paths=num_mc_paths, seed=self.seed, **self._kw)
         h = engine.handle
-        seeds = [self.seed + s for s in range(num_scenarios)]                                      # :271
-        premiums = np.array([r["price"] for r in engine.price_many(spot, strike, T, is_call, seeds=seeds)])   # :272-273
-        Z = None
-        if engine.rng == "reference":                                                              # :262,292
-            Z = np.random.default_rng(self.seed).standard_normal((num_scenarios, num_days))
-        pnl, cost = h.hedge_walk(p, spot, strike, T, is_call, num_days, num_scenarios, txn_cost_bps + slippage_bps,
-                                 premiums, Z, seed=self.seed)
+        lo, hi = 0, num_scenarios
+        world = self.comm.world if self.comm is not None else 1
+        if world > 1:
+            from .dist import shard_range
+            lo, hi = shard_range(num_scenarios, self.comm.rank, world)
+        pnl = np.zeros(num_scenarios)
+        cost = np.zeros(num_scenarios)
+        if hi > lo:
+            seeds = [self.seed + s for s in range(lo, hi)]                                         # :271
+            premiums = np.array([r["price"] for r in engine.price_many(spot, strike, T, is_call, seeds=seeds)])   # :272-273
+            Z = None
+            if engine.rng == "reference":                                                          # :262,292
+                Z = np.random.default_rng(self.seed).standard_normal((num_scenarios, num_days))[lo:hi]
+            pnl[lo:hi], cost[lo:hi] = h.hedge_walk(p, spot, strike, T, is_call, num_days, hi - lo, txn_cost_bps + slippage_bps,
+                                                   premiums, Z, seed=self.seed, scenario_offset=lo)
+        if world > 1:
+            both = self.comm.allreduce_sum(np.stack([pnl, cost]))
+            pnl, cost = both.reshape(2, num_scenarios)
         metrics = compute_risk_metrics(pnl, confidence=0.99, handle=h)                             # :319
         return {"mean_pnl": float(np.mean(pnl)), "std_pnl": float(np.std(pnl)),
                 "pnl_percentiles": {f"{q}%": float(np.percentile(pnl, q)) for q in (1, 5, 25, 50, 75, 95, 99)},

@@ -44,7 +44,10 @@ def _worker(rank, world, port, q):
         from monte_carlo_option_simulator_b200.risk import StressTestEngine
         many = eng.price_many([22500.0, 21000.0], [22500.0, 22000.0], 0.25, [True, False])
         stress = StressTestEngine(p, num_paths=n, seed=5, rng="philox", handle=h, comm=comm).jump_scenario(22500.0, 22500.0, 0.25)
-        q.put((rank, got, price, delta, shard_range(n, rank, world), risk, many, stress))
+        from monte_carlo_option_simulator_b200.risk import HedgingBacktest
+        hedge = HedgingBacktest(p, seed=9, rng="philox", handle=OracleBackedHandle(), comm=comm).run_backtest(
+            22500.0, 22500.0, 0.05, True, num_scenarios=11, num_mc_paths=200)       # scenarios 0..5 | 6..10
+        q.put((rank, got, price, delta, shard_range(n, rank, world), risk, many, stress, hedge))
     finally:
         dist.destroy_process_group()
 
@@ -79,7 +82,12 @@ def test_two_rank_sharding_matches_single_process():
     want_many = [eng1.price(22500.0, 22500.0, 0.25, True), eng1.price(21000.0, 22000.0, 0.25, False)]
     from monte_carlo_option_simulator_b200.risk import StressTestEngine
     want_stress = StressTestEngine(p, num_paths=1001, seed=5, rng="philox", handle=h).jump_scenario(22500.0, 22500.0, 0.25)
-    for rank, got, pr_, dl, _, risk, many, stress in results:
+    from monte_carlo_option_simulator_b200.risk import HedgingBacktest
+    from conftest import assert_tree_close
+    want_hedge = HedgingBacktest(p, seed=9, rng="philox", handle=OracleBackedHandle()).run_backtest(
+        22500.0, 22500.0, 0.05, True, num_scenarios=11, num_mc_paths=200)
+    for rank, got, pr_, dl, _, risk, many, stress, hedge in results:
+        assert_tree_close(hedge, want_hedge, rel=1e-10, abs_=1e-9)
         for g_, w_ in zip(many, want_many):
             assert g_ == pytest.approx(w_, rel=1e-10, abs=1e-9)
         assert stress == pytest.approx(want_stress, rel=1e-9, abs=1e-8)
