@@ -46,12 +46,41 @@ class TorchComm(Comm):
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
+    def allreduce_device(self, handle, nelem: int, fill) -> np.ndarray:
+        """NCCL only: `fill(ptr)` enqueues, on the handle's stream, the kernels that write `nelem` doubles at the device
+        pointer `ptr`; the buffer is all-reduced where it is and read back once (no host round trip between the kernel
+        and the collective).  fill=None leaves the buffer zero (a rank without work)."""
+        import torch
+        dev = torch.device("cuda", handle.device)
+        buf = getattr(self, "_buf", None)
+        if buf is None or buf.numel() < nelem or buf.device != dev:
+            buf = self._buf = torch.zeros(max(nelem, 4096), dtype=torch.float64, device=dev)
+        view = buf[:nelem]
+        cur = torch.cuda.current_stream(dev)
+        if fill is None:
+            view.zero_()
+        else:
+            if handle.stream != cur.cuda_stream:
+                cur.synchronize()                   # the buffer may still feed the previous call's read-back
+            fill(view.data_ptr())
+            if handle.stream != cur.cuda_stream:
+                handle.synchronize()                # order the collective after the kernels
+        self._dist.all_reduce(view, op=self._dist.ReduceOp.SUM, group=self.group)
+        return view.cpu().numpy()
+
 
 def sharded_sums(handle, comm: Comm, params, spot, T, steps, n_paths, seed, strikes, is_call, flags,
                  bumps=None) -> np.ndarray:
     """Each rank simulates its path range; returns the all-reduced [n_strikes, NSUMS] sums on every rank."""
     lo, hi = shard_range(n_paths, comm.rank, comm.world)
     ks = np.atleast_1d(np.asarray(strikes, dtype=np.float64))
+    if getattr(comm, "backend", None) == "nccl" and hasattr(comm, "allreduce_device") and hasattr(handle, "h"):
+        fill = None
+        if hi > lo:
+            def fill(ptr):
+                handle.price_european(params, spot, T, steps, hi - lo, seed, ks, is_call, flags, bumps, path_offset=lo,
+                                      out_dev=ptr)
+        return comm.allreduce_device(handle, ks.size * NSUMS, fill).reshape(ks.size, NSUMS)
     if hi > lo:
         local = handle.price_european(params, spot, T, steps, hi - lo, seed, ks, is_call, flags, bumps,
                                       path_offset=lo)
