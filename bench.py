@@ -261,10 +261,20 @@ def run_b200(args):
     flags = _lib.GREEKS
     out = torch.zeros(_lib.NSUMS, dtype=torch.float64, device="cuda")
 
+    # the exchange step (17 fp64 sums per step): one-shot all-reduce over NVLink peer memory (csrc/peer.cu) unless
+    # B200MC_EXCHANGE=nccl asks for the NCCL call
+    use_peer = world > 1 and os.environ.get("B200MC_EXCHANGE", "peer") != "nccl"
+    comm = None
+    if world > 1:
+        from monte_carlo_option_simulator_b200.dist import PeerComm
+        comm = PeerComm(h) if use_peer else TorchComm()
+
     def step(i):
         h.price_european(p, SPOT, T, N_STEPS, n, 42 + i, [STRIKE], True, flags, bumps, path_offset=rank * n,
                          out_dev=out.data_ptr())
-        if world > 1:
+        if use_peer:
+            h.peer_allreduce(out.data_ptr(), _lib.NSUMS)
+        elif world > 1:
             dist.all_reduce(out)
 
     def barrier():
@@ -312,7 +322,6 @@ def run_b200(args):
     sums = out.cpu().numpy()
 
     # ---- e2e through the public API (host arguments in, host dict out) -----------------------------------
-    comm = TorchComm() if world > 1 else None
     g = GreeksEngine(p, n * world, N_STEPS, seed=1000, rng="philox", handle=h, comm=comm)
     e2e_steps = args.steps
 
@@ -357,7 +366,9 @@ def run_b200(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "paths_per_gpu": n, "n_steps": N_STEPS, "rng": "Philox4x32-10 in registers",
-                           "exchange": "NCCL all-reduce of 17 fp64 sums per step" if world > 1 else "none",
+                           "exchange": ("none" if world == 1 else
+                                        "one-shot all-reduce of 17 fp64 sums per step over NVLink peer memory (k_peer_allreduce)"
+                                        if use_peer else "NCCL all-reduce of 17 fp64 sums per step"),
                            "l2": "kernel reads no global inputs (counter-based RNG), nothing to flush; every step uses a new seed"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": _lib.NSUMS * 8,

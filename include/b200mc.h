@@ -128,6 +128,21 @@ uint64_t b200mc_stream(const b200mc_handle *h);
 int b200mc_set_stream(b200mc_handle *h, uint64_t stream);
 int b200mc_synchronize(b200mc_handle *h);
 
+/* ---- the exchange step of the multi-GPU path over NVLink peer memory ---------------------------------------
+ * One process per GPU.  b200mc_peer_create allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle;
+ * the caller all-gathers the handles of all ranks (any transport: torch.distributed, MPI, a file) and passes them, in rank
+ * order, to b200mc_peer_connect, which maps the peers' buffers.  b200mc_peer_allreduce then sums data_dev[n_doubles]
+ * (DEVICE memory of this rank, e.g. the b200mc_sums a b200mc_price_european_async call just wrote) over all ranks IN
+ * PLACE: one single-CTA kernel on the handle's stream that stores the vector into every rank's buffer, raises a flag,
+ * waits for the flags of all ranks and adds the vectors in rank order (bitwise the same result on every rank).  A
+ * collective: all ranks call it, in the same order.  A peer that never arrives turns the result into NaN after 20 s. */
+#define B200MC_PEER_MAX_RANKS   16
+#define B200MC_PEER_MAX_DOUBLES 4352            /* 256 strikes x 17 sums */
+int b200mc_peer_create(b200mc_handle *h, unsigned char ipc_handle_out[64]);
+int b200mc_peer_connect(b200mc_handle *h, int rank, int world, const unsigned char *all_handles /* [world][64] */);
+int b200mc_peer_allreduce(b200mc_handle *h, double *data_dev, int32_t n_doubles);
+int b200mc_peer_close(b200mc_handle *h);
+
 /* ---- a1: deterministic "given normals" mode ------------------------------------------------------------
  * Drop-in for _simulate_svj_paths_numba(S0, v0, r, q, T, kappa, theta, xi, rho, lambda_j, mu_j, sigma_j,
  * Z1, Z2, Z_jump, Z_jump_size, num_steps, record_paths), engine/monte_carlo.py:189-243.

@@ -107,6 +107,10 @@ _PROTOS = {
     "b200mc_stream": (_u64, [_vp]),
     "b200mc_set_stream": (C.c_int, [_vp, _u64]),
     "b200mc_synchronize": (C.c_int, [_vp]),
+    "b200mc_peer_create": (C.c_int, [_vp, _vp]),
+    "b200mc_peer_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "b200mc_peer_allreduce": (C.c_int, [_vp, _vp, _i32]),
+    "b200mc_peer_close": (C.c_int, [_vp]),
     "b200mc_simulate_given_normals": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i64, _i32,
                                                  _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "b200mc_simulate_given_normals_dev": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i64, _i32,
@@ -247,6 +251,25 @@ class Handle:
 
     def synchronize(self):
         self._check(self.lib.b200mc_synchronize(self.h))
+
+    # -- exchange over NVLink peer memory (csrc/peer.cu) ----------------------------------------------------
+    def peer_create(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.b200mc_peer_create(self.h, buf))
+        return bytes(buf)
+
+    def peer_connect(self, rank: int, world: int, handles) -> None:
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise B200MCError(EINVAL, "peer_connect needs one 64-byte IPC handle per rank")
+        self._check(self.lib.b200mc_peer_connect(self.h, int(rank), int(world), blob))
+
+    def peer_allreduce(self, data_dev: int, n_doubles: int) -> None:
+        """In-place sum over the ranks of n_doubles float64 at device pointer data_dev (asynchronous, collective)."""
+        self._check(self.lib.b200mc_peer_allreduce(self.h, _vp(data_dev), int(n_doubles)))
+
+    def peer_close(self) -> None:
+        self._check(self.lib.b200mc_peer_close(self.h))
 
     def timer_begin(self):
         self._check(self.lib.b200mc_timer_begin(self.h))

@@ -29,6 +29,8 @@ struct b200mc_handle {
     const void *occ_kern[64]; size_t occ_smem[64]; int occ_val[64]; int n_occ;   // (kernel, smem) -> resident CTAs per SM
     const void *risk_x; int64_t risk_n; int risk_dtype; // vector of the multi-rank tail-metric primitives (risk.cu)
     unsigned int *d_counter;                           // "last block reduces" ticket
+    void *peer_local; void *peer_ptr[B200MC_PEER_MAX_RANKS]; int peer_rank, peer_world;   // peer.cu: exchange buffers
+    unsigned long long peer_epoch;
     char err[512];
 };
 

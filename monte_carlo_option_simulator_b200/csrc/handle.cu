@@ -62,6 +62,7 @@ extern "C" int b200mc_destroy(b200mc_handle *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    b200mc_peer_close(h);
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->d_result) cudaFree(h->d_result);

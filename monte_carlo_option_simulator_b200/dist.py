@@ -69,6 +69,47 @@ class TorchComm(Comm):
         return view.cpu().numpy()
 
 
+class PeerComm(TorchComm):
+    """TorchComm whose exchange of the per-strike sums is the one-shot all-reduce over NVLink peer memory of
+    csrc/peer.cu (b200mc_peer_allreduce) instead of an NCCL call.  torch.distributed is used once, to all-gather the CUDA
+    IPC handles of the exchange buffers; vectors that do not fit the exchange buffer, and host arrays, go through
+    TorchComm's paths.  One PeerComm per (handle, process group)."""
+
+    def __init__(self, handle, group=None):
+        super().__init__(group)
+        self.handle = handle
+        mine = handle.peer_create()
+        handles = [None] * self.world
+        self._dist.all_gather_object(handles, mine, group=group)
+        handle.peer_connect(self.rank, self.world, handles)
+        self._dist.barrier(group=group)                     # every buffer is zeroed and mapped before the first store
+
+    def allreduce_device(self, handle, nelem: int, fill) -> np.ndarray:
+        from ._lib import B200MCError  # noqa: F401
+        if handle is not self.handle or nelem > 4352:
+            return super().allreduce_device(handle, nelem, fill)
+        import torch
+        dev = torch.device("cuda", handle.device)
+        buf = getattr(self, "_buf", None)
+        if buf is None or buf.numel() < nelem or buf.device != dev:
+            buf = self._buf = torch.zeros(4352, dtype=torch.float64, device=dev)
+        view = buf[:nelem]
+        cur = torch.cuda.current_stream(dev)
+        same = handle.stream == cur.cuda_stream
+        if not same:
+            cur.synchronize()
+        if fill is None:
+            view.zero_()
+            if not same:
+                cur.synchronize()
+        else:
+            fill(view.data_ptr())
+        handle.peer_allreduce(view.data_ptr(), nelem)       # on the handle's stream, right behind the kernels
+        if not same:
+            handle.synchronize()
+        return view.cpu().numpy()
+
+
 def sharded_sums(handle, comm: Comm, params, spot, T, steps, n_paths, seed, strikes, is_call, flags,
                  bumps=None) -> np.ndarray:
     """Each rank simulates its path range; returns the all-reduced [n_strikes, NSUMS] sums on every rank."""
