@@ -85,7 +85,6 @@ class PeerComm(TorchComm):
         self._dist.barrier(group=group)                     # every buffer is zeroed and mapped before the first store
 
     def allreduce_device(self, handle, nelem: int, fill) -> np.ndarray:
-        from ._lib import B200MCError  # noqa: F401
         if handle is not self.handle or nelem > 4352:
             return super().allreduce_device(handle, nelem, fill)
         import torch

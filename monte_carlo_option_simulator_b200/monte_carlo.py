@@ -311,7 +311,7 @@ class MonteCarloEngine:
         .price(spot_i, strike_i, T_i, is_call_i) returns (same draws, sums equal up to the order of the fp64 additions).
         This is what the loops of engine/risk.py:33-111 (stress ladders) and :264-273 (premium of every hedging
         scenario) become.  With a communicator the paths of every cell are sharded and the sums all-reduced once."""
-        def seq(x, n=None):
+        def seq(x):
             return list(x) if isinstance(x, (list, tuple, np.ndarray)) else None
         cols = [seq(spots), seq(strikes), seq(Ts), seq(is_call), seq(params), seq(seeds)]
         m = max([len(c) for c in cols if c is not None] or [1])

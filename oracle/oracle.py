@@ -20,7 +20,7 @@ import math
 import os
 import subprocess
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional
 
 import numpy as np
 

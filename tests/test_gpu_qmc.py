@@ -1,8 +1,6 @@
 """GPU tests of the working quasi-Monte Carlo front end: device Sobol points bitwise SciPy's, the
 correct Brownian bridge, the sums against the oracle recurrence on the same draws, and the point of it all -- an error
 far below plain Monte Carlo's at equal path counts."""
-import math
-
 import numpy as np
 import pytest
 

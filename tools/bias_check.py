@@ -1,7 +1,6 @@
 """Large-sample bias check of the fused GBM kernel against Black-Scholes (log-Euler with constant variance has no
 discretisation bias, so any deviation beyond a few standard errors is generator / arithmetic bias).
     python tools/bias_check.py [n_paths]"""
-import math
 import os
 import sys
 

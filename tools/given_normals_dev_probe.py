@@ -1,7 +1,8 @@
+"""Given-normals kernel on DEVICE-resident normals (torch tensors): GB/s for SVJ / Heston / GBM parameter sets."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
-import numpy as np, torch
+import torch
 from monte_carlo_option_simulator_b200 import SVJParams, _lib
 h = _lib.Handle(0)
 for n, steps in ((1_000_000, 250), (4_000_000, 64)):
