@@ -142,6 +142,12 @@ int b200mc_peer_create(b200mc_handle *h, unsigned char ipc_handle_out[64]);
 int b200mc_peer_connect(b200mc_handle *h, int rank, int world, const unsigned char *all_handles /* [world][64] */);
 int b200mc_peer_allreduce(b200mc_handle *h, double *data_dev, int32_t n_doubles);
 int b200mc_peer_close(b200mc_handle *h);
+/* compute_risk_metrics (engine/risk.py:117-155) over a vector SHARDED across the ranks of the peer connection: every rank
+ * passes its own shard (n_local may be 0) and receives the GLOBAL metrics (out as b200mc_risk_metrics).  The shards never
+ * move: the radix select runs on every rank's keys and only 3 doubles, 8 x 256-bin histograms and 6 doubles are all-reduced,
+ * on the device, between the kernels.  A collective: all ranks call it. */
+int b200mc_risk_metrics_sharded(b200mc_handle *h, const void *pnl_local, int64_t n_local, int dtype, int on_device,
+                                double confidence, double out[8]);
 
 /* ---- a1: deterministic "given normals" mode ------------------------------------------------------------
  * Drop-in for _simulate_svj_paths_numba(S0, v0, r, q, T, kappa, theta, xi, rho, lambda_j, mu_j, sigma_j,

@@ -111,6 +111,7 @@ _PROTOS = {
     "b200mc_peer_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b200mc_peer_allreduce": (C.c_int, [_vp, _vp, _i32]),
     "b200mc_peer_close": (C.c_int, [_vp]),
+    "b200mc_risk_metrics_sharded": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _dbl, _dp]),
     "b200mc_simulate_given_normals": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i64, _i32,
                                                  _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "b200mc_simulate_given_normals_dev": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i64, _i32,
@@ -480,6 +481,24 @@ class Handle:
         code = F64 if a.dtype == np.float64 else F32
         self._check(self.lib.b200mc_risk_metrics(self.h, a.ctypes.data, a.size, code, 0, float(confidence),
                                                   out.ctypes.data_as(_dp)))
+        return out
+
+    def risk_metrics_sharded(self, pnl, confidence=0.99, n: Optional[int] = None, dtype=None) -> np.ndarray:
+        """Collective over the handle's peer connection: pnl is THIS rank's shard (NumPy array, or device pointer + n +
+        dtype); returns the global metrics."""
+        out = np.empty(8, dtype=np.float64)
+        if isinstance(pnl, int):
+            code = F64 if np.dtype(dtype) == np.float64 else F32
+            self._check(self.lib.b200mc_risk_metrics_sharded(self.h, _vp(pnl) if n else None, int(n), code, 1,
+                                                              float(confidence), out.ctypes.data_as(_dp)))
+            return out
+        a = np.asarray(pnl)
+        if a.dtype != np.float32:
+            a = a.astype(np.float64, copy=False)
+        a = np.ascontiguousarray(a).ravel()
+        code = F64 if a.dtype == np.float64 else F32
+        self._check(self.lib.b200mc_risk_metrics_sharded(self.h, a.ctypes.data if a.size else None, a.size, code, 0,
+                                                          float(confidence), out.ctypes.data_as(_dp)))
         return out
 
     def option_pnl(self, S_dev: int, n: int, strike: float, is_call: bool, discount: float, premium: float, pnl_dev: int,

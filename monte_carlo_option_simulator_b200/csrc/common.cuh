@@ -79,6 +79,10 @@ inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pi
     return 0;
 }
 
+// peer.cu: in-place sum over the ranks of n 8-byte elements (double, or unsigned long long with as_u64) at data_dev,
+// asynchronous on the handle's stream; a collective (needs b200mc_peer_connect)
+int peer_allreduce_async(b200mc_handle *h, void *data_dev, int32_t n, bool as_u64);
+
 // ---- warp / block reduction of NV doubles, deterministic "last block sums the partials" finish ---------
 template <int NV>
 __device__ __forceinline__ void warp_reduce(double (&v)[NV])

@@ -43,14 +43,16 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
+// T = double (sums) or unsigned long long (histogram counts of the sharded radix select, risk.cu): 8-byte elements
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_peer_allreduce(const __grid_constant__ PeerArgs a, double *__restrict__ data, int n)
+k_peer_allreduce(const __grid_constant__ PeerArgs a, T *__restrict__ data, int n)
 {
     const int tid = threadIdx.x, par = (int)(a.epoch & 1ull);
     __shared__ int timed_out;
     if (tid == 0) timed_out = 0;
     for (int r = 0; r < a.world; ++r) {
-        double *dst = a.peer[r]->data[par][a.rank];
+        T *dst = reinterpret_cast<T *>(a.peer[r]->data[par][a.rank]);
         for (int i = tid; i < n; i += blockDim.x) dst[i] = data[i];
     }
     __threadfence_system();
@@ -67,10 +69,32 @@ k_peer_allreduce(const __grid_constant__ PeerArgs a, double *__restrict__ data, 
     __syncthreads();
     const PeerBuf *mine = a.peer[a.rank];
     for (int i = tid; i < n; i += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < a.world; ++r) s += __ldcg(&mine->data[par][r][i]);     // written by peers: read at L2
-        data[i] = timed_out ? __longlong_as_double(0x7ff8000000000000ll) : s;
+        T s = (T)0;
+        for (int r = 0; r < a.world; ++r) s += __ldcg(reinterpret_cast<const T *>(&mine->data[par][r][i]));   // written by peers: read at L2
+        if (timed_out) {
+            if constexpr (sizeof(T) == 8 && T(0.5) != T(0)) s = (T)__longlong_as_double(0x7ff8000000000000ll);
+            else s = (T)0;
+        }
+        data[i] = s;
     }
+}
+
+int peer_allreduce_async(b200mc_handle *h, void *data_dev, int32_t n, bool as_u64)
+{
+    if (h->peer_world < 1) return fail(h, B200MC_EINVAL, "call b200mc_peer_connect first");
+    if (n < 1 || n > B200MC_PEER_MAX_DOUBLES)
+        return fail(h, B200MC_EINVAL, "n_doubles must be in [1, 4352] (256 strikes x 17 sums)");
+    PeerArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < h->peer_world; ++r) a.peer[r] = (PeerBuf *)h->peer_ptr[r];
+    a.rank = h->peer_rank;
+    a.world = h->peer_world;
+    a.epoch = ++h->peer_epoch;
+    if (as_u64) k_peer_allreduce<unsigned long long><<<1, 256, 0, h->stream>>>(a, (unsigned long long *)data_dev, n);
+    else k_peer_allreduce<double><<<1, 256, 0, h->stream>>>(a, (double *)data_dev, n);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
 }
 
 } // namespace b200mc
@@ -117,20 +141,8 @@ extern "C" int b200mc_peer_connect(b200mc_handle *h, int rank, int world, const 
 extern "C" int b200mc_peer_allreduce(b200mc_handle *h, double *data_dev, int32_t n_doubles)
 {
     if (!h || !data_dev) return fail(h, B200MC_EINVAL, "NULL argument");
-    if (h->peer_world < 1) return fail(h, B200MC_EINVAL, "call b200mc_peer_connect first");
-    if (n_doubles < 1 || n_doubles > B200MC_PEER_MAX_DOUBLES)
-        return fail(h, B200MC_EINVAL, "n_doubles must be in [1, 4352] (256 strikes x 17 sums)");
     B200MC_CUDA(h, cudaSetDevice(h->device));
-    PeerArgs a;
-    memset(&a, 0, sizeof(a));
-    for (int r = 0; r < h->peer_world; ++r) a.peer[r] = (PeerBuf *)h->peer_ptr[r];
-    a.rank = h->peer_rank;
-    a.world = h->peer_world;
-    a.epoch = ++h->peer_epoch;
-    k_peer_allreduce<<<1, 256, 0, h->stream>>>(a, data_dev, n_doubles);
-    B200MC_CUDA(h, cudaGetLastError());
-    h->launches += 1;
-    return 0;
+    return peer_allreduce_async(h, data_dev, n_doubles, false);
 }
 
 extern "C" int b200mc_peer_close(b200mc_handle *h)

@@ -109,12 +109,21 @@ k_risk_pass2(const T *__restrict__ x, int64_t n, double mean, int nsel, const Se
     block_finish<6>(v, smem, partials, counter, out);
 }
 
+__global__ void k_set_double(double *p, double v) { *p = v; }
+
+// sharded = the vector is the LOCAL shard of a vector spread over the ranks of the handle's peer connection (peer.cu):
+// the two sums of pass 1 (+ the shard length), the histograms of every radix pass and the six sums of pass 2 are
+// all-reduced on the device between the kernels, so every rank takes the same decisions and returns the GLOBAL metrics;
+// the shards never move and the host synchronises twice, as in the single-device case.  n may be 0 on a rank.
 template <typename T>
-static int risk_run(b200mc_handle *h, const T *x_dev, int64_t n, double confidence, double out[8])
+static int risk_run(b200mc_handle *h, const T *x_dev, const int64_t n_loc, double confidence, double out[8],
+                    bool sharded = false)
 {
-    int64_t grid = (n + RK_THREADS - 1) / RK_THREADS;
+    int64_t n = n_loc;                                 // becomes the GLOBAL length after pass 1 when sharded
+    int64_t grid = (n_loc + RK_THREADS - 1) / RK_THREADS;
     const int64_t cap = (int64_t)h->sm_count * 8;
     if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
     // scratch: [keys n*8][SelectState][partials grid*6*8][results 8*8]
     const size_t off_st = ((size_t)n * 8 + 255) & ~(size_t)255;
     const size_t off_pa = off_st + ((sizeof(SelectState) + 255) & ~(size_t)255);
@@ -125,12 +134,18 @@ static int risk_run(b200mc_handle *h, const T *x_dev, int64_t n, double confiden
     SelectState *st = (SelectState *)(sc + off_st);
     double *partials = (double *)(sc + off_pa), *res = (double *)(sc + off_re);
 
-    k_risk_pass1<T><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(x_dev, n, keys, partials, h->d_counter, res);
+    k_risk_pass1<T><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(x_dev, n_loc, keys, partials, h->d_counter, res);
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
-    double r1[2];
-    B200MC_CUDA(h, cudaMemcpyAsync(r1, res, 16, cudaMemcpyDeviceToHost, h->stream));
+    double r1[3] = {0.0, 0.0, (double)n_loc};
+    if (sharded) {
+        k_set_double<<<1, 1, 0, h->stream>>>(res + 2, (double)n_loc);
+        B200MC_TRY(peer_allreduce_async(h, res, 3, false));
+    }
+    B200MC_CUDA(h, cudaMemcpyAsync(r1, res, sharded ? 24 : 16, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    n = (int64_t)r1[2];                                                      // from here on: the GLOBAL length
+    if (n <= 0) return fail(h, B200MC_EINVAL, "returns must not be empty");
     const double mean = r1[0] / (double)n;                                   // :137
     const int64_t m = (int64_t)r1[1];                                        // len(losses), :147
 
@@ -153,14 +168,16 @@ static int risk_run(b200mc_handle *h, const T *x_dev, int64_t n, double confiden
     memcpy(h->h_pinned, &init, sizeof(init));
     B200MC_CUDA(h, cudaMemcpyAsync(st, h->h_pinned, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     for (int pass = 7; pass >= 0; --pass) {
-        k_risk_hist<<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(keys, n, pass, nsel, st);
+        k_risk_hist<<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(keys, n_loc, pass, nsel, st);
+        if (sharded) B200MC_TRY(peer_allreduce_async(h, &st->hist[0][0], 256 * nsel, true));
         k_risk_pick<<<1, 32, 0, h->stream>>>(pass, nsel, st);
         h->launches += 2;
     }
     B200MC_CUDA(h, cudaGetLastError());
-    k_risk_pass2<T><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(x_dev, n, mean, nsel, st, partials, h->d_counter, res);
+    k_risk_pass2<T><<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(x_dev, n_loc, mean, nsel, st, partials, h->d_counter, res);
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
+    if (sharded) B200MC_TRY(peer_allreduce_async(h, res, 6, false));
     double r2[6], thr[2];
     B200MC_CUDA(h, cudaMemcpyAsync(r2, res, 48, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaMemcpyAsync(thr, &st->thr[0], 16, cudaMemcpyDeviceToHost, h->stream));
@@ -354,4 +371,25 @@ extern "C" int b200mc_risk_metrics(b200mc_handle *h, const void *pnl, int64_t n,
     }
     if (dtype == B200MC_F64) return risk_run<double>(h, (const double *)x, n, confidence, out);
     return risk_run<float>(h, (const float *)x, n, confidence, out);
+}
+
+extern "C" int b200mc_risk_metrics_sharded(b200mc_handle *h, const void *pnl_local, int64_t n_local, int dtype, int on_device,
+                                           double confidence, double out[8])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out || (n_local > 0 && !pnl_local)) return fail(h, B200MC_EINVAL, "NULL argument");
+    if (n_local < 0) return fail(h, B200MC_EINVAL, "n_local must be >= 0");
+    if (dtype != B200MC_F32 && dtype != B200MC_F64) return fail(h, B200MC_EINVAL, "dtype must be B200MC_F32 or B200MC_F64");
+    if (!(confidence == confidence)) return fail(h, B200MC_EINVAL, "confidence is NaN");
+    if (h->peer_world < 1) return fail(h, B200MC_EINVAL, "call b200mc_peer_connect first");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const size_t esz = dtype == B200MC_F64 ? 8 : 4;
+    const void *x = pnl_local;
+    if (!on_device && n_local > 0) {
+        B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, (size_t)n_local * esz + 256));
+        B200MC_CUDA(h, cudaMemcpyAsync(h->d_stage, pnl_local, (size_t)n_local * esz, cudaMemcpyHostToDevice, h->stream));
+        x = h->d_stage;
+    }
+    if (dtype == B200MC_F64) return risk_run<double>(h, (const double *)x, n_local, confidence, out, true);
+    return risk_run<float>(h, (const float *)x, n_local, confidence, out, true);
 }

@@ -46,6 +46,14 @@ def compute_risk_metrics_sharded(local_returns, confidence: float = 0.99, *, com
     the radix select on its own keys and only 2 doubles, 8 x 512 counters and 6 doubles are all-reduced, so all ranks
     take the same decisions and return the same global metrics (same index conventions as the reference)."""
     h = handle or _lib.default_handle()
+    if getattr(comm, "handle", None) is h and hasattr(h, "risk_metrics_sharded"):
+        # PeerComm: the whole select runs device-side, histograms all-reduced over NVLink peer memory between the kernels
+        if isinstance(local_returns, tuple):
+            ptr, n_local, dt = local_returns
+            out = h.risk_metrics_sharded(int(ptr), confidence, n=n_local, dtype=dt)
+        else:
+            out = h.risk_metrics_sharded(np.asarray(local_returns), confidence)
+        return {k: float(v) for k, v in zip(KEYS, out)}
     if isinstance(local_returns, tuple):
         ptr, n_local, dt = local_returns
         s = h.risk_begin(int(ptr), n_local, dt)
