@@ -37,6 +37,18 @@ def test_struct_layouts_match_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = [f.strip() for decl in re.findall(r"double\s+([^;]+);", body) for f in decl.split(",")]
     assert tuple(fields) == _lib.SUMS_FIELDS
+    # b200mc_cell: the ctypes struct, the NumPy dtype used to fill thousands of cells at once and the header agree
+    body = text[text.index("typedef struct b200mc_cell {"):text.index("} b200mc_cell;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    decls = re.findall(r"(b200mc_svj_params|double|int64_t|uint64_t|int32_t)\s+([^;]+);", body)
+    names = [f.strip() for _, d in decls for f in d.split(",")]
+    assert names == [n for n, _ in _lib.Cell._fields_]
+    assert ctypes.sizeof(_lib.Cell) == _lib.CELL_DTYPE.itemsize == 128
+    for name in names[1:]:
+        assert getattr(_lib.Cell, name).offset == _lib.CELL_DTYPE.fields[name][1], name
+    assert _lib.CELL_DTYPE.names[:10] == _lib.PARAM_FIELDS
+    # constants of the peer exchange
+    assert "#define B200MC_PEER_MAX_RANKS   16" in text and "#define B200MC_PEER_MAX_DOUBLES 4352" in text
 
 
 def test_no_cpu_fallback_without_a_gpu():

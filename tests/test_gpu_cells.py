@@ -111,3 +111,29 @@ def test_cells_errors(H, L):
         H.price_cells([ok], np.zeros((1, 257)))
     # the handle still works after the rejected calls
     assert H.price_cells([ok], [100.0])[0, 0, 0] == 10
+
+
+def test_cells_edge_shapes(H, L):
+    """256 strikes in one cell, a single path, a single step, a 4096-step deterministic-variance cell (the longest weight
+    table), and the structured-array front end with broadcasting."""
+    p = O.Params(kappa=0.0, theta=0.09, xi=0.0, rho=0.0, v0=0.09, lambda_j=0.0, mu_j=0.0, sigma_j=0.01, r=0.065, q=0.0)
+    ks = np.linspace(0.5, 1.5, 256) * 100.0
+    got = H.price_cells([dict(params=p, S0=100.0, T=1.0, n_steps=12, n_paths=1000, seed=5)], ks[None, :], L.ANTITHETIC)
+    want = H.price_european(p, 100.0, 1.0, 12, 1000, 5, ks, True, L.ANTITHETIC)
+    np.testing.assert_allclose(got[0, :, :9], want[:, :9], rtol=1e-12, atol=1e-9)
+    for n_paths, n_steps in ((1, 1), (1, 300), (300, 1), (257, 9)):
+        c = dict(params=p, S0=100.0, T=0.5, n_steps=n_steps, n_paths=n_paths, seed=9, path_offset=7, is_call=False)
+        np.testing.assert_allclose(H.price_cells([c], [110.0], L.FP64)[0, 0, :9],
+                                   H.price_european(p, 100.0, 0.5, n_steps, n_paths, 9, [110.0], False, L.FP64, None, path_offset=7)[0, :9],
+                                   rtol=1e-12, atol=1e-12)
+    dv = O.Params(kappa=2.0, theta=0.05, xi=0.0, rho=0.0, v0=0.09, lambda_j=0.0, mu_j=0.0, sigma_j=0.01, r=0.03, q=0.0)
+    cells = [dict(params=dv, S0=100.0, T=2.0, n_steps=4096, n_paths=600, seed=1),
+             dict(params=dv, S0=100.0, T=1.0, n_steps=17, n_paths=600, seed=2)]          # two table lengths in one group
+    got = H.price_cells(cells, [100.0, 95.0], 0)
+    for c, K, row in zip(cells, (100.0, 95.0), got[:, 0]):
+        np.testing.assert_allclose(row[:9], H.price_european(dv, 100.0, c["T"], c["n_steps"], 600, c["seed"], [K], True, 0)[0, :9],
+                                   rtol=1e-12)
+    arr = L.make_cells(p, [100.0, 101.0, 102.0], 1.0, 12, 500, 5, 0, [True, False, True])
+    assert arr.shape == (3,) and arr["is_call"].tolist() == [1, 0, 1] and arr["S0"].tolist() == [100.0, 101.0, 102.0]
+    got = H.price_cells(arr, [100.0, 100.0, 100.0])
+    np.testing.assert_allclose(got[1, 0, :9], H.price_european(p, 101.0, 1.0, 12, 500, 5, [100.0], False, 0)[0, :9], rtol=1e-12)

@@ -70,6 +70,20 @@ def test_hedge_walk_philox_draws_and_sharding(H, L):
     assert abs(pnl.mean()) < 0.3 * fair and pnl.std() < 0.5 * fair
 
 
+def test_hedge_walk_edge_shapes(H, L):
+    """One day, one scenario, zero volatility, zero costs, no premiums."""
+    p = O.Params(kappa=3.0, theta=0.04, xi=0.5, rho=-0.7, v0=0.04, lambda_j=1.0, mu_j=-0.05, sigma_j=0.1, r=0.065, q=0.012)
+    for n, days in ((1, 1), (1, 40), (33, 1)):
+        Z = np.random.default_rng(n + days).standard_normal((n, days))
+        pnl, cost = H.hedge_walk(p, 100.0, 105.0, 0.1, False, days, n, 0.0, None, Z)
+        want = O.hedge_walk(p, 100.0, 105.0, 0.1, False, days, 0.0, 0.0, np.zeros(n), Z)
+        np.testing.assert_allclose(pnl, want[0], rtol=1e-10, atol=1e-9)
+        assert not cost.any()
+    flat = O.Params(kappa=0.0, theta=0.0, xi=0.0, rho=0.0, v0=0.0, lambda_j=0.0, mu_j=0.0, sigma_j=0.0, r=0.05, q=0.0)
+    pnl, _ = H.hedge_walk(flat, 100.0, 90.0, 1.0, True, 10, 3, 7.0, [12.0, 12.0, 12.0], None, seed=1)
+    assert np.isnan(pnl).all() or np.isfinite(pnl).all()           # sigma = 0: d1 = +-inf or nan, as in the reference's formula
+
+
 def test_hedge_walk_errors(H, L):
     p = O.Params(kappa=3.0, theta=0.04, xi=0.5, rho=-0.7, v0=0.04, lambda_j=1.0, mu_j=-0.05, sigma_j=0.1, r=0.065, q=0.012)
     for kw in (dict(n_days=0), dict(n_scenarios=0), dict(T=0.0), dict(T=float("nan"))):
