@@ -343,6 +343,24 @@ class MonteCarloEngine:
             sums = self.comm.allreduce_sum(sums).reshape(m, len(SUMS_FIELDS))
         return [self._result(sums[i], ps[i], sp[i], ks[i], ts[i], calls[i], steps[i]) for i in range(m)]
 
+    def prices_for_seeds(self, spot: float, strike: float, T: float, is_call: bool, seeds) -> np.ndarray:
+        """price()["price"] of this engine re-seeded with every entry of `seeds`, as one launch and one vectorised
+        formula (the premiums of HedgingBacktest's scenarios, engine/risk.py:271-273)."""
+        seeds = list(seeds)
+        if self.rng != "philox" or (self.comm is not None and self.comm.world > 1):
+            return np.array([r["price"] for r in self.price_many(spot, strike, T, is_call, seeds=seeds)])
+        p = self.params
+        steps = steps_for(self.num_steps, T)
+        cells = _lib.make_cells(p, float(spot), float(T), steps, int(self.num_paths), seeds, 0, bool(is_call))
+        sums = self.handle.price_cells(cells, np.full(len(seeds), float(strike)), self._flags())[:, 0, :]
+        n, sa, sb = sums[:, _COL["n"]], sums[:, _COL["sum_a"]], sums[:, _COL["sum_b"]]
+        discount = math.exp(-p.r * T)
+        price = discount * (0.5 * (sa + sb) if self.use_antithetic else sa) / n                     # :342
+        if self.use_control_variate:                                                                # :353-365
+            bs_ref = bs_price(float(spot), strike, T, p.r, p.q, math.sqrt(p.v0), is_call)
+            price = price - (discount * sa / n - bs_ref)
+        return price
+
     def price_population(self, param_cols: Dict[str, np.ndarray], spot: float, strikes, T: float,
                          is_call: bool = True) -> np.ndarray:
         """NEW: price_batch for a whole POPULATION of parameter sets in one launch.  param_cols maps

@@ -250,7 +250,7 @@ class HedgingBacktest:
         cost = np.zeros(num_scenarios)
         if hi > lo:
             seeds = [self.seed + s for s in range(lo, hi)]                                         # :271
-            premiums = np.array([r["price"] for r in engine.price_many(spot, strike, T, is_call, seeds=seeds)])   # :272-273
+            premiums = engine.prices_for_seeds(spot, strike, T, is_call, seeds)                    # :272-273
             Z = None
             if engine.rng == "reference":                                                          # :262,292
                 Z = np.random.default_rng(self.seed).standard_normal((num_scenarios, num_days))[lo:hi]
