@@ -9,7 +9,7 @@
 namespace b200mc {
 
 enum { MB_FFMA = 0, MB_IMAD_WIDE = 1, MB_LOP3 = 2, MB_MUFU_EX2 = 3, MB_MUFU_SIN = 4, MB_IADD3 = 5, MB_PHILOX = 6,
-       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_COUNT = 15 };
+       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_FFMA2 = 15, MB_COUNT = 16 };
 
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, const __grid_constant__ PhiloxKey key,
@@ -32,6 +32,20 @@ __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, co
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += a[k];
         if (s == 123.456f) sink[0] = t;
+    } else if constexpr (WHICH == MB_FFMA2) {
+        // packed fp32 (fma.rn.f32x2 -> FFMA2): counted as INSTRUCTIONS (each does two FMAs per lane)
+        unsigned long long a[8];
+        const unsigned long long b = 0x3f8000013f800001ull + (seed & 1), c = 0x3380000033800000ull;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = ((unsigned long long)__float_as_uint((float)(t + k)) << 32) | __float_as_uint((float)(t + k + 1));
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[k]) : "l"(b), "l"(c));
+        }
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s ^= a[k];
+        if (s == 0x12345ull) sink[0] = t;
     } else if constexpr (WHICH == MB_IMAD_WIDE) {
         uint32_t a[8];
 #pragma unroll
@@ -245,7 +259,8 @@ extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double 
         case 11: mb_launch<11>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         case 12: mb_launch<12>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         case 13: mb_launch<13>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        default: mb_launch<14>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 14: mb_launch<14>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        default: mb_launch<15>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         }
         B200MC_CUDA(h, cudaGetLastError());
         B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
