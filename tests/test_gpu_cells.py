@@ -137,3 +137,27 @@ def test_cells_edge_shapes(H, L):
     assert arr.shape == (3,) and arr["is_call"].tolist() == [1, 0, 1] and arr["S0"].tolist() == [100.0, 101.0, 102.0]
     got = H.price_cells(arr, [100.0, 100.0, 100.0])
     np.testing.assert_allclose(got[1, 0, :9], H.price_european(p, 101.0, 1.0, 12, 500, 5, [100.0], False, 0)[0, :9], rtol=1e-12)
+
+
+def test_population_and_seed_batches_equal_the_scalar_calls(H, L):
+    """MonteCarloEngine.price_population (a DE generation in one launch) == price_batch per candidate, and
+    prices_for_seeds (the hedging premiums) == price() per seed."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    ks = np.array([21500.0, 22500.0, 23500.0, 24000.0])
+    cols = dict(kappa=np.array([3.0, 1.0, 5.0]), theta=np.array([0.04, 0.02, 0.09]), xi=np.array([0.5, 0.6, 0.2]),
+                rho=np.array([-0.7, -0.3, -0.1]), v0=np.array([0.04, 0.05, 0.01]), lambda_j=0.0, mu_j=0.0, sigma_j=0.01,
+                r=0.065, q=0.012)
+    for is_call in (True, False):
+        eng = MonteCarloEngine(SVJParams(), num_paths=20_000, num_steps=50, handle=H)
+        got = eng.price_population(cols, 22500.0, ks, 0.08, is_call)
+        assert got.shape == (3, 4)
+        for s_ in range(3):
+            p = SVJParams(kappa=cols["kappa"][s_], theta=cols["theta"][s_], xi=cols["xi"][s_], rho=cols["rho"][s_],
+                          v0=cols["v0"][s_], lambda_j=0.0, mu_j=0.0, sigma_j=0.01, r=0.065, q=0.012)
+            want = [r_["price"] for r_ in MonteCarloEngine(p, num_paths=20_000, num_steps=50, handle=H).price_batch(22500.0, ks, 0.08, is_call)]
+            np.testing.assert_allclose(got[s_], want, rtol=1e-10, atol=1e-9)
+    eng = MonteCarloEngine(SVJParams(), num_paths=5_000, handle=H)
+    seeds = [42, 43, 1000, 2 ** 40]
+    got = eng.prices_for_seeds(22500.0, 22000.0, 0.25, False, seeds)
+    want = [MonteCarloEngine(SVJParams(), num_paths=5_000, seed=s_, handle=H).price(22500.0, 22000.0, 0.25, False)["price"] for s_ in seeds]
+    np.testing.assert_allclose(got, want, rtol=1e-12)
