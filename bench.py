@@ -267,7 +267,15 @@ def run_b200(args):
     comm = None
     if world > 1:
         from monte_carlo_option_simulator_b200.dist import PeerComm
-        comm = PeerComm(h) if use_peer else TorchComm()
+        if use_peer:
+            try:
+                comm = PeerComm(h)              # raises on ALL ranks when CUDA IPC / P2P is not available on any of them
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] {e}; using the NCCL all-reduce", file=sys.stderr, flush=True)
+                use_peer = False
+        if not use_peer:
+            comm = TorchComm()
 
     def step(i):
         h.price_european(p, SPOT, T, N_STEPS, n, 42 + i, [STRIKE], True, flags, bumps, path_offset=rank * n,

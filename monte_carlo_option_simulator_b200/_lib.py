@@ -255,6 +255,8 @@ class Handle:
 
     # -- exchange over NVLink peer memory (csrc/peer.cu) ----------------------------------------------------
     def peer_create(self) -> bytes:
+        if os.environ.get("B200MC_PEER_DISABLE_RANK") == os.environ.get("RANK", "0"):     # fault injection for the fallback
+            raise B200MCError(ECUDA, "peer exchange disabled on this rank (B200MC_PEER_DISABLE_RANK)")
         buf = (C.c_ubyte * 64)()
         self._check(self.lib.b200mc_peer_create(self.h, buf))
         return bytes(buf)

@@ -78,11 +78,35 @@ class PeerComm(TorchComm):
     def __init__(self, handle, group=None):
         super().__init__(group)
         self.handle = handle
-        mine = handle.peer_create()
+        # Every step is agreed on by all ranks before the next collective, so that a rank on which CUDA IPC is not
+        # available (e.g. peers hidden by CUDA_VISIBLE_DEVICES, no P2P) makes ALL ranks raise instead of leaving the
+        # others waiting: callers catch the error and fall back to TorchComm.
+        def agree(ok: bool, what: str):
+            flags = [None] * self.world
+            self._dist.all_gather_object(flags, bool(ok), group=group)
+            if not all(flags):
+                try:
+                    handle.peer_close()
+                except Exception:  # noqa: BLE001
+                    pass
+                raise RuntimeError(f"peer-memory exchange unavailable: {what} failed on rank(s) "
+                                   f"{[r for r, f in enumerate(flags) if not f]}")
+        mine, err = None, None
+        try:
+            mine = handle.peer_create()
+        except Exception as e:  # noqa: BLE001
+            err = e
         handles = [None] * self.world
         self._dist.all_gather_object(handles, mine, group=group)
-        handle.peer_connect(self.rank, self.world, handles)
+        agree(err is None and all(h_ is not None for h_ in handles), "b200mc_peer_create")
+        try:
+            handle.peer_connect(self.rank, self.world, handles)
+        except Exception as e:  # noqa: BLE001
+            err = e
+        agree(err is None, "b200mc_peer_connect (cudaIpcOpenMemHandle)")
         self._dist.barrier(group=group)                     # every buffer is zeroed and mapped before the first store
+        probe = self.allreduce_sum(np.array([1.0, float(self.rank)]))          # one real exchange as a self-test
+        agree(bool(probe[0] == self.world and probe[1] == self.world * (self.world - 1) / 2), "the first exchange")
 
     def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
         """Host arrays of up to 4352 doubles take the same exchange (copy in, one-shot all-reduce, copy out)."""
