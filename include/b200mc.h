@@ -246,12 +246,35 @@ int b200mc_implied_vol(b200mc_handle *h, int64_t n, const double *prices, const 
  * b200mc_price_european_qmc: those draws, device resident, through the fp64 recurrence of
  * b200mc_simulate_given_normals_dev, terminal values reduced on the device; flags: ANTITHETIC only; out[n_strikes]
  * with the price sums of b200mc_sums (Greek fields 0). */
+/* One placement of a Brownian-bridge construction: W[t] = W[l] + ((W[r] - W[l]) * a) / b + sd * z[dim], in construction
+ * order; index 0 is the known W_0 = 0, t in [1, n_steps], every t exactly once, l and r placed earlier (or 0). */
+typedef struct b200mc_bridge_node {
+    int32_t t, l, r, dim;
+    double a, b, sd;
+} b200mc_bridge_node;
 int b200mc_qmc_normals(b200mc_handle *h, int64_t n_paths, uint64_t path_offset, int32_t n_steps, const uint32_t *sv,
                        const uint32_t *shift, int32_t n_dims, int32_t bits, int which, double *out);
 int b200mc_price_european_qmc(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T, int32_t n_steps,
                               int64_t n_paths, uint64_t path_offset, const uint32_t *sv, const uint32_t *shift,
                               int32_t n_dims, int32_t bits, const double *strikes, int32_t n_strikes, int is_call,
                               uint32_t flags, b200mc_sums *out);
+
+/* NumPy's default_rng(seed).random(n), bit for bit, on the device: state = {state_hi, state_lo, inc_hi, inc_lo} of the PCG64
+ * bit generator (NumPy: default_rng(seed).bit_generator.state["state"]), `first` = how many outputs to skip.  out: float64
+ * [n] on the HOST.  (The reference draws its jump uniforms this way, engine/monte_carlo.py:308.) */
+int b200mc_pcg64_random(b200mc_handle *h, const uint64_t state[4], uint64_t first, int64_t n, double *out);
+/* Terminal spots of paths driven by the Sobol point set through a CALLER-SUPPLIED bridge table (nodes[n_nodes], n_nodes ==
+ * n_steps; NULL = the built-in correct bridge): the device-side form of the reference's own use_sobol=True front end
+ * (engine/monte_carlo.py:290-299).  With the table of the reference's brownian_bridge_reorder (:88-145,172-183 -- degenerate,
+ * SURVEY section 0 quirk 1; monte_carlo.reference_bridge_nodes builds it) and Z_jump_host = default_rng(seed + 1).random((n,
+ * steps)) (:308; HOST, [n_paths][n_steps]) -- or, with Z_jump_host NULL, pcg64_state[4] = that generator's state, from which
+ * the same uniforms are produced on the device (both may be NULL when lambda_j == 0) -- the outputs are those of the reference's default
+ * price() inputs (~1e-12), without its seconds of host work.  Blocks of the point set: Z1, Z2 (bridged), jump sizes (plain).
+ * flags: ANTITHETIC -> also S_anti (the -Z1, -Z2, U, -Zjs twin).  S_final / S_anti: float64 [n_paths] on the HOST. */
+int b200mc_qmc_terminal(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T, int32_t n_steps,
+                        int64_t n_paths, uint64_t path_offset, const uint32_t *sv, const uint32_t *shift, int32_t n_dims,
+                        int32_t bits, const b200mc_bridge_node *nodes, int32_t n_nodes, const double *Z_jump_host,
+                        const uint64_t *pcg64_state, uint32_t flags, double *S_final, double *S_anti);
 
 /* Terminal values of the fused simulation (deterministic-mode parity of the fused kernels, and the terminal
  * P&L vector for compute_risk_metrics, engine/risk.py:117).  S_T / S_T_anti / v_T are [n_paths] of `dtype`

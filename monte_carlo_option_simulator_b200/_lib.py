@@ -127,6 +127,9 @@ _PROTOS = {
     "b200mc_qmc_normals": (C.c_int, [_vp, _i64, _u64, _i32, _vp, _vp, _i32, _i32, C.c_int, _vp]),
     "b200mc_price_european_qmc": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _vp, _vp, _i32, _i32,
                                              _vp, _i32, C.c_int, _u32, _vp]),
+    "b200mc_qmc_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _vp, _vp, _i32, _i32, _vp, _i32,
+                                       _vp, _vp, _u32, _vp, _vp]),
+    "b200mc_pcg64_random": (C.c_int, [_vp, _vp, _u64, _i64, _vp]),
     "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                             _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
@@ -181,6 +184,17 @@ def select_stream(params, T: float, n_steps: int, flags: int = 0, bumps: Optiona
     if rc != OK:
         raise B200MCError(rc, (load().b200mc_last_error(None) or b"").decode())
     return int(out.value)
+
+
+# numpy mirror of b200mc_bridge_node
+BRIDGE_DTYPE = np.dtype([("t", "<i4"), ("l", "<i4"), ("r", "<i4"), ("dim", "<i4"), ("a", "<f8"), ("b", "<f8"), ("sd", "<f8")])
+
+
+def pcg64_state(seed) -> np.ndarray:
+    """{state_hi, state_lo, inc_hi, inc_lo} (uint64[4]) of np.random.default_rng(seed)'s PCG64 bit generator."""
+    st = np.random.default_rng(seed).bit_generator.state["state"]
+    m = (1 << 64) - 1
+    return np.array([st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m], dtype=np.uint64)
 
 
 def sobol_tables(n_dims: int, seed: int):
@@ -430,6 +444,34 @@ class Handle:
                                                         int(bits), strikes.ctypes.data, strikes.size, int(bool(is_call)),
                                                         int(flags), out.ctypes.data))
         return out
+
+    def pcg64_random(self, seed, n: int, first: int = 0) -> np.ndarray:
+        """np.random.default_rng(seed).random(first + n)[first:], generated on the device (bitwise)."""
+        st = pcg64_state(seed)
+        out = np.empty(int(n), dtype=np.float64)
+        self._check(self.lib.b200mc_pcg64_random(self.h, st.ctypes.data, int(first), int(n), out.ctypes.data))
+        return out
+
+    def qmc_terminal(self, params, S0, T, n_steps, n_paths, sobol, nodes=None, Z_jump=None, flags=0, path_offset=0,
+                     pcg64_seed=None):
+        """Terminal spots (and the antithetic twin's with ANTITHETIC) of Sobol-driven paths with a caller-supplied bridge
+        table (BRIDGE_DTYPE array in construction order; None = the built-in correct bridge) and, optionally, host jump
+        uniforms [n_paths, n_steps].  Returns (S, S_anti or None), float64 [n_paths]."""
+        sv, shift, bits = sobol
+        n = int(n_paths)
+        S = np.empty(n, dtype=np.float64)
+        A = np.empty(n, dtype=np.float64) if flags & ANTITHETIC else None
+        nd = None if nodes is None else np.ascontiguousarray(nodes, dtype=BRIDGE_DTYPE)
+        zj = None if Z_jump is None else np.ascontiguousarray(Z_jump, dtype=np.float64)
+        if zj is not None and zj.shape != (n, int(n_steps)):
+            raise B200MCError(EINVAL, "Z_jump must be [n_paths, n_steps]")
+        sp = to_params(params)
+        st = None if pcg64_seed is None else pcg64_state(pcg64_seed)      # jump uniforms = default_rng(pcg64_seed).random(...)
+        self._check(self.lib.b200mc_qmc_terminal(self.h, C.byref(sp), float(S0), float(T), int(n_steps), n, int(path_offset),
+                                                  sv.ctypes.data, shift.ctypes.data, sv.shape[0], int(bits), _ptr(nd),
+                                                  0 if nd is None else nd.size, _ptr(zj), _ptr(st), int(flags),
+                                                  S.ctypes.data, _ptr(A)))
+        return S, A
 
     def simulate_terminal(self, params, S0, T, n_steps, n_paths, seed, flags=0, dtype=np.float64, path_offset=0,
                           want_anti=False, want_v=False, dev_ptrs=None):

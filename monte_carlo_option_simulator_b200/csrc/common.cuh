@@ -83,6 +83,10 @@ inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pi
 // asynchronous on the handle's stream; a collective (needs b200mc_peer_connect)
 int peer_allreduce_async(b200mc_handle *h, void *data_dev, int32_t n, bool as_u64);
 
+// pcg64.cu: n outputs of NumPy's PCG64 .random() starting at output index `first` -> out_dev; st = {state_hi, state_lo,
+// inc_hi, inc_lo}; `chunk` consecutive outputs per thread
+int pcg64_uniform_async(b200mc_handle *h, const uint64_t st[4], uint64_t first, int64_t n, int chunk, double *out_dev);
+
 // ---- warp / block reduction of NV doubles, deterministic "last block sums the partials" finish ---------
 template <int NV>
 __device__ __forceinline__ void warp_reduce(double (&v)[NV])

@@ -29,40 +29,64 @@ namespace b200mc {
 constexpr int QMC_PT_MAX = 32;      // paths per CTA tile: 32, 16 or 8 (the largest whose tile leaves >= 4 CTAs per SM)
 constexpr int QMC_THREADS = 256;
 
-struct BridgeNode {                 // node k of the construction: W[t] = wl W[l] + wr W[r] + sd z_k
-    int32_t t, l, r, level;
-    double wl, wr, sd;
-};
+using BridgeNode = b200mc_bridge_node;   // W[t] = W[l] + ((W[r] - W[l]) * a) / b + sd * z[dim]   (index 0 = the known W_0 = 0)
 
-// Breadth-first bridge over the grid 0..n (W[0] = 0 known): the endpoint first, then midpoints of the open intervals.
+// The built-in, CORRECT bridge over the grid 0..n in construction order: the endpoint first (W_n ~ N(0, n)), then the
+// midpoints of the open intervals breadth first: W_m | W_l, W_r ~ N(W_l + (W_r - W_l)(m-l)/(r-l), (m-l)(r-m)/(r-l)).
 static std::vector<BridgeNode> bridge_table(int n)
 {
     std::vector<BridgeNode> nodes;
     nodes.reserve((size_t)n);
-    nodes.push_back({n, 0, 0, 0, 0.0, 0.0, sqrt((double)n)});           // W_n ~ N(0, n)  (l = r = 0: W[0] = 0)
+    nodes.push_back({n, 0, 0, 0, 0.0, 1.0, sqrt((double)n)});
     std::vector<std::pair<int, int>> cur{{0, n}}, next;
-    int level = 1;
     while (!cur.empty()) {
         next.clear();
         for (auto [l, r] : cur) {
             if (r - l <= 1) continue;
             const int m = (l + r) / 2;
-            const double len = (double)(r - l);
-            nodes.push_back({m, l, r, level, (double)(r - m) / len, (double)(m - l) / len,
-                             sqrt((double)(m - l) * (double)(r - m) / len)});
+            nodes.push_back({m, l, r, (int32_t)nodes.size(), (double)(m - l), (double)(r - l),
+                             sqrt((double)(m - l) * (double)(r - m) / (double)(r - l))});
             next.push_back({l, m});
             next.push_back({m, r});
         }
         cur.swap(next);
-        ++level;
     }
     return nodes;
+}
+
+// Nodes in construction order -> nodes grouped by dependency level (a node needs W[l] and W[r] of earlier nodes), so that
+// a level can be built by all threads at once.  Returns false when the table is not a valid construction.
+static bool schedule_nodes(const BridgeNode *in, int n_nodes, int n_steps, std::vector<BridgeNode> &out,
+                           std::vector<int32_t> &level_start)
+{
+    std::vector<int> level_of_index((size_t)n_steps + 1, -1), lvl((size_t)n_nodes, 0);
+    level_of_index[0] = 0;                                   // W_0 = 0 is known from the start
+    int max_level = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+        const BridgeNode &nd = in[k];
+        if (nd.t < 1 || nd.t > n_steps || nd.l < 0 || nd.l > n_steps || nd.r < 0 || nd.r > n_steps || nd.dim < 0 ||
+            nd.dim >= n_steps || !(nd.b != 0.0) || level_of_index[nd.t] >= 0 || level_of_index[nd.l] < 0 ||
+            level_of_index[nd.r] < 0)
+            return false;
+        lvl[k] = 1 + std::max(level_of_index[nd.l], level_of_index[nd.r]);
+        level_of_index[nd.t] = lvl[k];
+        max_level = std::max(max_level, lvl[k]);
+    }
+    out.clear();
+    level_start.clear();
+    for (int L = 1; L <= max_level; ++L) {
+        level_start.push_back((int32_t)out.size());
+        for (int k = 0; k < n_nodes; ++k)
+            if (lvl[k] == L) out.push_back(in[k]);
+    }
+    level_start.push_back((int32_t)out.size());
+    return true;
 }
 
 struct QmcArgs {
     uint64_t path0;
     int64_t n_paths;
-    int32_t n_steps, bits, pitch, n_levels, pt, pad_;
+    int32_t n_steps, bits, pitch, n_levels, pt, n_set;    // n_set: every W[1..n_set] is written by the table
     double sign;                    // +1, or -1 for the antithetic pass (normals negated, uniforms kept)
     double scale;                   // 2^-bits
 };
@@ -125,7 +149,9 @@ k_qmc_block(const __grid_constant__ QmcArgs a, int which, const uint32_t *__rest
                         const BridgeNode nd = nodes[k];
                         double *w = W + (size_t)p * a.pitch;
                         const double wl = nd.l == 0 ? 0.0 : w[nd.l], wr = nd.r == 0 ? 0.0 : w[nd.r];
-                        w[nd.t] = nd.wl * wl + nd.wr * wr + nd.sd * zb[(size_t)p * a.pitch + k];
+                        // the reference's operation order, monte_carlo.py:128-133 (no FMA contraction)
+                        const double mean = __dadd_rn(wl, __ddiv_rn(__dmul_rn(__dadd_rn(wr, -wl), nd.a), nd.b));
+                        w[nd.t] = __dadd_rn(mean, __dmul_rn(nd.sd, zb[(size_t)p * a.pitch + nd.dim]));
                     }
                 }
                 __syncthreads();
@@ -137,7 +163,7 @@ k_qmc_block(const __grid_constant__ QmcArgs a, int which, const uint32_t *__rest
             double v;
             if (which == 0) {
                 const double *w = W + (size_t)p * a.pitch;
-                v = w[t + 1] - (t == 0 ? 0.0 : w[t]);
+                v = (t + 1 <= a.n_set ? w[t + 1] : 0.0) - (t == 0 ? 0.0 : w[t]);
             } else {
                 v = zb[(size_t)p * a.pitch + t];
             }
@@ -189,7 +215,8 @@ struct QmcPlan {
 
 // Tables -> device (inside d_scratch).  Returns the bytes used at the front of the scratch buffer.
 static int qmc_prepare(b200mc_handle *h, int32_t n_steps, const uint32_t *sv, const uint32_t *shift, int32_t n_dims,
-                       int32_t bits, int n_blocks, QmcPlan &pl, size_t extra_bytes, char **extra)
+                       int32_t bits, int n_blocks, QmcPlan &pl, size_t extra_bytes, char **extra,
+                       const BridgeNode *custom = nullptr, int32_t n_custom = 0)
 {
     if (!sv || !shift) return fail(h, B200MC_EINVAL, "sv / shift is NULL");
     if (bits < 1 || bits > 32) return fail(h, B200MC_EINVAL, "bits must be in [1, 32]");
@@ -200,11 +227,12 @@ static int qmc_prepare(b200mc_handle *h, int32_t n_steps, const uint32_t *sv, co
     while (pl.pt > 8 && (size_t)2 * pl.pt * pl.pitch * sizeof(double) > 56 * 1024) pl.pt >>= 1;
     pl.smem = (size_t)2 * pl.pt * pl.pitch * sizeof(double);
     if (pl.smem > (size_t)h->smem_optin - 1024) return fail(h, B200MC_EINVAL, "too many steps for the bridge tile");
-    std::vector<BridgeNode> nodes = bridge_table(n_steps);
+    std::vector<BridgeNode> built, nodes;
     std::vector<int32_t> levels;
-    for (size_t k = 0; k < nodes.size(); ++k)
-        if (k == 0 || nodes[k].level != nodes[k - 1].level) levels.push_back((int32_t)k);
-    levels.push_back((int32_t)nodes.size());
+    if (!custom) built = bridge_table(n_steps);
+    else if (n_custom != n_steps) return fail(h, B200MC_EINVAL, "a bridge table must place every one of the n_steps points");
+    if (!schedule_nodes(custom ? custom : built.data(), n_steps, n_steps, nodes, levels))
+        return fail(h, B200MC_EINVAL, "the bridge table is not a valid construction (indices, order or b == 0)");
     pl.n_levels = (int)levels.size() - 1;
     const size_t nd = (size_t)n_blocks * n_steps;
     const size_t b_sv = nd * bits * 4, b_sh = nd * 4, b_nodes = nodes.size() * sizeof(BridgeNode), b_lv = levels.size() * 4;
@@ -232,7 +260,7 @@ static int qmc_block(b200mc_handle *h, const QmcPlan &pl, int b, uint64_t path0,
 {
     QmcArgs a;
     a.path0 = path0; a.n_paths = n; a.n_steps = pl.n_steps; a.bits = pl.bits; a.pitch = pl.pitch; a.n_levels = pl.n_levels;
-    a.pt = pl.pt; a.pad_ = 0;
+    a.pt = pl.pt; a.n_set = pl.n_steps;
     a.sign = sign;
     a.scale = ldexp(1.0, -pl.bits);
     const int which = b <= 1 ? 0 : (b == 2 ? 1 : 2);
@@ -334,6 +362,63 @@ extern "C" int b200mc_price_european_qmc(b200mc_handle *h, const b200mc_svj_para
         o.n = (double)n_paths;
         o.sum_a = v[0]; o.sum_b = v[1]; o.sum_aa = v[2]; o.sum_bb = v[3]; o.sum_ab = v[4];
         o.sum_s = v[5]; o.sum_ss = v[6]; o.sum_ps = v[7];
+    }
+    return 0;
+}
+
+// Terminal values of paths driven by Sobol points with a caller-supplied bridge table: the device-side form of the
+// reference's OWN use_sobol=True front end (engine/monte_carlo.py:290-299: generate_sobol_normals(n, 3 steps, seed),
+// brownian_bridge_reorder on the first two blocks, the third block as jump sizes, jump uniforms from
+// default_rng(seed + 1).random -- passed in as a host array).  With the reference's (degenerate) table this reproduces the
+// reference's default price() inputs without its 7-11 s of host work per call.
+extern "C" int b200mc_qmc_terminal(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T, int32_t n_steps,
+                                   int64_t n_paths, uint64_t path_offset, const uint32_t *sv, const uint32_t *shift,
+                                   int32_t n_dims, int32_t bits, const b200mc_bridge_node *nodes, int32_t n_nodes,
+                                   const double *Z_jump_host, const uint64_t *pcg64_state, uint32_t flags, double *S_final,
+                                   double *S_anti)
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!p || !S_final) return fail(h, B200MC_EINVAL, "NULL argument");
+    if (n_paths <= 0 || n_steps <= 0) return fail(h, B200MC_EINVAL, "n_paths and n_steps must be positive");
+    if (!(T > 0.0) || !isfinite(T) || !isfinite(S0)) return fail(h, B200MC_EINVAL, "T must be positive and finite, S0 finite");
+    if (path_offset + (uint64_t)n_paths > (1ull << (bits < 1 ? 1 : bits)))
+        return fail(h, B200MC_EINVAL, "the Sobol sequence holds 2^bits points");
+    const bool anti = flags & B200MC_ANTITHETIC;
+    if (anti && !S_anti) return fail(h, B200MC_EINVAL, "B200MC_ANTITHETIC needs S_anti");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    const bool jumps = p->lambda_j * (T / n_steps) > 0.0;
+    const bool own_u = Z_jump_host || pcg64_state;                                   // jump uniforms not from the point set
+    const int nb_sobol = jumps ? (own_u ? 3 : 4) : (p->xi != 0.0 ? 2 : 1);           // blocks taken from the point set
+
+    int64_t chunk = std::max<int64_t>(QMC_PT_MAX, ((int64_t)1 << 27) / n_steps);
+    chunk = std::min(chunk, n_paths);
+    const size_t zbytes = (size_t)chunk * n_steps * 8;
+    const size_t extra_bytes = zbytes * 4 + (size_t)chunk * 8 * 3;                   // [Z1][Z2][Zjs][U][S][A][v]
+    QmcPlan pl;
+    char *extra = nullptr;
+    B200MC_TRY(qmc_prepare(h, n_steps, sv, shift, n_dims, bits, nb_sobol, pl, extra_bytes, &extra, nodes, n_nodes));
+    double *Z[4];
+    for (int b = 0; b < 4; ++b) Z[b] = (double *)(extra + zbytes * b);
+    double *dS = (double *)(extra + zbytes * 4), *dA = dS + chunk, *dV = dA + chunk;
+    for (int64_t done = 0; done < n_paths; done += chunk) {
+        const int64_t n = std::min(chunk, n_paths - done);
+        if (jumps && Z_jump_host)
+            B200MC_CUDA(h, cudaMemcpyAsync(Z[3], Z_jump_host + (size_t)done * n_steps, (size_t)n * n_steps * 8,
+                                           cudaMemcpyHostToDevice, h->stream));
+        else if (jumps && pcg64_state)       // row i of .random((n, steps)) = outputs [i steps, (i + 1) steps): one thread per row
+            B200MC_TRY(pcg64_uniform_async(h, pcg64_state, (uint64_t)(path_offset + done) * (uint64_t)n_steps,
+                                           n * (int64_t)n_steps, n_steps, Z[3]));
+        for (int pass = 0; pass < (anti ? 2 : 1); ++pass) {
+            const double sign = pass ? -1.0 : 1.0;                                   // monte_carlo.py:318-324
+            for (int b = 0; b < nb_sobol; ++b)
+                if (!(pass && b == 3)) B200MC_TRY(qmc_block(h, pl, b, path_offset + (uint64_t)done, n, sign, Z[b]));
+            B200MC_TRY(b200mc_simulate_given_normals_dev(h, p, S0, T, n, n_steps, Z[0], nb_sobol >= 2 ? Z[1] : Z[0],
+                                                         jumps ? Z[3] : Z[0], jumps ? Z[2] : Z[0], 0, pass ? dA : dS, dV,
+                                                         nullptr));
+        }
+        B200MC_CUDA(h, cudaMemcpyAsync(S_final + done, dS, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        if (anti) B200MC_CUDA(h, cudaMemcpyAsync(S_anti + done, dA, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
     }
     return 0;
 }

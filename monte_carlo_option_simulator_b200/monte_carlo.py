@@ -24,6 +24,7 @@ SURVEY.md section 0 quirk 3); the reference's degenerate Sobol/Brownian-bridge p
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
 from typing import Dict, List, Optional
@@ -133,6 +134,32 @@ def brownian_bridge_reorder(normals: np.ndarray, num_steps: int) -> np.ndarray:
         W[:, j] = mean + math.sqrt(max(var, 0)) * normals[:, dim]
         known[j] = True
     return np.diff(W, axis=1)
+
+
+@functools.lru_cache(maxsize=64)
+def reference_bridge_nodes(num_steps: int) -> np.ndarray:
+    """The placements of brownian_bridge_reorder above as a b200mc_bridge_node table (_lib.BRIDGE_DTYPE, construction
+    order): W[t] = W[l] + ((W[r] - W[l]) * a) / b + sd * z[dim], the reference's arithmetic (monte_carlo.py:128-133) with
+    its neighbour search (:172-183).  A right neighbour that has not been placed yet is read as the zero it still holds
+    (index 0) -- that is the first placement, the endpoint against itself, whose variance is therefore 0 (quirk 1)."""
+    dt = 1.0 / num_steps
+    known = np.zeros(num_steps + 2, dtype=bool)
+    out = np.zeros(num_steps, dtype=_lib.BRIDGE_DTYPE)
+    for dim, tidx in enumerate(_bb_ordering(num_steps)):
+        j = tidx + 1
+        lo = np.flatnonzero(known[1:j + 1])
+        hi = np.flatnonzero(known[j:num_steps])
+        left = int(lo[-1]) + 1 if lo.size else 0
+        right = int(hi[0]) + j if hi.size else num_steps
+        t, tl, tr = j * dt, left * dt, right * dt
+        if right > left:
+            a, b, var = t - tl, tr - tl, (t - tl) * (tr - t) / (tr - tl)
+        else:
+            a, b, var = 0.0, 1.0, t - tl
+        r_idx = right if (right == 0 or known[right]) else 0
+        out[dim] = (j, left, r_idx, dim, a, b, math.sqrt(max(var, 0)))
+        known[j] = True
+    return out
 
 
 def _reference_draws(seed: int, n: int, steps: int, use_sobol: bool):
@@ -534,8 +561,19 @@ class MonteCarloEngine:
         p = self.params
         n = int(self.num_paths)
         steps = steps_for(self.num_steps, T)
-        Z1, Z2, Zj, Zjs = _reference_draws(self.seed, n, steps, self.use_sobol)
         h = self.handle
+        if self.use_sobol and hasattr(h, "qmc_terminal") and os.environ.get("B200MC_REFERENCE_SOBOL", "device") == "device":
+            # the reference's Sobol front end (:290-299,308) on the device: SciPy's scrambled points (bitwise), norm.ppf,
+            # the reference's own bridge table, NumPy's PCG64 uniforms for the jumps -- nothing is drawn on the host
+            key = (steps, self.seed)
+            cache = getattr(self, "_ref_sobol", None)
+            if cache is None or cache[0] != key:
+                self._ref_sobol = cache = (key, _lib.sobol_tables(3 * steps, self.seed), reference_bridge_nodes(steps))
+            # (the jump uniforms of :308, default_rng(seed + 1).random((n, steps)), are reproduced on the device too)
+            S, S_anti = h.qmc_terminal(p, float(spot), T, steps, n, cache[1], cache[2], None,
+                                       ANTITHETIC if self.use_antithetic else 0, pcg64_seed=self.seed + 1)
+            return steps, S, S_anti
+        Z1, Z2, Zj, Zjs = _reference_draws(self.seed, n, steps, self.use_sobol)
         S = h.simulate_given_normals(p, float(spot), T, Z1, Z2, Zj, Zjs, steps)[0]
         S_anti = None
         if self.use_antithetic:                                                # :318-324

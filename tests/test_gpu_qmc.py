@@ -110,3 +110,45 @@ def test_heston_qmc_within_mc_error_of_plain_mc(H, L):
     mc = MonteCarloEngine(HES, 4_000_000, 63, 3, use_control_variate=False, handle=H).price(22500.0, 22500.0, 0.25)
     q = MonteCarloEngine(HES, 65536, 63, 3, use_control_variate=False, rng="sobol", handle=H).price(22500.0, 22500.0, 0.25)
     assert abs(q["price"] - mc["price"]) < 4 * mc["std_error"] + 0.002 * mc["price"]
+
+
+@pytest.mark.parametrize("pname", ["svj", "heston", "gbm"])
+def test_reference_sobol_front_end_on_the_device(H, L, pname, monkeypatch):
+    """rng="reference", use_sobol=True -- the reference's DEFAULT configuration: the device-side front end (SciPy's points,
+    norm.ppf, the reference's own bridge table, host PCG64 jump uniforms) gives the results of the host front end
+    (the reference's NumPy/SciPy code path, pinned to the reference's golden prices elsewhere)."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine
+    p = {"svj": SVJ, "heston": HES, "gbm": GBM}[pname]
+    for n, steps_T in ((3000, 0.25), (257, 0.04)):
+        kw = dict(num_paths=n, num_steps=252, seed=13, use_sobol=True, rng="reference", handle=H)
+        monkeypatch.setenv("B200MC_REFERENCE_SOBOL", "host")
+        want = MonteCarloEngine(p, **kw).price(22500.0, 22000.0, steps_T, False)
+        want_b = MonteCarloEngine(p, **kw).price_batch(22500.0, [21000.0, 23000.0], steps_T, True)
+        monkeypatch.setenv("B200MC_REFERENCE_SOBOL", "device")
+        got = MonteCarloEngine(p, **kw).price(22500.0, 22000.0, steps_T, False)
+        got_b = MonteCarloEngine(p, **kw).price_batch(22500.0, [21000.0, 23000.0], steps_T, True)
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k] == pytest.approx(want[k], rel=1e-9, abs=1e-9), (pname, k)
+        for g_, w_ in zip(got_b, want_b):
+            assert g_ == pytest.approx(w_, rel=1e-9, abs=1e-9)
+    # the degenerate bridge as a table: the step normals sum to 0 on every path (W_T == 0, SURVEY quirk 1)
+    from monte_carlo_option_simulator_b200.monte_carlo import reference_bridge_nodes
+    with pytest.raises(L.B200MCError, match="bridge table"):
+        bad = reference_bridge_nodes(10).copy()
+        bad[3]["t"] = bad[2]["t"]
+        H.qmc_terminal(GBM, 100.0, 1.0, 10, 8, L.sobol_tables(30, 1), bad)
+
+
+def test_numpy_pcg64_uniforms_on_the_device_bitwise(H, L):
+    """default_rng(seed).random(...) -- the reference's jump uniforms (monte_carlo.py:308) -- reproduced on the device."""
+    for seed, first, n in ((43, 0, 1), (43, 0, 1000), (0, 5, 64), (2 ** 63 + 11, 123_457, 10_001), (7, 2 ** 33 + 3, 500)):
+        want_rng = np.random.default_rng(seed)
+        if first < 10 ** 7:
+            want = want_rng.random(first + n)[first:]
+        else:
+            want_rng.bit_generator.advance(first)
+            want = want_rng.random(n)
+        np.testing.assert_array_equal(H.pcg64_random(seed, n, first), want)
+    with pytest.raises(L.B200MCError):
+        H.pcg64_random(1, 0)

@@ -110,6 +110,22 @@ def test_reference_front_end_sobol_and_bridge(golden, garr):
         np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-15)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 10, 63, 64, 250])
+def test_reference_bridge_as_a_node_table(n):
+    """The table handed to the device (b200mc_bridge_node) reproduces the reference's brownian_bridge_reorder bit for bit,
+    degeneracy included: the first placement is the endpoint with sd == 0."""
+    g = np.random.default_rng(n)
+    z = g.standard_normal((6, n))
+    nodes = MC.reference_bridge_nodes(n)
+    W = np.zeros((6, n + 1))
+    for nd in nodes:
+        W[:, nd["t"]] = W[:, nd["l"]] + ((W[:, nd["r"]] - W[:, nd["l"]]) * nd["a"]) / nd["b"] + nd["sd"] * z[:, nd["dim"]]
+    np.testing.assert_array_equal(np.diff(W, axis=1), MC.brownian_bridge_reorder(z, n))
+    np.testing.assert_array_equal(np.diff(W, axis=1), O.bb_reorder(z, n))
+    assert nodes[0]["t"] == n and nodes[0]["sd"] == 0.0 and sorted(nodes["t"].tolist()) == list(range(1, n + 1))
+    assert nodes.dtype.itemsize == 40
+
+
 @pytest.mark.parametrize("anti", [False, True])
 @pytest.mark.parametrize("cv", [False, True])
 @pytest.mark.parametrize("is_call", [True, False])
