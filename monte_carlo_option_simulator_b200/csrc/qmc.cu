@@ -225,6 +225,7 @@ static int qmc_prepare(b200mc_handle *h, int32_t n_steps, const uint32_t *sv, co
     pl.pitch = (n_steps + 1) | 1;                       // odd pitch (in doubles): conflict-free with lanes over paths
     pl.pt = QMC_PT_MAX;                                 // 128 KB tiles (1 CTA per SM) were latency bound: 0.62 ms per 64k x 250
     while (pl.pt > 8 && (size_t)2 * pl.pt * pl.pitch * sizeof(double) > 56 * 1024) pl.pt >>= 1;
+    while (pl.pt > 1 && (size_t)2 * pl.pt * pl.pitch * sizeof(double) > (size_t)h->smem_optin - 1024) pl.pt >>= 1;   // very long paths
     pl.smem = (size_t)2 * pl.pt * pl.pitch * sizeof(double);
     if (pl.smem > (size_t)h->smem_optin - 1024) return fail(h, B200MC_EINVAL, "too many steps for the bridge tile");
     std::vector<BridgeNode> built, nodes;

@@ -152,3 +152,20 @@ def test_numpy_pcg64_uniforms_on_the_device_bitwise(H, L):
         np.testing.assert_array_equal(H.pcg64_random(seed, n, first), want)
     with pytest.raises(L.B200MCError):
         H.pcg64_random(1, 0)
+
+
+def test_chunked_runs_equal_offset_runs(H, L):
+    """Long paths force the path range through several chunks (2^27 / n_steps paths each for the terminal entry point, 2^28 /
+    n_steps for the sums): the result must equal that of separate calls on sub-ranges (which are single chunks)."""
+    steps, n = 2000, 150_000                       # chunks of 67_108 paths (terminal) / 134_217 (sums)
+    tables = L.sobol_tables(steps, 3)
+    p = GBM
+    S, A = H.qmc_terminal(p, 100.0, 1.0, steps, n, tables, None, None, L.ANTITHETIC)
+    parts = [H.qmc_terminal(p, 100.0, 1.0, steps, hi - lo, tables, None, None, L.ANTITHETIC, path_offset=lo)
+             for lo, hi in ((0, 60_000), (60_000, 120_000), (120_000, n))]
+    np.testing.assert_array_equal(S, np.concatenate([q[0] for q in parts]))
+    np.testing.assert_array_equal(A, np.concatenate([q[1] for q in parts]))
+    whole = H.price_european_qmc(p, 100.0, 1.0, steps, n, tables, [100.0], True, L.ANTITHETIC)
+    pay_a, pay_b = np.maximum(S - 100.0, 0.0), np.maximum(A - 100.0, 0.0)
+    np.testing.assert_allclose(whole[0, :6], [n, pay_a.sum(), pay_b.sum(), (pay_a ** 2).sum(), (pay_b ** 2).sum(),
+                                              (pay_a * pay_b).sum()], rtol=1e-12)
