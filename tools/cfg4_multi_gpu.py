@@ -79,6 +79,17 @@ for name, comm in (("nccl, host-driven select", HostLoop()), ("peer memory, devi
         print(f"   Student-t(3) x 3,000,001 in shards {np.diff(cuts).tolist()}: VaR {got['var']:.6f} CVaR {got['cvar']:.6f} tail index "
               f"{got['tail_index']:.4f} kurtosis {got['kurtosis']:.2f}; equals the single-GPU metrics on every rank: {bool(flag.item())}", flush=True)
     assert flag.item() == 1.0
+    # an EMPTY shard on the last rank (a rank without data still takes part in every exchange)
+    y = x[:100_001]
+    mine = y if rank == 0 else (y[:0] if rank == world - 1 else y[:0])
+    want = dict(zip(KEYS, h.risk_metrics(y, 0.95)))
+    got = compute_risk_metrics_sharded(mine, 0.95, comm=comm, handle=h)
+    ok = all(abs(got[k] - want[k]) <= 1e-10 * max(1.0, abs(want[k])) for k in got)
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"   all data on rank 0, empty shards elsewhere: equals the single-GPU metrics on every rank: {bool(flag.item())}", flush=True)
+    assert flag.item() == 1.0
 if rank == 0:
     print("CFG4 MULTI-GPU OK")
 dist.barrier()
