@@ -1,0 +1,36 @@
+"""CPU: the inspection tools bench.py relies on still understand the shipped library (no GPU needed: cuobjdump reads the
+.so).  Guards the instruction roofline against silently falling back to its built-in constants after a kernel edit."""
+import os
+import shutil
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.mark.skipif(not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")), reason="no cuobjdump")
+def test_sass_mix_of_the_headline_kernel():
+    import sass_mix
+    mixes = sass_mix.mix("k_europeanILi0ELb0ELb1EfLb1E")          # k_european<GBM, !ANTI, GREEKS, float, SINGLE>
+    assert len(mixes) == 1
+    m = list(mixes.values())[0]
+    # one Philox4x32-10 call per loop iteration = 8 steps: 4 Box-Muller pairs x 4 MUFU, at most 20 wide multiplies
+    assert m["philox_calls"] == 1 and m["xu"] == 16 and 17 <= m["imad_wide"] <= 20
+    assert 80 <= m["total"] <= 110, m           # 94 today; a jump means the hot loop changed -- re-measure before shipping
+
+
+def test_ptxas_logs_report_no_spills_in_the_hot_kernels():
+    """Registers / spills of the fused kernels as ptxas reported them at build time (csrc/build/*.ptxas.log)."""
+    import re
+    log = os.path.join(ROOT, "monte_carlo_option_simulator_b200", "csrc", "build", "european.ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("library was not built in this checkout")
+    text = open(log).read()
+    blocks = re.findall(r"Compiling entry function '(\w+)'.*?(\d+) bytes spill stores.*?Used (\d+) registers", text, flags=re.S)
+    assert len(blocks) >= 64
+    for name, spill, regs in blocks:
+        if "k_europeanILi0E" in name and "EfLb1E" in name:            # GBM, fp32, single strike: the headline family
+            assert int(spill) == 0 and int(regs) <= 128, (name, spill, regs)
