@@ -43,6 +43,13 @@ from engine.monte_carlo import MonteCarloEngine as RefEngine  # noqa: E402
 
 svj = SVJParams()
 ref_price = RefEngine(svj, num_paths=50_000, use_sobol=False, use_control_variate=False).price(22500.0, 22500.0, 0.25, True)
+# the reference's DEFAULT configuration (Sobol + antithetic + control variate), unpatched, for the exact comparison below
+t0 = time.time()
+ref_default = RefEngine(svj, num_paths=50_000).price(22500.0, 22500.0, 0.25, True)
+ref_default_put = RefEngine(svj, num_paths=50_000, seed=7).price(22500.0, 23000.0, 0.08, False)
+t_ref_default = (time.time() - t0) / 2
+from engine.risk import StressTestEngine as RefStress  # noqa: E402
+ref_stress = RefStress(svj, num_paths=20_000).full_stress_report(22500.0, 22500.0, 0.08, True)
 
 from monte_carlo_option_simulator_b200 import patch_reference  # noqa: E402
 done = patch_reference("engine")
@@ -60,6 +67,26 @@ z = abs(ours["price"] - ref_price["price"]) / math.hypot(ours["std_error"], ref_
 print(f"[price] reference {ref_price['price']:.3f} +- {ref_price['std_error']:.3f} (50k paths, CPU)   "
       f"patched {ours['price']:.3f} +- {ours['std_error']:.3f} (2M paths, GPU)   |z| = {z:.2f}")
 assert z < 3.5
+
+# rng="reference": the reference's own draws regenerated on the device -> the reference's numbers, exactly
+t0 = time.time()
+ours_default = MonteCarloEngine(svj, num_paths=50_000, rng="reference").price(22500.0, 22500.0, 0.25, True)
+ours_default_put = MonteCarloEngine(svj, num_paths=50_000, seed=7, rng="reference").price(22500.0, 23000.0, 0.08, False)
+t_ours_default = (time.time() - t0) / 2
+for a, b in ((ref_default, ours_default), (ref_default_put, ours_default_put)):
+    for k, v in a.items():
+        assert abs(b[k] - v) <= 1e-9 * max(1.0, abs(v)), (k, v, b[k])
+from engine.risk import StressTestEngine as OurStress  # noqa: E402
+ours_stress = OurStress(svj, num_paths=20_000, rng="reference").full_stress_report(22500.0, 22500.0, 0.08, True)
+for sec in ("spot_shocks", "vol_shocks"):
+    for ra, rb in zip(ref_stress[sec], ours_stress[sec]):
+        for k, v in ra.items():
+            assert abs(rb[k] - v) <= 1e-8 * max(1.0, abs(v)), (sec, k, v, rb[k])
+for k, v in ref_stress["jump_scenario"].items():
+    assert abs(ours_stress["jump_scenario"][k] - v) <= 1e-8 * max(1.0, abs(v)), (k, v)
+print(f"[exact] default-flag price() (Sobol + antithetic + CV, 50k paths): reference {ref_default['price']:.9f} "
+      f"({t_ref_default:.2f} s per call, CPU)   patched rng=reference {ours_default['price']:.9f} ({t_ours_default * 1e3:.1f} ms per call)"
+      f"   every key of two price() dicts and of a full stress report equal to 1e-9 / 1e-8")
 
 app = engine.app
 calls = (("price", app.price_option, app.PriceRequest(spot=22500.0, strike=22500.0, T=0.08, num_paths=50_000)),
