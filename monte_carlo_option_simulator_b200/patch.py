@@ -112,7 +112,7 @@ def _population_de(scipy_de):
 
 
 def patch_reference(package: str = "engine", batch_calibration: bool = True, batch_scenarios: bool = True,
-                    batch_population: bool = False) -> List[str]:
+                    batch_population: bool = False, rng: str = None) -> List[str]:
     """Returns the list of 'module.attribute' names that were rebound.  batch_calibration: also replace the two
     calibration objectives by versions that price all strikes of a candidate in one launch.
     batch_scenarios: also replace StressTestEngine / HedgingBacktest / LiquidityStress (engine/risk.py:23-337) by the
@@ -121,7 +121,16 @@ def patch_reference(package: str = "engine", batch_calibration: bool = True, bat
     batch_population (opt-in, needs batch_calibration): also wrap engine.calibration.differential_evolution so that a
     whole DE generation is ONE launch (SciPy's vectorized=True, updating='deferred').  This changes the optimiser's
     update rule from SciPy's default 'immediate' to 'deferred', so the calibrated parameters differ from the reference's
-    run (both are noisy optimisers of the same objective); hence not the default."""
+    run (both are noisy optimisers of the same objective); hence not the default.
+    rng: sets the default draw mode (the B200MC_RNG environment variable) for the engines the reference constructs."""
+    if rng is not None:
+        # default draw mode of every engine the reference's code constructs from now on (it never passes rng=):
+        # "philox" device draws (statistical agreement), "reference" the reference's own draws (its numbers to ~1e-9;
+        # at GPU speed for its default use_sobol=True flags), "sobol" the working quasi-Monte Carlo front end
+        if rng not in ("philox", "reference", "sobol"):
+            raise ValueError("rng must be 'philox', 'reference' or 'sobol'")
+        import os
+        os.environ["B200MC_RNG"] = rng
     done = []
 
     def rebind(modname, attr, obj):

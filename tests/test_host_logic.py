@@ -3,6 +3,7 @@ patch_reference) against the oracle and the golden fixtures.  The CUDA library i
 that produces b200mc_sums from the ORACLE's terminal spots, so that the algebra from sums to result dictionaries
 (including the reference's pseudo control variate, quirk 2) is checked against MonteCarloOracle / GreeksOracle."""
 import math
+import os
 import sys
 import types
 
@@ -218,6 +219,17 @@ def test_patch_reference_rebinds_import_by_name_sites():
     sys.modules["fakeengine"] = pkg
     try:
         from monte_carlo_option_simulator_b200 import risk as R
+        with pytest.raises(ValueError):
+            patch_reference("fakeengine", rng="mt19937")
+        old = os.environ.get("B200MC_RNG")
+        try:
+            patch_reference("fakeengine", batch_scenarios=False, rng="reference")
+            assert MonteCarloEngine(SVJParams()).rng == "reference"
+        finally:
+            if old is None:
+                os.environ.pop("B200MC_RNG", None)
+            else:
+                os.environ["B200MC_RNG"] = old
         done = patch_reference("fakeengine", batch_scenarios=False)
         assert not isinstance(mods["app"].StressTestEngine, type)       # caller classes: left alone on request
         assert not isinstance(mods["risk"].HedgingBacktest, type)
