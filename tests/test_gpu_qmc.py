@@ -169,3 +169,48 @@ def test_chunked_runs_equal_offset_runs(H, L):
     pay_a, pay_b = np.maximum(S - 100.0, 0.0), np.maximum(A - 100.0, 0.0)
     np.testing.assert_allclose(whole[0, :6], [n, pay_a.sum(), pay_b.sum(), (pay_a ** 2).sum(), (pay_b ** 2).sum(),
                                               (pay_a * pay_b).sum()], rtol=1e-12)
+
+
+def _sobol_model(tables, n, off):
+    """Points off .. off + n - 1 of the scrambled sequence from its direction numbers: shift ^ XOR_{b in gray(i)} sv[:, b]
+    (what the device evaluates; equal to SciPy's Sobol.random, checked below where SciPy is fast enough to ask)."""
+    sv, shift, bits = tables
+    out = np.empty((n, sv.shape[0]))
+    for r, i in enumerate(range(off, off + n)):
+        gray, x, b = i ^ (i >> 1), shift.copy(), 0
+        while gray:
+            if gray & 1:
+                x ^= sv[:, b]
+            gray >>= 1
+            b += 1
+        out[r] = x.astype(np.float64) * 2.0 ** -bits
+    return out
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_device_draws_random_shapes(H, L, case):
+    """Random step counts (the bridge over non-powers of two, tiles of 32 / 16 / 8 / fewer paths), path counts and offsets
+    deep into the sequence: bridged normals, plain normals and uniforms against the textbook bridge over the points of the
+    sequence (SciPy's, where SciPy can fast-forward in reasonable time; its direction numbers otherwise)."""
+    import warnings
+    from scipy.stats import norm
+    from scipy.stats.qmc import Sobol
+    g = np.random.default_rng(4000 + case)
+    steps = int(g.choice([1, 2, 3, 5, 31, 33, 100, 251, 400, 777, 1500, 3000])) if case < 6 else int(g.integers(1, 500))
+    n = int(g.integers(1, 120))
+    off = int(g.choice([0, 1, 1023, 2 ** 20 + 17, 2 ** 29 - n - 1]))
+    seed = int(g.integers(0, 2 ** 31))
+    nb = 1 if steps > 800 else 4
+    tables = L.sobol_tables(nb * steps, seed)
+    u = _sobol_model(tables, n, off)
+    if off <= 1023:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            np.testing.assert_array_equal(u, Sobol(d=nb * steps, scramble=True, seed=seed).random(off + n)[off:])
+    u = np.clip(u, 1e-10, 1 - 1e-10)
+    np.testing.assert_allclose(H.qmc_normals(tables, n, steps, L.Z1, path_offset=off), O.qmc_bridge(norm.ppf(u[:, :steps])),
+                               rtol=1e-11, atol=1e-11)
+    if nb == 4:
+        np.testing.assert_allclose(H.qmc_normals(tables, n, steps, L.ZJUMP_SIZE, path_offset=off), norm.ppf(u[:, 2 * steps:3 * steps]),
+                                   rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(H.qmc_normals(tables, n, steps, L.ZJUMP_U, path_offset=off), u[:, 3 * steps:])
