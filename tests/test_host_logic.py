@@ -466,3 +466,44 @@ def test_hedging_backtest_host_logic(risk_golden):
     # default day count: max(int(T * 252), 1)
     got = bt.run_backtest(c["spot"], c["strike"], 0.003, True, num_scenarios=4, num_mc_paths=50)
     assert got["num_scenarios"] == 4
+
+
+# ---------------------------------------------------------------------------------------------- 8(f)-3: surface host logic
+class OracleIvHandle:
+    """Stands in for _lib.Handle.implied_vol: the oracle's brentq per element, NaN for None."""
+
+    def implied_vol(self, prices, S, strikes, maturities, r, q, is_call=True, lo=0.001, hi=5.0):
+        pr, ks, ts, cl = np.broadcast_arrays(np.asarray(prices, dtype=float), np.asarray(strikes, dtype=float),
+                                             np.asarray(maturities, dtype=float), np.asarray(is_call))
+        out = np.full(pr.shape, np.nan)
+        for idx in np.ndindex(pr.shape):
+            v = O.implied_vol(pr[idx], S, ks[idx], ts[idx], r, q, bool(cl[idx]), lo, hi)
+            if v is not None:
+                out[idx] = v
+        return out
+
+
+@pytest.mark.parametrize("with_spreads", [True, False])
+def test_extract_iv_surface_host_logic(iv_golden, with_spreads):
+    """Broadcasting of the chain, the bid-ask filter, NaN / valid_mask conventions of surface.extract_iv_surface against the
+    surface written by the reference (the inversions themselves come from the stand-in above)."""
+    from monte_carlo_option_simulator_b200.surface import extract_iv_surface, implied_vol
+    g = iv_golden
+    tag = "" if with_spreads else "_ns"
+    s_ = extract_iv_surface(float(g["spot"]), float(g["r"]), float(g["q"]), g["strikes"], g["maturities"], g["calls"], g["puts"],
+                            g["spreads"] if with_spreads else None, handle=OracleIvHandle())
+    np.testing.assert_array_equal(s_["valid_mask"], g["valid" + tag])
+    np.testing.assert_allclose(s_["iv_call"], g["iv_call" + tag], atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(s_["iv_put"], g["iv_put" + tag], atol=1e-12, equal_nan=True)
+    assert implied_vol(1e9, 100.0, 100.0, 1.0, 0.05, 0.0, handle=OracleIvHandle()) is None
+    assert implied_vol(10.45, 100.0, 100.0, 1.0, 0.05, 0.0, handle=OracleIvHandle()) == pytest.approx(0.2, abs=1e-3)
+
+
+def test_surface_closed_forms_match_the_oracle():
+    from monte_carlo_option_simulator_b200 import surface as SF
+    for S, K, T, r, q, sig in [(100.0, 110.0, 0.5, 0.03, 0.01, 0.25), (22500.0, 21000.0, 0.08, 0.065, 0.012, 0.18),
+                               (100.0, 100.0, 1e-11, 0.05, 0.0, 0.2), (100.0, 90.0, 1.0, 0.05, 0.0, 1e-11)]:
+        assert SF.bs_call_price(S, K, T, r, q, sig) == pytest.approx(O.bs_call_price(S, K, T, r, q, sig), rel=1e-13, abs=1e-13)
+        assert SF.bs_put_price(S, K, T, r, q, sig) == pytest.approx(O.bs_put_price(S, K, T, r, q, sig), rel=1e-13, abs=1e-13)
+    assert SF.bs_vega(100.0, 100.0, 1e-11, 0.05, 0.0, 0.2) == 0.0
+    assert SF.bs_vega(100.0, 100.0, 1.0, 0.05, 0.0, 0.2) == pytest.approx(37.524, abs=1e-3)
