@@ -26,10 +26,14 @@
  * a = 2 pi f(w >> 9) - 3 pi,  f(m) = the float in [1,2) with mantissa m  (fp32, MUFU lg2/sqrt/sin/cos).  Streams:
  *   B200MC_STREAM_GBM    block j -> steps 8j..8j+7: word i gives the normals of steps 8j+2i and 8j+2i+1
  *   B200MC_STREAM_HESTON block j -> steps 4j..4j+3: word i gives (Z1, Z2) of step 4j+i
- *   B200MC_STREAM_SVJ    block j -> steps 2j, 2j+1: (w0 -> (Z1,Z2), w1 -> U_jump), (w2 -> (Z1,Z2), w3 -> U_jump);
- *                        U_jump = (w + 0.5) / 2^32
- *                        the jump fires iff U_jump < lambda_j dt and, given that, U_jump / (lambda_j dt) is uniform on
- *                        (0,1): Z_jump_size = normcdfinv(U_jump / (lambda_j dt)) -- the same word sizes the jump
+ *   B200MC_STREAM_SVJ    block j -> steps 4j..4j+3 like B200MC_STREAM_HESTON (the diffusion of the SVJ model)
+ *   B200MC_STREAM_SVJ_JUMP  the jump times and sizes of the SVJ model.  The reference tests U < p = lambda_j dt at every
+ *                        step (engine/monte_carlo.py:233); the same process is drawn here as geometric GAPS, one uniform
+ *                        per jump: block k -> jumps 2k and 2k+1 of the path, (w0 -> gap, w1 -> size), (w2 -> gap,
+ *                        w3 -> size); gap = floor(lg2(U) / lg2(1 - p)) jump-free steps before the jump,
+ *                        U = ((float)w + 0.5) 2^-32 (fp32); size Z_jump_size = first member of BM(w).
+ *                        b200mc_dump_normals(B200MC_ZJUMP_U) turns the jump times back into a per-step uniform array
+ *                        (p U' at the jump steps, p + (1 - p) U'' elsewhere) that makes the reference fire the same jumps.
  * b200mc_dump_normals returns exactly the values the fused kernels use, so the reference (or the oracle) can be
  * fed identical draws.
  */
@@ -62,6 +66,8 @@ extern "C" {
 #define B200MC_STREAM_HESTON 1u
 #define B200MC_STREAM_SVJ    2u
 #define B200MC_STREAM_HEDGE  3u   /* b200mc_hedge_walk: GBM layout, counter path = scenario index */
+#define B200MC_STREAM_SVJ_JUMP 4u /* jump gaps and sizes of the SVJ model (not a b200mc_dump_normals selector) */
+#define B200MC_STREAM_FILL   5u   /* b200mc_dump_normals only: the uniforms of the jump-free steps of ZJUMP_U */
 
 /* which array b200mc_dump_normals returns */
 #define B200MC_Z1         0

@@ -31,6 +31,7 @@ struct b200mc_handle {
     unsigned int *d_counter;                           // "last block reduces" ticket
     void *peer_local; void *peer_ptr[B200MC_PEER_MAX_RANKS]; int peer_rank, peer_world;   // peer.cu: exchange buffers
     unsigned long long peer_epoch;
+    void *peer_status, *peer_status_dev;               // pinned + mapped: epoch of the first exchange that timed out (0 = none)
     char err[512];
 };
 
@@ -82,6 +83,8 @@ inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pi
 // peer.cu: in-place sum over the ranks of n 8-byte elements (double, or unsigned long long with as_u64) at data_dev,
 // asynchronous on the handle's stream; a collective (needs b200mc_peer_connect)
 int peer_allreduce_async(b200mc_handle *h, void *data_dev, int32_t n, bool as_u64);
+// non-zero (B200MC_ECUDA + message) once an exchange on this handle has timed out; call after a stream synchronisation
+int peer_check(b200mc_handle *h);
 
 // pcg64.cu: n outputs of NumPy's PCG64 .random() starting at output index `first` -> out_dev; st = {state_hi, state_lo,
 // inc_hi, inc_lo}; `chunk` consecutive outputs per thread

@@ -3,9 +3,14 @@
 //
 // b200mc_dump_normals returns, as float64 [n_paths, n_steps], exactly the values the fused kernels consume:
 //   Z1 / Z2        BM_SCALE * (double)raw   with raw the fp32 Box-Muller output of philox.cuh
-//   Z_jump         (w + 0.5) / 2^32                                   (SVJ stream; 1.0 = "never jumps" elsewhere)
-//   Z_jump_size    (double)normcdfinvf(U_jump / jump_prob) where the jump fires (U_jump < jump_prob = lambda_j dt),
-//                  0 elsewhere -- the reference only reads it where the jump fires (monte_carlo.py:233-234)
+//   Z_jump         (SVJ) the fused kernels draw jump TIMES (geometric gaps, philox.cuh JumpStream), the reference wants
+//                  a uniform per step that it compares with jump_prob = lambda_j dt (monte_carlo.py:233).  The array
+//                  returned here is i.i.d. U(0,1) in distribution and fires exactly at the kernels' jump steps:
+//                  jump_prob * U' at a jump step (U' from the jump's size word), jump_prob + (1 - jump_prob) * U''
+//                  elsewhere (U'' from B200MC_STREAM_FILL, block s / 4, word s % 4).  1.0 = "never jumps" on the
+//                  other streams.
+//   Z_jump_size    BM_SCALE * (double)raw of the jump's size word at the jump steps, 0 elsewhere -- the reference only
+//                  reads it where the jump fires (monte_carlo.py:233-234)
 // Arrays a stream does not carry come back as neutral values (Z2 = 0, Z_jump = 1, Z_jump_size = 0).
 #include "prep.cuh"
 
@@ -24,10 +29,10 @@ __global__ void k_dump_philox(PhiloxKey key, uint64_t path0, int64_t n_paths, in
 }
 
 __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_steps, uint32_t stream, int which,
-                               double jump_prob, double *__restrict__ out)
+                               double *__restrict__ out)
 {
     const bool gbm_layout = stream == B200MC_STREAM_GBM || stream == B200MC_STREAM_HEDGE;
-    const int per = gbm_layout ? 8 : (stream == B200MC_STREAM_HESTON ? 4 : 2);
+    const int per = gbm_layout ? 8 : 4;
     const int n_blocks = (n_steps + per - 1) / per;
     const int64_t total = n_paths * n_blocks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -45,27 +50,46 @@ __global__ void k_dump_normals(PhiloxKey key, uint64_t path0, int64_t n_paths, i
                 vals[2 * t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rc : neutral;
                 vals[2 * t + 1] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rs : neutral;
             }
-        } else if (stream == B200MC_STREAM_HESTON) {
+        } else {                       // HESTON and the diffusion of SVJ (the jump arrays come from k_dump_jumps)
             for (int t = 0; t < 4; ++t) {
                 const BM2 b = box_muller_word(ww[t]);
                 vals[t] = which == B200MC_Z1 ? B200MC_BM_SCALE * (double)b.rc
                         : which == B200MC_Z2 ? B200MC_BM_SCALE * (double)b.rs : neutral;
             }
-        } else {
-            for (int t = 0; t < 2; ++t) {
-                const BM2 b = box_muller_word(ww[2 * t]);
-                if (which == B200MC_Z1) vals[t] = B200MC_BM_SCALE * (double)b.rc;
-                else if (which == B200MC_Z2) vals[t] = B200MC_BM_SCALE * (double)b.rs;
-                else if (which == B200MC_ZJUMP_U) vals[t] = jump_uniform(ww[2 * t + 1]);
-                else {   // defined where the jump fires (U < jump_prob); 0 elsewhere (the reference never reads it there)
-                    const bool fired = jump_uniform(ww[2 * t + 1]) < jump_prob;
-                    vals[t] = fired ? (double)jump_size_normal(ww[2 * t + 1], 1.0 / (jump_prob * 4294967296.0)) : 0.0;
-                }
-            }
         }
         for (int t = 0; t < per; ++t) {
             const int s = blk * per + t;
             if (s < n_steps) out[(size_t)pi * n_steps + s] = vals[t];
+        }
+    }
+}
+
+// The jump arrays of the SVJ model: one thread walks one path's jump stream exactly as simulate_path does.
+__global__ void k_dump_jumps(PhiloxKey key, uint64_t path0, int64_t n_paths, int n_steps, int which, double jump_prob,
+                             float inv_lg2_q, int jump_on, double *__restrict__ out)
+{
+    for (int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pi < n_paths; pi += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t path = path0 + (uint64_t)pi;
+        const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
+        JumpStream jmp;
+        jmp.init(c0, c1, key, inv_lg2_q, jump_on != 0);
+        U4 fill = U4{0u, 0u, 0u, 0u};
+        for (int s = 0; s < n_steps; ++s) {
+            if (which == B200MC_ZJUMP_U && (s & 3) == 0)
+                fill = philox4x32_10(c0, c1, (uint32_t)(s >> 2), B200MC_STREAM_FILL, key);
+            const uint32_t fw = (s & 3) == 0 ? fill.x : (s & 3) == 1 ? fill.y : (s & 3) == 2 ? fill.z : fill.w;
+            double val;
+            if (s == jmp.next) {
+                if (which == B200MC_ZJUMP_U) val = jump_prob * word_uniform(jmp.w_size);      // < jump_prob
+                else val = B200MC_BM_SCALE * (double)jmp.size_raw();
+                jmp.advance(c0, c1, key, inv_lg2_q, s);
+            } else if (which == B200MC_ZJUMP_U) {
+                val = jump_prob + (1.0 - jump_prob) * word_uniform(fw);
+                if (!(val > jump_prob)) val = 1.0;                                            // never below the threshold
+            } else {
+                val = 0.0;
+            }
+            out[(size_t)pi * n_steps + s] = val;
         }
     }
 }
@@ -149,8 +173,15 @@ extern "C" int b200mc_dump_normals(b200mc_handle *h, uint64_t seed, uint64_t pat
     B200MC_CUDA(h, cudaSetDevice(h->device));
     const size_t bytes = (size_t)n_paths * n_steps * 8;
     B200MC_TRY(ensure(h, &h->d_stage, &h->stage_bytes, bytes));
-    k_dump_normals<<<h->sm_count * 4, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_steps, stream,
-                                                           which, jump_prob, (double *)h->d_stage);
+    if (stream == B200MC_STREAM_SVJ && (which == B200MC_ZJUMP_U || which == B200MC_ZJUMP_SIZE)) {
+        double inv = 0.0;
+        const int on = jump_setup(jump_prob, &inv);
+        k_dump_jumps<<<h->sm_count * 4, 128, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_steps, which,
+                                                            jump_prob, (float)inv, on, (double *)h->d_stage);
+    } else {
+        k_dump_normals<<<h->sm_count * 4, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_steps, stream,
+                                                               which, (double *)h->d_stage);
+    }
     B200MC_CUDA(h, cudaGetLastError());
     h->launches += 1;
     B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));

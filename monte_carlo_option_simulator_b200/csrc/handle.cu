@@ -97,8 +97,12 @@ extern "C" int b200mc_set_stream(b200mc_handle *h, uint64_t stream)
 {
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
     B200MC_CUDA(h, cudaSetDevice(h->device));
-    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    // only the handle's OWN stream is drained here: an external stream set earlier belongs to the caller (it may have
+    // been destroyed already) and the caller orders its work itself
+    if (h->own_stream) {
+        B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaStreamDestroy(h->stream);
+    }
     h->stream = (cudaStream_t)(uintptr_t)stream;
     h->own_stream = false;
     return 0;
@@ -109,7 +113,7 @@ extern "C" int b200mc_synchronize(b200mc_handle *h)
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
     B200MC_CUDA(h, cudaSetDevice(h->device));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
-    return 0;
+    return peer_check(h);
 }
 
 extern "C" int b200mc_malloc(b200mc_handle *h, size_t bytes, void **dev_ptr)
@@ -141,7 +145,7 @@ extern "C" int b200mc_memcpy_d2h(b200mc_handle *h, void *dst_host, const void *s
     B200MC_CUDA(h, cudaSetDevice(h->device));
     B200MC_CUDA(h, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
-    return 0;
+    return peer_check(h);
 }
 extern "C" int b200mc_malloc_host(b200mc_handle *h, size_t bytes, void **host_ptr)
 {

@@ -9,7 +9,7 @@
 namespace b200mc {
 
 enum { MB_FFMA = 0, MB_IMAD_WIDE = 1, MB_LOP3 = 2, MB_MUFU_EX2 = 3, MB_MUFU_SIN = 4, MB_IADD3 = 5, MB_PHILOX = 6,
-       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_FFMA2 = 15, MB_COUNT = 16 };
+       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_FFMA2 = 15, MB_F2F = 16, MB_DADD = 17, MB_COUNT = 18 };
 
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, const __grid_constant__ PhiloxKey key,
@@ -46,6 +46,37 @@ __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, co
 #pragma unroll
         for (int k = 0; k < 8; ++k) s ^= a[k];
         if (s == 0x12345ull) sink[0] = t;
+    } else if constexpr (WHICH == MB_F2F) {
+        // fp32 <-> fp64 conversions (the fp64 path state consumes fp32 draws): one widening + one narrowing per
+        // link of the chain, counted as TWO conversions
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = 1.0f + (float)((t + k) & 1023);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double d;
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(a[k]));
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(a[k]) : "d"(d));
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += a[k];
+        if (s == 123.456f) sink[0] = t;
+    } else if constexpr (WHICH == MB_DADD) {
+        double a[8];
+        const double b = 1.0 + 1e-9 * (double)(seed & 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = (double)(t + k);
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(a[k]) : "d"(b));
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += a[k];
+        if (s == 123.456) sink[0] = t;
     } else if constexpr (WHICH == MB_IMAD_WIDE) {
         uint32_t a[8];
 #pragma unroll
@@ -232,7 +263,8 @@ extern "C" int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, dou
 }
 
 // which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox + 4 Box-Muller
-// pairs = 8 normals (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs).
+// pairs = 8 normals (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs),
+// 12-14 IMAD lo / hi / lo+hi, 15 FFMA2, 16 fp32<->fp64 conversions, 17 DADD.
 // *ops_per_s = thread-level operations per second over the whole device (kernel time by CUDA events, best of 3).
 extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s)
 {
@@ -260,7 +292,9 @@ extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double 
         case 12: mb_launch<12>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         case 13: mb_launch<13>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         case 14: mb_launch<14>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        default: mb_launch<15>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 15: mb_launch<15>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 16: mb_launch<16>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        default: mb_launch<17>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
         }
         B200MC_CUDA(h, cudaGetLastError());
         B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -271,7 +305,7 @@ extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double 
         h->launches += 1;
     }
     const double per_thread = (which == MB_PHILOX || which == MB_PHILOX_BM) ? (double)iters
-                            : (which == MB_MIX_FFMA_LOP3 ? 4.0 * iters : 8.0 * iters);
+                            : (which == MB_MIX_FFMA_LOP3 ? 4.0 * iters : (which == MB_F2F ? 16.0 * iters : 8.0 * iters));
     *ops_per_s = (double)grid * 256.0 * per_thread / ((double)best * 1e-3);
     return 0;
 }

@@ -10,6 +10,8 @@
 //                             and a 32x32 tile in shared memory; each lane fills its own row as the steps come out
 //                             of the recurrence, then the warp writes the tile out row by row so that every store
 //                             instruction covers 128 (fp32) or 256 (fp64) contiguous bytes.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -18,6 +20,12 @@
 namespace b200mc {
 
 constexpr int PT_THREADS = 256;
+#ifndef B200MC_PATHS_DEFAULT_POLY
+#define B200MC_PATHS_DEFAULT_POLY 0
+#endif
+#ifndef B200MC_PATHS_DEFAULT_MINB
+#define B200MC_PATHS_DEFAULT_MINB 1
+#endif
 constexpr float LOG2E_F = 1.4426950408889634f;
 
 struct PathArgs {
@@ -271,8 +279,12 @@ k_paths_det(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
 // Philox work.  No per-row store instructions, no partial sectors.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool TAB, typename R, typename O, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+// DEG > 0 (fp32 state, constant variance): the spot is carried MULTIPLICATIVELY, S_{t+1} = S_t + S_t expm1(delta_t) with
+// expm1 a degree-DEG Taylor polynomial on the FMA pipe (|delta| is small: sigma sqrt(dt) * 5.65 + |drift dt|, the host
+// picks DEG from that bound and falls back to the MUFU form when it is too large) -- no ex2 per stored value, i.e. 2
+// instead of 3 MUFU per path-step.
+template <bool TAB, typename R, typename O, int MAXT, int DEG, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_g, const double *__restrict__ dtab_g,
             O *__restrict__ out)
 {
@@ -295,7 +307,8 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
     }
     const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
     const R S0 = (R)a.m.S0;
-    const R wc = (R)(a.m.x_w[0] * (double)UNIT), dc = (R)(a.m.step_drift[0] * (double)UNIT);
+    static_assert(DEG == 0 || (!TAB && sizeof(R) == 4), "the polynomial form is for the constant-variance fp32 state");
+    const R wc = (R)(a.m.x_w[0] * (double)(DEG ? (R)1 : UNIT)), dc = (R)(a.m.step_drift[0] * (double)(DEG ? (R)1 : UNIT));
     const int64_t n_groups = (a.n_paths + 31) / 32;
     const bool dst_aligned = ((uintptr_t)out & 15) == 0;
     for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -307,7 +320,16 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
         const int rows = (int)((a.n_paths - path0) < 32 ? (a.n_paths - path0) : 32);
         // ---- chunk-local log returns of steps 32c .. 32c + 31 ----------------------------------------------------
         R xl[32];
-        R x = (R)0;
+        R x = DEG ? (R)1 : (R)0;
+        auto growth = [&](R z) {                 // DEG > 0: x <- x exp(wc z + dc), chunk-local running product
+            const R d = fmaf((float)wc, (float)z, (float)dc);
+            R q = DEG >= 5 ? (R)(1.0 / 120.0) : (R)(1.0 / 24.0);
+            if (DEG >= 5) q = fmaf(d, q, (R)(1.0 / 24.0));
+            q = fmaf(d, q, (R)(1.0 / 6.0));
+            q = fmaf(d, q, (R)0.5);
+            q = fmaf(d, q, (R)1);
+            x = fmaf(x, d * q, x);
+        };
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const U4 u = philox4x32_10(c0, c1, (uint32_t)(4 * c + b), B200MC_STREAM_GBM, a.key);
@@ -315,23 +337,32 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const BM2 bm = box_muller_word(ww[t]);
-                R wa, wb, da, db;
-                if constexpr (TAB) {
-                    const int s = 32 * c + 8 * b + 2 * t;
-                    wa = w2[s]; wb = w2[s + 1]; da = d2[s]; db = d2[s + 1];
-                } else { wa = wb = wc; da = db = dc; }
-                x = (x + da) + wa * (R)bm.rc;
-                xl[8 * b + 2 * t] = x;
-                x = (x + db) + wb * (R)bm.rs;
-                xl[8 * b + 2 * t + 1] = x;
+                if constexpr (DEG > 0) {
+                    growth((R)bm.rc);
+                    xl[8 * b + 2 * t] = x;
+                    growth((R)bm.rs);
+                    xl[8 * b + 2 * t + 1] = x;
+                } else {
+                    R wa, wb, da, db;
+                    if constexpr (TAB) {
+                        const int s = 32 * c + 8 * b + 2 * t;
+                        wa = w2[s]; wb = w2[s + 1]; da = d2[s]; db = d2[s + 1];
+                    } else { wa = wb = wc; da = db = dc; }
+                    x = (x + da) + wa * (R)bm.rc;
+                    xl[8 * b + 2 * t] = x;
+                    x = (x + db) + wb * (R)bm.rs;
+                    xl[8 * b + 2 * t + 1] = x;
+                }
             }
         }
         totals[c * 32 + lane] = x;
         // the TMA engine must have finished READING the tile of the previous group before anyone refills it
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
-        R off = (R)0;
-        for (int cc = 0; cc < c; ++cc) off += totals[cc * 32 + lane];
+        R off = DEG ? S0 : (R)0;
+        for (int cc = 0; cc < c; ++cc) {
+            if constexpr (DEG > 0) off *= totals[cc * 32 + lane]; else off += totals[cc * 32 + lane];
+        }
         // ---- fill: y_{32c + 1 + j} = S0 exp(off + xl[j]) -----------------------------------------------------------
         O *row = tile + (size_t)lane * ncol;
         if (c == 0) row[0] = (O)a.m.S0;                                             // column 0 = S0   (:217)
@@ -339,14 +370,17 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
         if (colbase + 31 < ncol) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if constexpr (sizeof(R) == 4) row[colbase + j] = (O)(S0 * ex2_approx((float)(off + xl[j])));
+                if constexpr (DEG > 0) row[colbase + j] = (O)(off * xl[j]);
+                else if constexpr (sizeof(R) == 4) row[colbase + j] = (O)(S0 * ex2_approx((float)(off + xl[j])));
                 else row[colbase + j] = (O)(S0 * exp(off + xl[j]));
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 O y;
-                if constexpr (sizeof(R) == 4) y = (O)(S0 * ex2_approx((float)(off + xl[j]))); else y = (O)(S0 * exp(off + xl[j]));
+                if constexpr (DEG > 0) y = (O)(off * xl[j]);
+                else if constexpr (sizeof(R) == 4) y = (O)(S0 * ex2_approx((float)(off + xl[j])));
+                else y = (O)(S0 * exp(off + xl[j]));
                 if (colbase + j < ncol) row[colbase + j] = y;
             }
         }
@@ -518,15 +552,48 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
         if (ld == (int64_t)n_steps + 1 && n_steps <= 1024 && tma_smem <= 200 * 1024) {
             // reference layout: CTA tile = 32 whole paths, one TMA bulk store per tile
             const int64_t grid = std::min<int64_t>(groups, (int64_t)h->sm_count * 16);
-            with_bool(tab, [&](auto t) {
-                with_bool(nch > 8, [&](auto big) {
-                    with_types(fp64, dtype, [&](auto r, auto o) {
-                        using O = decltype(o);
-                        auto k = k_paths_tma<decltype(t)::value, decltype(r), O, decltype(big)::value ? 1024 : 256>;
+            // fp32 state, constant variance: carry the spot multiplicatively with a polynomial expm1 when every
+            // |delta| = |drift dt| + sigma sqrt(dt) * 4.8 (largest raw draw) keeps the Taylor remainder below 2e-7 per step
+            int deg = 0;
+            if (!tab && !fp64) {
+                const double dmax = fabs(pr.m.step_drift[0]) + fabs(pr.m.x_w[0]) * 4.8;
+                const char *e = getenv("B200MC_PATHS_EXP");              // tuning knob: mufu | poly4 | poly5
+                if (e && !strcmp(e, "mufu")) deg = 0;
+                else if (e && !strcmp(e, "poly5")) deg = dmax <= 0.30 ? 5 : 0;
+                else if (e && !strcmp(e, "poly4")) deg = dmax <= 0.30 ? 4 : 0;
+                else deg = B200MC_PATHS_DEFAULT_POLY ? (dmax <= 0.125 ? 4 : (dmax <= 0.30 ? 5 : 0)) : 0;
+            }
+            const char *mb = getenv("B200MC_PATHS_MINB");               // tuning knob: resident CTAs per SM asked of ptxas
+            const bool minb4 = !tab && !fp64 && nch <= 8 && (mb ? atoi(mb) == 4 : B200MC_PATHS_DEFAULT_MINB == 4);
+            auto launch = [&](auto t, auto big, auto r, auto o, auto dg) {
+                using O = decltype(o);
+                using Rr = decltype(r);
+                constexpr bool T_ = decltype(t)::value, B_ = decltype(big)::value;
+                constexpr int D_ = decltype(dg)::value;
+                if constexpr (!T_ && !B_ && sizeof(Rr) == 4) {
+                    if (minb4) {
+                        auto k = k_paths_tma<false, Rr, O, 256, D_, 4>;
                         allow_smem(k, tma_smem);
                         k<<<(unsigned)grid, 32 * nch, tma_smem, h->stream>>>(a, wtab_d, dtab_d, (O *)dO);
+                        return;
+                    }
+                }
+                auto k = k_paths_tma<T_, Rr, O, B_ ? 1024 : 256, D_>;
+                allow_smem(k, tma_smem);
+                k<<<(unsigned)grid, 32 * nch, tma_smem, h->stream>>>(a, wtab_d, dtab_d, (O *)dO);
+            };
+            with_bool(nch > 8, [&](auto big) {
+                if (deg) {
+                    with_bool(dtype == B200MC_F64, [&](auto wide) {
+                        using O = std::conditional_t<decltype(wide)::value, double, float>;
+                        if (deg == 5) launch(std::false_type{}, big, float{}, O{}, std::integral_constant<int, 5>{});
+                        else launch(std::false_type{}, big, float{}, O{}, std::integral_constant<int, 4>{});
                     });
-                });
+                } else {
+                    with_bool(tab, [&](auto t) {
+                        with_types(fp64, dtype, [&](auto r, auto o) { launch(t, big, r, o, std::integral_constant<int, 0>{}); });
+                    });
+                }
             });
         } else {
             // padded rows (or very long paths): row-tiled kernel, 128-bit stores when the rows allow them

@@ -116,19 +116,73 @@ __device__ __forceinline__ BM2 box_muller_word(uint32_t w)
     return o;
 }
 
-// jump uniform as the reference sees it (float64 in (0,1)): U = (w + 0.5) / 2^32
-__device__ __forceinline__ double jump_uniform(uint32_t w)
+// Same transform with the three factors kept apart: normals = B200MC_BM_SCALE * rad * (cs, sn).  The stochastic-variance
+// kernels (fp32 state) fold their per-step constants into `rad` once instead of scaling both products per state.
+struct BM3 { float rad, cs, sn; };
+__device__ __forceinline__ BM3 box_muller_parts(uint32_t w)
+{
+    const float u1 = 2.0f - mant12(w);
+    const float f2 = __uint_as_float(__funnelshift_r(w, 0x7Fu, 9));
+    const float ang = fmaf(f2, 6.283185307179586f, -9.42477796076938f);
+    BM3 o;
+    o.rad = sqrt_approx(-lg2_approx(u1));
+    o.cs = cos_approx(ang);
+    o.sn = sin_approx(ang);
+    return o;
+}
+
+// uniform in (0, 1) on the 2^32 grid, as a double: U = (w + 0.5) / 2^32
+__device__ __forceinline__ double word_uniform(uint32_t w)
 {
     return ((double)w + 0.5) * 2.3283064365386963e-10;
 }
 
-// jump-size standard normal from the jump word itself (only evaluated when the jump fired, i.e. w < jump_thr):
-// conditional on the event, (w + 0.5) * scale with scale = 1 / (lambda dt 2^32) is uniform on (0, 1).
-__device__ __forceinline__ float jump_size_normal(uint32_t w, double scale)
+// ---- jumps (SVJ): the gap to the next jump instead of one Bernoulli test per step --------------------------------------
+// The reference tests U < p = lambda_j dt at EVERY step (engine/monte_carlo.py:233): the number of jump-free steps before
+// the next jump is geometric, P(G = g) = (1 - p)^g p.  Drawing G = floor(ln U / ln(1 - p)) from ONE uniform per JUMP is
+// the same process in distribution and takes the jump uniform out of the per-step loop (it cost half a Philox call per
+// step).  inv_lg2_q = 1 / lg2(1 - p) (<= 0; 0 when p >= 1: a jump at every step), computed on the host in double.
+// Everything here is fp32 for every path-state precision, so the fp32 / fp64 kernels and b200mc_dump_normals see the
+// same jump times.
+__device__ __forceinline__ int jump_gap(uint32_t w, float inv_lg2_q)
 {
-    float u = (float)(((double)w + 0.5) * scale);
-    u = fminf(fmaxf(u, 2.9802322387695312e-08f), 0.99999994f);
-    return normcdfinvf(u);
+    const float u = ((float)w + 0.5f) * 2.3283064365386963e-10f;           // (0, 1]
+    const float g = floorf(log2f(u) * inv_lg2_q);                          // >= 0 (or -0)
+    return (int)fminf(g, 1.0e9f);
 }
+
+struct JumpStream {
+    // Philox stream B200MC_STREAM_SVJ_JUMP, counter block k -> jumps 2k and 2k + 1 of the path:
+    //   (w0 -> gap before jump 2k, w1 -> its size), (w2 -> gap before jump 2k + 1, w3 -> its size)
+    // size: Z_jump_size = B200MC_BM_SCALE * rc(BM(w)) (the cosine member of the word's Box-Muller pair)
+    int next, next2;            // step index of the next jump and of the one after it
+    uint32_t w_size, w_size2;   // their size words
+    uint32_t m;                 // jumps consumed so far
+
+    __device__ __forceinline__ void refill(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int from)
+    {
+        const U4 q = philox4x32_10(c0, c1, m >> 1, B200MC_STREAM_SVJ_JUMP, key);
+        next = from + jump_gap(q.x, inv_lg2_q);
+        w_size = q.y;
+        next2 = next + 1 + jump_gap(q.z, inv_lg2_q);
+        w_size2 = q.w;
+    }
+    __device__ __forceinline__ void init(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, bool on)
+    {
+        m = 0u;
+        next = next2 = 0x7fffffff;
+        w_size = w_size2 = 0u;
+        if (on) refill(c0, c1, key, inv_lg2_q, 0);
+    }
+    // the jump at step `s` (== next) has been applied: move to the following one
+    __device__ __forceinline__ void advance(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int s)
+    {
+        ++m;
+        if (m & 1u) { next = next2; w_size = w_size2; }
+        else refill(c0, c1, key, inv_lg2_q, s + 1);
+    }
+    // unscaled size draw of the pending jump: Z_jump_size = B200MC_BM_SCALE * size_raw()
+    __device__ __forceinline__ float size_raw() const { return box_muller_word(w_size).rc; }
+};
 
 } // namespace b200mc

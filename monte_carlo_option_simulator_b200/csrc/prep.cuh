@@ -20,6 +20,16 @@ struct Prep {
 
 #define B200MC_DETVAR_MAX_STEPS 4096
 
+// Jump process of a run with per-step jump probability p = lambda_j dt (engine/monte_carlo.py:233, "U < lambda_j dt"):
+// returns whether jumps can fire at all and the constant of the geometric gap draw, 1 / lg2(1 - p) (philox.cuh).
+inline int jump_setup(double p, double *inv_lg2_q)
+{
+    *inv_lg2_q = 0.0;                                   // p >= 1: every step jumps, gap = floor(lg2 U * 0) = 0
+    if (!(p > 0.0)) return 0;
+    if (p < 1.0) *inv_lg2_q = M_LN2 / log1p(-p);
+    return 1;
+}
+
 inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T, int32_t n_steps,
                    int64_t n_paths, uint64_t seed, uint32_t flags, const b200mc_bumps *bumps, Prep &o)
 {
@@ -49,13 +59,8 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
     m.crho = sqrt(1.0 - p->rho * p->rho);
     m.mu_j = p->mu_j;
     m.sigma_j = p->sigma_j;
-    {   // jump iff (w + 0.5) 2^-32 < lambda dt  <=>  w < ceil(lambda dt 2^32 - 0.5)   (w integer)
-        const double lim = p->lambda_j * dt * 4294967296.0 - 0.5;
-        if (!(lim > 0.0)) m.jump_thr = 0;
-        else if (lim >= 4294967296.0) m.jump_thr = 4294967296ull;
-        else m.jump_thr = (uint64_t)ceil(lim);
-        m.jump_scale = m.jump_thr ? 1.0 / (p->lambda_j * dt * 4294967296.0) : 0.0;
-    }
+    m.sigma_j_s = p->sigma_j * B200MC_BM_SCALE;
+    m.jump_on = jump_setup(p->lambda_j * dt, &m.jump_inv_lg2q);             // :233
     m.v0[0] = p->v0;
     m.v0[1] = (flags & B200MC_GREEKS) ? bumps->v0_up : p->v0;
     m.v0[2] = (flags & B200MC_GREEKS) ? bumps->v0_dn : p->v0;
@@ -66,7 +71,7 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
     for (int r = 0; r < nvar; ++r)
         if (!(m.v0[r] >= 0.0) || (p->kappa != 0.0 && p->theta != m.v0[r])) constant_var = false;
 
-    if ((flags & B200MC_FORCE_SVJ) || m.jump_thr != 0) o.mode = MODE_SVJ;
+    if ((flags & B200MC_FORCE_SVJ) || m.jump_on) o.mode = MODE_SVJ;
     else if (p->xi != 0.0) o.mode = MODE_HESTON;
     else if (constant_var) o.mode = MODE_GBM;
     else if (n_steps <= B200MC_DETVAR_MAX_STEPS) o.mode = MODE_DETVAR;

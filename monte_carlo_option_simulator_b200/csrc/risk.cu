@@ -144,6 +144,7 @@ static int risk_run(b200mc_handle *h, const T *x_dev, const int64_t n_loc, doubl
     }
     B200MC_CUDA(h, cudaMemcpyAsync(r1, res, sharded ? 24 : 16, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (sharded) B200MC_TRY(peer_check(h));
     n = (int64_t)r1[2];                                                      // from here on: the GLOBAL length
     if (n <= 0) return fail(h, B200MC_EINVAL, "returns must not be empty");
     const double mean = r1[0] / (double)n;                                   // :137
@@ -182,6 +183,7 @@ static int risk_run(b200mc_handle *h, const T *x_dev, const int64_t n_loc, doubl
     B200MC_CUDA(h, cudaMemcpyAsync(r2, res, 48, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaMemcpyAsync(thr, &st->thr[0], 16, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (sharded) B200MC_TRY(peer_check(h));
 
     const double nn = (double)n;
     const double var_pop = r2[0] / nn;

@@ -14,7 +14,8 @@
 //     DETVAR  xi = 0, lambda = 0, variance deterministic but moving (kappa != 0, theta != v0): per-step
 //             weights w_s = sqrt(v_s dt) come from a table in shared memory (built on the host in fp64)
 //     HESTON  lambda = 0: one Box-Muller pair (Z1, Z2) per step, four steps per Philox call
-//     SVJ     everything: a pair word and a jump-uniform word per step, two steps per Philox call
+//     SVJ     everything: the same diffusion layout on its own stream; the jump times come from geometric gaps drawn
+//             once per JUMP on a second stream (philox.cuh, JumpStream), not from a uniform per step
 // R is the type of the path state (float or double); the draws are float in both cases.
 #pragma once
 #include "common.cuh"
@@ -31,11 +32,13 @@ struct ModelArgs {
     double theta;
     double one_m_kdt;       // 1 - kappa dt
     double kdt_theta;       // kappa dt theta
-    double jump_scale;      // 1 / (lambda_j dt 2^32): (w + 0.5) * jump_scale is uniform on (0,1) GIVEN that the jump fired
+    double jump_inv_lg2q;   // 1 / lg2(1 - lambda_j dt): gap to the next jump = floor(lg2 U * this)   (philox.cuh)
     double xi_sqrt_dt_s;    // xi sqrt(dt) BM_SCALE
     double rho, crho;       // crho = sqrt(1 - rho^2)                        :227
     double mu_j, sigma_j;
-    uint64_t jump_thr;      // jump iff w2 < jump_thr  <=>  (w2 + 0.5) / 2^32 < lambda_j dt    :233
+    double sigma_j_s;       // sigma_j BM_SCALE
+    int32_t jump_on;        // lambda_j dt > 0                                :233
+    int32_t pad_;
     double v0[3];           // base, up, down
     double x_drift[3];      // GBM / DETVAR: total drift of x over [0, T] for the three variance starts
     double x_w[3];          // GBM: x_T = x_drift + x_w * sum(raw z);  x_w = sqrt(v0 dt) BM_SCALE
@@ -43,11 +46,13 @@ struct ModelArgs {
 };
 
 template <typename R> struct Consts {
-    R drift_dt, half_dt, sqrt_dt_s, one_m_kdt, kdt_theta, xi_sqrt_dt_s, rho, crho, mu_j, sigma_j;
+    R drift_dt, half_dt, sqrt_dt_s, one_m_kdt, kdt_theta, xi_sqrt_dt_s, rho, crho, mu_j, sigma_j_s;
+    R xs_rho, xs_crho;      // xi sqrt(dt) BM_SCALE * (rho, sqrt(1 - rho^2))
     __device__ __forceinline__ explicit Consts(const ModelArgs &m)
         : drift_dt((R)m.drift_dt), half_dt((R)m.half_dt), sqrt_dt_s((R)m.sqrt_dt_s), one_m_kdt((R)m.one_m_kdt),
           kdt_theta((R)m.kdt_theta), xi_sqrt_dt_s((R)m.xi_sqrt_dt_s), rho((R)m.rho), crho((R)m.crho),
-          mu_j((R)m.mu_j), sigma_j((R)m.sigma_j) {}
+          mu_j((R)m.mu_j), sigma_j_s((R)m.sigma_j_s), xs_rho((R)(m.xi_sqrt_dt_s * m.rho)),
+          xs_crho((R)(m.xi_sqrt_dt_s * m.crho)) {}
 };
 
 __device__ __forceinline__ float  rsqrt_of(float x)  { return sqrt_approx(x); }
@@ -64,15 +69,15 @@ template <bool ANTI, bool GREEKS> struct StateLayout {
     static constexpr int DN_IDX = UP_IDX + 1;
 };
 
-// One stochastic-variance step for all states.  z1, zc are UNSCALED draws (zc = rho z1 + sqrt(1-rho^2) z2; the Box-Muller
-// scale is folded in the constants).  Lean form of monte_carlo.py:223-238:
+// One stochastic-variance step for all states.  zs1 = sqrt(dt) Z1 and zsc = xi sqrt(dt) (rho Z1 + sqrt(1-rho^2) Z2) are
+// scaled ONCE per step by the caller (scaled_draws below), not once per state.  Lean form of monte_carlo.py:223-238:
 //   * the constant drift (r - q - lambda k) dt is NOT added here: n_steps * drift_dt is added once at the end;
 //   * v is carried unclamped -- the clamp of :238 is the max(v, 0) of :223 at the next step (and of the final v_T);
 //   * jumps are added by the caller inside the (rare) branch that detects them.
-// 7 FP32 + 1 MUFU per state and step.
+// 5 FP32 + 1 MUFU per state and step.
 template <typename R, bool ANTI, bool GREEKS>
 __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R (&v)[StateLayout<ANTI, GREEKS>::NS],
-                                        const Consts<R> &c, R z1, R zc)
+                                        const Consts<R> &c, R zs1, R zsc)
 {
     constexpr int NS = StateLayout<ANTI, GREEKS>::NS;
 #pragma unroll
@@ -80,12 +85,28 @@ __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R
         const bool neg = ANTI && k == 1;                 // twin: -Z1, -Z2  (:323)
         const R vp = rmax(v[k], (R)0);                   // :223
         const R sv = rsqrt_of(vp);                       // :224
-        const R a = sv * c.sqrt_dt_s;                    // sqrt(v+) sqrt(dt)
-        const R b = sv * c.xi_sqrt_dt_s;
         const R t = x[k] - c.half_dt * vp;               // :229 without the constant part
         const R mr = vp * c.one_m_kdt + c.kdt_theta;     // v+ + kappa (theta - v+) dt      :237
-        x[k] = neg ? t - a * z1 : t + a * z1;            // :230,236
-        v[k] = neg ? mr - b * zc : mr + b * zc;          // :237
+        x[k] = neg ? t - sv * zs1 : t + sv * zs1;        // :230,236
+        v[k] = neg ? mr - sv * zsc : mr + sv * zsc;      // :237
+    }
+}
+
+// The two scaled draws of a step from its Box-Muller word.  fp64 state: from the fp32 pair exactly as b200mc_dump_normals
+// exports it (Z = BM_SCALE * (double)raw), so the oracle fed the dumped draws agrees to rounding.  fp32 state: the
+// constants are folded into the radius first (5 FP32 per step in all; the results differ from the fp64 route by fp32
+// rounding only, far inside the 1e-4 band).
+template <typename R>
+__device__ __forceinline__ void scaled_draws(uint32_t w, const Consts<R> &c, R &zs1, R &zsc)
+{
+    if constexpr (sizeof(R) == 4) {
+        const BM3 b = box_muller_parts(w);
+        zs1 = (b.rad * c.sqrt_dt_s) * b.cs;
+        zsc = b.rad * fmaf(c.xs_crho, b.sn, c.xs_rho * b.cs);
+    } else {
+        const BM2 b = box_muller_word(w);
+        zs1 = c.sqrt_dt_s * (R)b.rc;
+        zsc = c.xi_sqrt_dt_s * (c.rho * (R)b.rc + c.crho * (R)b.rs);
     }
 }
 
@@ -93,9 +114,8 @@ __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R
 // every 32-bit output word w yields one Box-Muller pair (rc, rs) = box_muller_word(w):
 //   GBM / DETVAR  stream 0, block j -> steps 8j..8j+7: word i gives the normals of steps 8j+2i (rc) and 8j+2i+1 (rs)
 //   HESTON        stream 1, block j -> steps 4j..4j+3: word i gives (Z1, Z2) = (rc, rs) of step 4j+i
-//   SVJ           stream 2, block j -> steps 2j, 2j+1: (w0 -> (Z1, Z2), w1 -> U_jump) and (w2, w3) likewise; the jump
-//                 fires iff U_jump = (w + 0.5) / 2^32 < lambda dt, and GIVEN that, U_jump / (lambda dt) is uniform on
-//                 (0,1): Z_jump_size = normcdfinv(U_jump / (lambda dt)) -- no second draw
+//   SVJ           stream 2, block j -> steps 4j..4j+3 like HESTON; jumps: stream 4, block k -> jumps 2k, 2k+1 of the path,
+//                 (w0, w2) -> the geometric gaps before them, (w1, w3) -> their sizes (philox.cuh, JumpStream)
 //
 // Simulates global path `path` to T.  On return xT[k] = log(S_T / S0) of state k and vT[k] its variance
 // (GBM / DETVAR: vT is left untouched); sumz_out = sum of the raw draws (GBM only; feeds the pathwise vega).
@@ -209,41 +229,37 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         for (int k = 0; k < NS; ++k) { x[k] = (R)0; v[k] = (R)m.v0[0]; }
         if constexpr (GREEKS) { v[L::UP_IDX] = (R)m.v0[1]; v[L::DN_IDX] = (R)m.v0[2]; }
         R dacc = (R)0;                                   // running constant drift, only for the path store
-        if constexpr (MODE == MODE_HESTON) {
-            const int nblk = (n_steps + 3) >> 2;
-            for (int j = 0; j < nblk; ++j) {
-                const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_HESTON, key);
-                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+        // Software-pipelined like the GBM loop: the Philox rounds of block j+1 are issued next to the transforms and
+        // variance steps of block j.
+        JumpStream jmp;
+        const float inv_lg2_q = (float)m.jump_inv_lg2q;
+        if constexpr (MODE == MODE_SVJ) jmp.init(c0, c1, key, inv_lg2_q, m.jump_on != 0);
+        constexpr uint32_t STREAM = MODE == MODE_HESTON ? B200MC_STREAM_HESTON : B200MC_STREAM_SVJ;
+        const int nblk = (n_steps + 3) >> 2;
+        U4 u = philox4x32_10(c0, c1, 0u, STREAM, key);
+        for (int j = 0; j < nblk; ++j) {
+            U4 un = u;
+            if (j + 1 < nblk) un = philox4x32_10(c0, c1, (uint32_t)(j + 1), STREAM, key);
+            const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (t == 0 || 4 * j + t < n_steps) {
-                        const BM2 b = box_muller_word(ww[t]);
-                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs);
-                        if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(4 * j + t, x[0] + dacc); }
-                    }
-                }
-            }
-        } else {
-            const int nblk = (n_steps + 1) >> 1;
-            for (int j = 0; j < nblk; ++j) {
-                const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_SVJ, key);
-                const uint32_t wz[2] = {u.x, u.z}, wu[2] = {u.y, u.w};
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int s = 2 * j + t;
-                    if (t == 0 || s < n_steps) {
-                        const BM2 b = box_muller_word(wz[t]);
-                        sv_step<R, ANTI, GREEKS>(x, v, c, (R)b.rc, c.rho * (R)b.rc + c.crho * (R)b.rs);
-                        if ((uint64_t)wu[t] < m.jump_thr) {                              // :233-234, rare
-                            // given that it fired, the same word is uniform on (0, jump_thr): it also sizes the jump
-                            const R jsz = c.sigma_j * (R)jump_size_normal(wu[t], m.jump_scale);
+            for (int t = 0; t < 4; ++t) {
+                const int s = 4 * j + t;
+                if (t == 0 || s < n_steps) {
+                    R zs1, zsc;
+                    scaled_draws<R>(ww[t], c, zs1, zsc);
+                    sv_step<R, ANTI, GREEKS>(x, v, c, zs1, zsc);
+                    if constexpr (MODE == MODE_SVJ) {
+                        if (s == jmp.next) {                                             // :233-234, rare
+                            const R jsz = c.sigma_j_s * (R)jmp.size_raw();
 #pragma unroll
                             for (int k = 0; k < NS; ++k) x[k] += (ANTI && k == 1) ? c.mu_j - jsz : c.mu_j + jsz;
+                            jmp.advance(c0, c1, key, inv_lg2_q, s);
                         }
-                        if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }
                     }
+                    if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }
                 }
             }
+            u = un;
         }
         {
             const R total_drift = (R)((double)n_steps * m.drift_dt);

@@ -67,7 +67,7 @@ def test_normals_are_standard(H, L):
     assert abs((z ** 3).mean()) < 5 * math.sqrt(15 / z.size) and abs((z ** 4).mean() - 3) < 5 * math.sqrt(96 / z.size)
     z1 = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.Z1)
     z2 = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.Z2)
-    u = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_U)
+    u = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_U, jump_prob=0.25)     # jump times -> per-step uniforms
     zj = H.dump_normals(7, 20000, 33, L.STREAM_SVJ, L.ZJUMP_SIZE, jump_prob=0.25)
     assert abs(np.corrcoef(z1.ravel(), z2.ravel())[0, 1]) < 5 / math.sqrt(z1.size)
     assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 5 / math.sqrt(12 * u.size)
