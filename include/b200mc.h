@@ -168,12 +168,32 @@ int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_params *p, 
                                   const double *Z1, const double *Z2,
                                   const double *Z_jump, const double *Z_jump_size,
                                   int record_paths, double *S_final, double *v_final, double *all_paths);
+/* record_paths is a flag word: B200MC_GIVEN_RECORD (= 1, the reference's record_paths=True) and / or B200MC_GIVEN_NEGATE:
+ * evaluate the antithetic twin, i.e. use -Z1, -Z2, Z_jump, -Z_jump_size (engine/monte_carlo.py:318-324) WITHOUT the caller
+ * materialising negated copies of the arrays (the negation is exact). */
+#define B200MC_GIVEN_RECORD 1
+#define B200MC_GIVEN_NEGATE 2
 /* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the handle's stream. */
 int b200mc_simulate_given_normals_dev(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
                                       int64_t n_paths, int32_t n_steps,
                                       const double *Z1, const double *Z2,
                                       const double *Z_jump, const double *Z_jump_size,
                                       int record_paths, double *S_final, double *v_final, double *all_paths);
+
+/* ---- a2: NumPy's pseudo-random front end on the device, bit for bit --------------------------------------
+ * Replaces np.random.default_rng(seed).standard_normal((n, steps)) x 3 and default_rng(seed + 1).random((n, steps))
+ * (engine/monte_carlo.py:301-308, engine/greeks.py:33-41, :458-462) for rng="reference" runs: PCG64 + NumPy's 256-layer
+ * Ziggurat (numpy 2.3.5, random_standard_normal), the data-dependent stream resolved in parallel (csrc/np_normal.cu).
+ * state = {state_hi, state_lo, inc_hi, inc_lo} of default_rng(seed).bit_generator (the SeedSequence hash stays in NumPy);
+ * first_raw = generator outputs already consumed (consecutive calls on one generator chain through *raws_consumed);
+ * out: n doubles, device pointer when on_device else host.  Successive standard_normal calls on one generator are ONE
+ * stream, so Z1 | Z2 | Z_jump_size of the reference are a single call with n = 3 * n_paths * n_steps. */
+#define B200MC_NUMPY_RANDOM          0   /* Generator.random():          one output per double                    */
+#define B200MC_NUMPY_STANDARD_NORMAL 1   /* Generator.standard_normal(): 1.0215 outputs per double on average     */
+int b200mc_numpy_fill(b200mc_handle *h, const uint64_t state[4], uint64_t first_raw, int64_t n, int kind, int on_device,
+                      double *out, uint64_t *raws_consumed);
+/* The Ziggurat tables in use (numpy's ki_double / wi_double / fi_double).  Host only, no device needed. */
+int b200mc_numpy_ziggurat_tables(uint64_t ki[256], double wi[256], double fi[256]);
 
 /* ---- a2+a1+a3/a4/a6-a9 fused: Philox draws in registers, payoff and Greek sums reduced on chip ----------
  * Replaces the RNG front end + both kernel runs + the NumPy reductions of MonteCarloEngine.price

@@ -21,6 +21,8 @@ ANTITHETIC, GREEKS, FP64, FORCE_SVJ = 0x1, 0x2, 0x4, 0x8
 STREAM_GBM, STREAM_HESTON, STREAM_SVJ, STREAM_HEDGE = 0, 1, 2, 3
 Z1, Z2, ZJUMP_U, ZJUMP_SIZE = 0, 1, 2, 3
 F32, F64 = 0, 1
+NUMPY_RANDOM, NUMPY_STANDARD_NORMAL = 0, 1
+GIVEN_RECORD, GIVEN_NEGATE = 1, 2
 
 
 class B200MCError(RuntimeError):
@@ -130,6 +132,8 @@ _PROTOS = {
     "b200mc_qmc_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _vp, _vp, _i32, _i32, _vp, _i32,
                                        _vp, _vp, _u32, _vp, _vp]),
     "b200mc_pcg64_random": (C.c_int, [_vp, _vp, _u64, _i64, _vp]),
+    "b200mc_numpy_fill": (C.c_int, [_vp, _vp, _u64, _i64, C.c_int, C.c_int, _vp, C.POINTER(_u64)]),
+    "b200mc_numpy_ziggurat_tables": (C.c_int, [_vp, _vp, _vp]),
     "b200mc_simulate_terminal": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
                                             _u32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200mc_generate_paths": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _dbl, _i32, _i64, _u64, _u64,
@@ -195,6 +199,15 @@ def pcg64_state(seed) -> np.ndarray:
     st = np.random.default_rng(seed).bit_generator.state["state"]
     m = (1 << 64) - 1
     return np.array([st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m], dtype=np.uint64)
+
+
+def numpy_ziggurat_tables():
+    """(ki, wi, fi): the Ziggurat tables compiled into the library (numpy's ki_double / wi_double / fi_double)."""
+    ki, wi, fi = np.empty(256, np.uint64), np.empty(256, np.float64), np.empty(256, np.float64)
+    rc = load().b200mc_numpy_ziggurat_tables(ki.ctypes.data, wi.ctypes.data, fi.ctypes.data)
+    if rc != OK:
+        raise B200MCError(rc, "b200mc_numpy_ziggurat_tables failed")
+    return ki, wi, fi
 
 
 def sobol_tables(n_dims: int, seed: int):
@@ -452,6 +465,32 @@ class Handle:
         self._check(self.lib.b200mc_pcg64_random(self.h, st.ctypes.data, int(first), int(n), out.ctypes.data))
         return out
 
+    def numpy_fill(self, seed, n: int, kind: int = NUMPY_STANDARD_NORMAL, first_raw: int = 0, out_dev: Optional[int] = None):
+        """n doubles of np.random.default_rng(seed).standard_normal(...) (kind NUMPY_STANDARD_NORMAL) or .random(...)
+        (NUMPY_RANDOM), generated on the device bit for bit, starting `first_raw` generator outputs into the stream.
+        `seed` is anything default_rng accepts, or the uint64[4] state from pcg64_state.  Returns (array or None when
+        out_dev is given, generator outputs consumed)."""
+        st = seed if isinstance(seed, np.ndarray) and seed.dtype == np.uint64 and seed.size == 4 else pcg64_state(seed)
+        used = _u64(0)
+        if out_dev is not None:
+            self._check(self.lib.b200mc_numpy_fill(self.h, st.ctypes.data, int(first_raw), int(n), int(kind), 1, _vp(out_dev),
+                                                    C.byref(used)))
+            return None, int(used.value)
+        out = np.empty(int(n), dtype=np.float64)
+        self._check(self.lib.b200mc_numpy_fill(self.h, st.ctypes.data, int(first_raw), int(n), int(kind), 0, out.ctypes.data,
+                                                C.byref(used)))
+        return out, int(used.value)
+
+    def simulate_given_normals_dev(self, params, S0, T, n_paths, n_steps, Z1, Z2, Z_jump, Z_jump_size, S_dev, v_dev,
+                                   paths_dev: Optional[int] = None, negate: bool = False):
+        """b200mc_simulate_given_normals_dev: every array a DEVICE pointer; asynchronous on the handle's stream.
+        negate=True evaluates the antithetic twin (-Z1, -Z2, Z_jump, -Z_jump_size) on the same arrays."""
+        sp = to_params(params)
+        fl = (GIVEN_RECORD if paths_dev is not None else 0) | (GIVEN_NEGATE if negate else 0)
+        self._check(self.lib.b200mc_simulate_given_normals_dev(
+            self.h, C.byref(sp), float(S0), float(T), int(n_paths), int(n_steps), _vp(Z1), _vp(Z2), _vp(Z_jump),
+            _vp(Z_jump_size), fl, _vp(S_dev), _vp(v_dev), _vp(paths_dev) if paths_dev is not None else None))
+
     def qmc_terminal(self, params, S0, T, n_steps, n_paths, sobol, nodes=None, Z_jump=None, flags=0, path_offset=0,
                      pcg64_seed=None):
         """Terminal spots (and the antithetic twin's with ANTITHETIC) of Sobol-driven paths with a caller-supplied bridge
@@ -606,6 +645,68 @@ class Handle:
 
 _default = {}
 _default_lock = threading.Lock()
+
+
+class ReferenceDraws:
+    """The four arrays of the reference's pseudo-random front end, generated ON THE DEVICE and kept there:
+        g = default_rng(seed);  Z1, Z2, Z_jump_size = g.standard_normal((n, steps)) x 3
+        Z_jump = default_rng(seed + 1).random((n, steps))          engine/monte_carlo.py:301-308, engine/greeks.py:33-41
+    (uniform_seed=None: Z_jump continues the SAME generator after the normals, the order of get_sample_paths, :458-462).
+    NumPy's doubles bit for bit (csrc/np_normal.cu, csrc/pcg64.cu); nothing crosses PCIe.  simulate() runs the reference
+    recurrence over them (b200mc_simulate_given_normals_dev) and returns host arrays."""
+
+    def __init__(self, handle, seed, n_paths: int, n_steps: int, uniform_seed="seed+1"):
+        self.h, self.n, self.steps = handle, int(n_paths), int(n_steps)
+        N = self.n * self.steps
+        self.buf = handle.malloc(4 * N * 8 + 16 * self.n * 8)
+        self.Z1, self.Z2, self.Zjs, self.Zj = (self.buf + i * N * 8 for i in range(4))
+        self.S = self.buf + 4 * N * 8
+        self.v = self.S + self.n * 8
+        _, used = handle.numpy_fill(seed, 3 * N, NUMPY_STANDARD_NORMAL, 0, out_dev=self.Z1)
+        if uniform_seed is None:
+            handle.numpy_fill(seed, N, NUMPY_RANDOM, used, out_dev=self.Zj)
+        else:
+            handle.numpy_fill(seed + 1 if isinstance(uniform_seed, str) else uniform_seed, N, NUMPY_RANDOM, 0, out_dev=self.Zj)
+        self.raws_consumed = used
+
+    def simulate(self, params, S0, T, record_paths=False, negate=False):
+        paths_dev = None
+        if record_paths:
+            paths_dev = self.h.malloc(self.n * (self.steps + 1) * 8)
+        try:
+            self.h.simulate_given_normals_dev(params, S0, T, self.n, self.steps, self.Z1, self.Z2, self.Zj, self.Zjs, self.S,
+                                              self.v, paths_dev, negate)
+            S, v = np.empty(self.n), np.empty(self.n)
+            self.h.d2h(S, self.S)
+            self.h.d2h(v, self.v)
+            paths = None
+            if record_paths:
+                paths = np.empty((self.n, self.steps + 1))
+                self.h.d2h(paths, paths_dev)
+        finally:
+            if paths_dev is not None:
+                self.h.free(paths_dev)
+        return S, v, paths
+
+    def host_arrays(self):
+        """(Z1, Z2, Z_jump, Z_jump_size) copied to the host (tests)."""
+        out = []
+        for ptr in (self.Z1, self.Z2, self.Zj, self.Zjs):
+            a = np.empty((self.n, self.steps))
+            self.h.d2h(a, ptr)
+            out.append(a)
+        return out
+
+    def close(self):
+        if self.buf:
+            self.h.free(self.buf)
+            self.buf = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def default_handle(device: Optional[int] = None) -> Handle:

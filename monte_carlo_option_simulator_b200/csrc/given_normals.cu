@@ -27,6 +27,7 @@ constexpr int GN_WARPS = 4;
 
 struct GivenArgs {
     double S0, v0, dt, sqrt_dt, drift_comp, kappa, theta, xi, rho, sq1mr2, jump_thr, mu_j, sigma_j;
+    double zsign;            // +1, or -1 for the antithetic twin: -Z1, -Z2, U, -Z_jump_size (monte_carlo.py:318-324); exact
     int64_t n_paths;
     int32_t n_steps;
     int32_t need_z2, need_jump, record;
@@ -95,20 +96,20 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
             __syncwarp();
             const int ns = min(GN_TS, a.n_steps - s0);
             for (int t = 0; t < ns; ++t) {
-                const double z1 = t1[lane * GN_PITCH + t];
+                const double z1 = __dmul_rn(a.zsign, t1[lane * GN_PITCH + t]);
                 const double v_pos = fmax(v, 0.0);                               // :223
                 const double sqrt_v = sqrt(v_pos);                               // :224
                 const double dW1 = __dmul_rn(z1, a.sqrt_dt);                     // :226
                 double dW2 = 0.0;                                                // :227 (unused when xi == 0)
                 if (a.need_z2)
                     dW2 = __dadd_rn(__dmul_rn(__dmul_rn(a.rho, z1), a.sqrt_dt),
-                                    __dmul_rn(__dmul_rn(a.sq1mr2, t2[lane * GN_PITCH + t]), a.sqrt_dt));
+                                    __dmul_rn(__dmul_rn(a.sq1mr2, __dmul_rn(a.zsign, t2[lane * GN_PITCH + t])), a.sqrt_dt));
                 const double log_drift = __dmul_rn(__dadd_rn(a.drift_comp, -__dmul_rn(0.5, v_pos)), a.dt);   // :229
                 const double log_diff = __dmul_rn(sqrt_v, dW1);                  // :230
                 double jump = 0.0;                                               // :232
                 if (a.need_jump) {
                     if (tj[lane * GN_PITCH + t] < a.jump_thr)                    // :233
-                        jump = __dadd_rn(a.mu_j, __dmul_rn(a.sigma_j, tjs[lane * GN_PITCH + t]));   // :234
+                        jump = __dadd_rn(a.mu_j, __dmul_rn(a.sigma_j, __dmul_rn(a.zsign, tjs[lane * GN_PITCH + t])));   // :234
                 }
                 S = __dmul_rn(S, exp(__dadd_rn(__dadd_rn(log_drift, log_diff), jump)));              // :236
                 const double mr = __dmul_rn(__dmul_rn(a.kappa, __dadd_rn(a.theta, -v_pos)), a.dt);
@@ -144,6 +145,9 @@ constexpr size_t H2D_CHUNK = (size_t)4 << 20;
 
 static int parallel_h2d(b200mc_handle *h, void *dst, const void *src, size_t bytes)
 {
+    // the destination (d_stage) may still be read by work queued on the handle's stream; the workers below copy on
+    // private streams, so that work has to drain first
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
     if (bytes < 8 * H2D_CHUNK) {
         B200MC_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
         return 0;
@@ -196,7 +200,8 @@ static int check_given(b200mc_handle *h, const b200mc_svj_params *p, int64_t n_p
     if (!(T == T)) return fail(h, B200MC_EINVAL, "T is NaN");
     if (n_paths > 0 && (!Z1 || !Z2 || !Zj || !Zjs || !S_final || !v_final))
         return fail(h, B200MC_EINVAL, "NULL array argument");
-    if (record && n_paths > 0 && !all_paths) return fail(h, B200MC_EINVAL, "record_paths set but all_paths is NULL");
+    if ((record & B200MC_GIVEN_RECORD) && n_paths > 0 && !all_paths) return fail(h, B200MC_EINVAL, "record_paths set but all_paths is NULL");
+    if (record & ~(B200MC_GIVEN_RECORD | B200MC_GIVEN_NEGATE)) return fail(h, B200MC_EINVAL, "record_paths: unknown flag bits");
     return 0;
 }
 
@@ -217,7 +222,8 @@ static GivenArgs make_args(const b200mc_svj_params *p, double S0, double T, int6
     a.need_z2 = (p->xi != 0.0) ? 1 : 0;
     // Z_jump is a uniform in [0, 1): with lambda_j dt <= 0 the test :233 can never fire
     a.need_jump = (a.jump_thr > 0.0) ? 1 : 0;
-    a.record = record ? 1 : 0;
+    a.record = (record & B200MC_GIVEN_RECORD) ? 1 : 0;
+    a.zsign = (record & B200MC_GIVEN_NEGATE) ? -1.0 : 1.0;
     return a;
 }
 
@@ -272,9 +278,10 @@ extern "C" int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_
     if (n_paths == 0) return 0;
     B200MC_CUDA(h, cudaSetDevice(h->device));
     GivenArgs a = make_args(p, S0, T, n_paths, n_steps, record_paths);
+    const bool rec = (record_paths & B200MC_GIVEN_RECORD) != 0;
     const int narr = 1 + a.need_z2 + 2 * a.need_jump;
     // stage at most ~2 GiB of inputs + outputs per chunk of paths
-    const size_t in_row = (size_t)n_steps * 8, out_row = 16 + (record_paths ? (size_t)(n_steps + 1) * 8 : 0);
+    const size_t in_row = (size_t)n_steps * 8, out_row = 16 + (rec ? (size_t)(n_steps + 1) * 8 : 0);
     const size_t per_path = (size_t)narr * in_row + out_row;
     int64_t chunk = (int64_t)(((size_t)2 << 30) / per_path);
     chunk = chunk < 32 ? 32 : (chunk & ~(int64_t)31);
@@ -289,7 +296,7 @@ extern "C" int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_
     }
     double *dS = (double *)(base + off); off += (size_t)chunk * 8;
     double *dv = (double *)(base + off); off += (size_t)chunk * 8;
-    double *dP = record_paths ? (double *)(base + off) : nullptr;
+    double *dP = rec ? (double *)(base + off) : nullptr;
     const double *src[4] = {Z1, Z2, Z_jump, Z_jump_size};
     for (int64_t p0 = 0; p0 < n_paths; p0 += chunk) {
         const int64_t np = (n_paths - p0 < chunk) ? (n_paths - p0) : chunk;
@@ -301,7 +308,7 @@ extern "C" int b200mc_simulate_given_normals(b200mc_handle *h, const b200mc_svj_
                                 dP));
         B200MC_CUDA(h, cudaMemcpyAsync(S_final + p0, dS, (size_t)np * 8, cudaMemcpyDeviceToHost, h->stream));
         B200MC_CUDA(h, cudaMemcpyAsync(v_final + p0, dv, (size_t)np * 8, cudaMemcpyDeviceToHost, h->stream));
-        if (record_paths)
+        if (rec)
             B200MC_CUDA(h, cudaMemcpyAsync(all_paths + (size_t)p0 * (n_steps + 1), dP, (size_t)np * (n_steps + 1) * 8,
                                            cudaMemcpyDeviceToHost, h->stream));
         B200MC_CUDA(h, cudaStreamSynchronize(h->stream));

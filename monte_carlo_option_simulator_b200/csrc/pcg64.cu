@@ -7,33 +7,9 @@
 // "square and multiply" on (multiplier, increment) pairs in 128-bit arithmetic and then produces its chunk.  The caller
 // passes the generator's 128-bit state and increment (NumPy: default_rng(seed).bit_generator.state), so the seeding hash
 // (SeedSequence) stays in NumPy.  With this the reference's use_sobol=True front end needs no host array at all.
-#include "common.cuh"
+#include "pcg64.cuh"
 
 namespace b200mc {
-
-struct U128 {
-    unsigned long long hi, lo;
-};
-__host__ __device__ __forceinline__ U128 mul128(U128 a, U128 b)
-{
-    U128 r;
-#ifdef __CUDA_ARCH__
-    r.lo = a.lo * b.lo;
-    r.hi = __umul64hi(a.lo, b.lo) + a.hi * b.lo + a.lo * b.hi;
-#else
-    const unsigned __int128 p = ((unsigned __int128)a.hi << 64 | a.lo) * ((unsigned __int128)b.hi << 64 | b.lo);
-    r.lo = (unsigned long long)p;
-    r.hi = (unsigned long long)(p >> 64);
-#endif
-    return r;
-}
-__host__ __device__ __forceinline__ U128 add128(U128 a, U128 b)
-{
-    U128 r;
-    r.lo = a.lo + b.lo;
-    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
-    return r;
-}
 
 struct Pcg64Args {
     U128 state, inc;
@@ -44,29 +20,12 @@ struct Pcg64Args {
 
 __global__ void __launch_bounds__(256) k_pcg64_uniform(const __grid_constant__ Pcg64Args a, double *__restrict__ out)
 {
-    const U128 MULT = {0x2360ED051FC65DA4ull, 0x4385DF649FCCF645ull};
     const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * a.chunk;
     if (i0 >= a.n) return;
-    // advance the state by (first + i0) steps
-    unsigned long long delta = a.first + (unsigned long long)i0;
-    U128 acc_mult = {0ull, 1ull}, acc_plus = {0ull, 0ull}, cur_mult = MULT, cur_plus = a.inc;
-    while (delta) {
-        if (delta & 1ull) {
-            acc_mult = mul128(acc_mult, cur_mult);
-            acc_plus = add128(mul128(acc_plus, cur_mult), cur_plus);
-        }
-        cur_plus = mul128(add128(cur_mult, U128{0ull, 1ull}), cur_plus);
-        cur_mult = mul128(cur_mult, cur_mult);
-        delta >>= 1;
-    }
-    U128 s = add128(mul128(acc_mult, a.state), acc_plus);
+    U128 s = pcg64_advance(a.state, a.inc, a.first + (unsigned long long)i0);      // jump to output index first + i0
     const long long i1 = min(a.n, i0 + a.chunk);
     for (long long i = i0; i < i1; ++i) {
-        s = add128(mul128(s, MULT), a.inc);
-        const unsigned long long x = s.hi ^ s.lo;
-        const unsigned int rot = (unsigned int)(s.hi >> 58);
-        const unsigned long long o = (x >> rot) | (x << ((64u - rot) & 63u));
-        out[i] = (double)(o >> 11) * (1.0 / 9007199254740992.0);
+        out[i] = pcg64_double(pcg64_next(s, a.inc));
     }
 }
 

@@ -13,6 +13,7 @@ offered under new keys.  ``rng="reference"`` reproduces the reference draw for d
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -69,6 +70,16 @@ class GreeksEngine:
 
     # ---- rng="reference" helpers (greeks.py:33-51) -----------------------------------------------------------
     def _generate_shared_randoms(self, steps: int):
+        if hasattr(self.handle, "numpy_fill") and os.environ.get("B200MC_REFERENCE_PCG64", "device") == "device":
+            # NumPy's draws generated on the device and kept there (bit for bit, csrc/np_normal.cu); cached while
+            # (seed, n, steps) stay the same, which is how the reference obtains its common random numbers (:33-41)
+            key = (self.seed, int(self.num_paths), int(steps), id(self.handle))
+            cache = getattr(self, "_ref_draws", None)
+            if cache is None or cache[0] != key:
+                if cache is not None:
+                    cache[1].close()
+                self._ref_draws = cache = (key, _lib.ReferenceDraws(self.handle, self.seed, self.num_paths, steps))
+            return (cache[1],)
         g = np.random.default_rng(self.seed)
         Z1 = g.standard_normal((self.num_paths, steps))
         Z2 = g.standard_normal((self.num_paths, steps))
@@ -76,7 +87,12 @@ class GreeksEngine:
         Zj = np.random.default_rng(self.seed + 1).random((self.num_paths, steps))
         return Z1, Z2, Zj, Zjs
 
-    def _simulate_with_randoms(self, spot, T, Z1, Z2, Z_jump, Z_jump_size, steps, params=None):
+    def _simulate_with_randoms(self, spot, T, Z1, Z2=None, Z_jump=None, Z_jump_size=None, steps=None, params=None):
+        if isinstance(Z1, _lib.ReferenceDraws):            # device-resident draws: _generate_shared_randoms returned (d,)
+            if steps is None:
+                steps = Z2
+            S, v, _ = Z1.simulate(params or self.params, float(spot), T)
+            return S, v, np.zeros((0, 0))
         S, v, _ = self.handle.simulate_given_normals(params or self.params, float(spot), T, Z1, Z2, Z_jump,
                                                      Z_jump_size, steps)
         return S, v, np.zeros((0, 0))

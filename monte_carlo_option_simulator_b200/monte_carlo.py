@@ -546,6 +546,14 @@ class MonteCarloEngine:
     def get_sample_paths(self, spot: float, T: float, num_samples: int = 50) -> np.ndarray:
         """[num_samples, steps + 1] float64, column 0 = spot (monte_carlo.py:452-471)."""
         steps = steps_for(self.num_steps, T, floor=50)                         # :455
+        if self.rng == "reference" and hasattr(self.handle, "numpy_fill") and \
+                os.environ.get("B200MC_REFERENCE_PCG64", "device") == "device":
+            # :458-462 -- ONE generator (seed + 999): three normal arrays, then the jump uniforms from the same stream
+            d = _lib.ReferenceDraws(self.handle, self.seed + 999, int(num_samples), steps, uniform_seed=None)
+            try:
+                return d.simulate(self.params, float(spot), T, record_paths=True)[2]
+            finally:
+                d.close()
         if self.rng == "reference":
             g = np.random.default_rng(self.seed + 999)                         # :458-462
             Z1 = g.standard_normal((num_samples, steps))
@@ -573,12 +581,28 @@ class MonteCarloEngine:
             S, S_anti = h.qmc_terminal(p, float(spot), T, steps, n, cache[1], cache[2], None,
                                        ANTITHETIC if self.use_antithetic else 0, pcg64_seed=self.seed + 1)
             return steps, S, S_anti
+        if not self.use_sobol and hasattr(h, "numpy_fill") and os.environ.get("B200MC_REFERENCE_PCG64", "device") == "device":
+            # the reference's pseudo-random front end (:301-308) on the device: NumPy's PCG64 Ziggurat normals and uniforms
+            # bit for bit (csrc/np_normal.cu), kept in HBM and reused while (seed, n, steps) stay the same
+            d = self._reference_draws_device(n, steps)
+            S = d.simulate(p, float(spot), T)[0]
+            S_anti = d.simulate(p, float(spot), T, negate=True)[0] if self.use_antithetic else None      # :318-324
+            return steps, S, S_anti
         Z1, Z2, Zj, Zjs = _reference_draws(self.seed, n, steps, self.use_sobol)
         S = h.simulate_given_normals(p, float(spot), T, Z1, Z2, Zj, Zjs, steps)[0]
         S_anti = None
         if self.use_antithetic:                                                # :318-324
             S_anti = h.simulate_given_normals(p, float(spot), T, -Z1, -Z2, Zj, -Zjs, steps)[0]
         return steps, S, S_anti
+
+    def _reference_draws_device(self, n, steps):
+        key = (self.seed, int(n), int(steps), id(self.handle))
+        cache = getattr(self, "_ref_pcg64", None)
+        if cache is None or cache[0] != key:
+            if cache is not None:
+                cache[1].close()
+            self._ref_pcg64 = cache = (key, _lib.ReferenceDraws(self.handle, self.seed, n, steps))
+        return cache[1]
 
     def _price_reference(self, spot, strike, T, is_call):
         p, n = self.params, self.num_paths
