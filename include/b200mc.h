@@ -373,6 +373,11 @@ int b200mc_dump_philox(b200mc_handle *h, uint64_t seed, uint64_t path_offset, in
  * the two members of each Box-Muller pair }.  The statistical certificate of the generator (tools/normal_moments.py). */
 int b200mc_normal_moments(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths, int32_t n_blocks,
                           double out[6]);
+/* Counts of consecutive normals of the GBM stream on a 64 x 64 grid of equiprobable cells, out[64 a + b] with a, b =
+ * floor(64 Phi(z)) of the first / second member: lag 0 = the two members of every Box-Muller word, lag 1 = the second
+ * member of a word with the first member of the next word.  4 (lag 0) or 3 (lag 1) pairs per Philox block. */
+int b200mc_normal_hist2d(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths, int32_t n_blocks, int lag,
+                         uint64_t out[4096]);
 
 /* ---- device memory helpers for callers without a CUDA runtime of their own (ctypes) ---------------------- */
 int b200mc_malloc(b200mc_handle *h, size_t bytes, void **dev_ptr);

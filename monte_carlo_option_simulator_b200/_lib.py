@@ -147,6 +147,7 @@ _PROTOS = {
     "b200mc_select_stream": (C.c_int, [_vp, C.POINTER(SvjParams), _dbl, _i32, _u32, C.POINTER(Bumps), C.POINTER(_u32)]),
     "b200mc_dump_philox": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _u32, _vp]),
     "b200mc_normal_moments": (C.c_int, [_vp, _u64, _u64, _i64, _i32, _dp]),
+    "b200mc_normal_hist2d": (C.c_int, [_vp, _u64, _u64, _i64, _i32, C.c_int, _vp]),
     "b200mc_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "b200mc_free": (C.c_int, [_vp, _vp]),
     "b200mc_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
@@ -635,6 +636,13 @@ class Handle:
         self._check(self.lib.b200mc_normal_moments(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths),
                                                     int(n_blocks), out.ctypes.data_as(_dp)))
         return out
+
+    def normal_hist2d(self, seed, n_paths, n_blocks, lag=0, path_offset=0) -> np.ndarray:
+        """uint64[64, 64] counts of consecutive normals of the GBM stream on a grid of equiprobable cells (see the header)."""
+        out = np.zeros(4096, dtype=np.uint64)
+        self._check(self.lib.b200mc_normal_hist2d(self.h, int(seed) & (2 ** 64 - 1), int(path_offset), int(n_paths), int(n_blocks),
+                                                   int(lag), out.ctypes.data))
+        return out.reshape(64, 64)
 
     def dump_philox(self, seed, n_paths, n_blocks, stream, path_offset=0) -> np.ndarray:
         out = np.empty((n_paths, n_blocks, 4), dtype=np.uint32)

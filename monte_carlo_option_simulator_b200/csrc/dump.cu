@@ -72,7 +72,7 @@ __global__ void k_dump_jumps(PhiloxKey key, uint64_t path0, int64_t n_paths, int
         const uint64_t path = path0 + (uint64_t)pi;
         const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
         JumpStream jmp;
-        jmp.init(c0, c1, key, inv_lg2_q, jump_on != 0);
+        jmp.init(c0, c1, key, inv_lg2_q, 2, jump_on != 0);
         U4 fill = U4{0u, 0u, 0u, 0u};
         for (int s = 0; s < n_steps; ++s) {
             if (which == B200MC_ZJUMP_U && (s & 3) == 0)
@@ -80,9 +80,9 @@ __global__ void k_dump_jumps(PhiloxKey key, uint64_t path0, int64_t n_paths, int
             const uint32_t fw = (s & 3) == 0 ? fill.x : (s & 3) == 1 ? fill.y : (s & 3) == 2 ? fill.z : fill.w;
             double val;
             if (s == jmp.next) {
-                if (which == B200MC_ZJUMP_U) val = jump_prob * word_uniform(jmp.w_size);      // < jump_prob
-                else val = B200MC_BM_SCALE * (double)jmp.size_raw();
-                jmp.advance(c0, c1, key, inv_lg2_q, s);
+                if (which == B200MC_ZJUMP_U) val = jump_prob * word_uniform(jmp.jword[jmp.m & 1u]);      // < jump_prob
+                else val = B200MC_BM_SCALE * (double)jmp.size_raw(2);
+                jmp.advance(c0, c1, key, inv_lg2_q, 2, s);
             } else if (which == B200MC_ZJUMP_U) {
                 val = jump_prob + (1.0 - jump_prob) * word_uniform(fw);
                 if (!(val > jump_prob)) val = 1.0;                                            // never below the threshold
@@ -125,8 +125,66 @@ k_normal_moments(const __grid_constant__ PhiloxKey key, uint64_t path0, int64_t 
     block_finish<6>(v, smem, partials, counter, out);
 }
 
+// Joint distribution of consecutive normals of the GBM stream on a 64 x 64 grid of EQUIPROBABLE cells (cell = floor(64
+// Phi(z))): the input of the chi-square / Kolmogorov checks of the generator (tests/test_gpu_rng_quality.py).
+//   lag 0: the two members of every Box-Muller pair (same 32-bit word)
+//   lag 1: the second member of word i with the first member of word i + 1 (adjacent words of a Philox block)
+__global__ void __launch_bounds__(256)
+k_normal_hist2d(const __grid_constant__ PhiloxKey key, uint64_t path0, int64_t n_paths, int n_blocks, int lag,
+                unsigned long long *__restrict__ out)
+{
+    __shared__ unsigned int hist[64 * 64];
+    for (int i = threadIdx.x; i < 4096; i += 256) hist[i] = 0u;
+    __syncthreads();
+    auto cell = [](float raw) -> int {
+        const double u = normcdf(B200MC_BM_SCALE * (double)raw);
+        const int c = (int)(u * 64.0);
+        return c > 63 ? 63 : c;
+    };
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_paths; i += (int64_t)gridDim.x * 256) {
+        const uint64_t path = path0 + (uint64_t)i;
+        for (int j = 0; j < n_blocks; ++j) {
+            const U4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)j, B200MC_STREAM_GBM, key);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            BM2 b[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) b[t] = box_muller_word(ww[t]);
+            if (lag == 0) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) atomicAdd(&hist[cell(b[t].rc) * 64 + cell(b[t].rs)], 1u);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) atomicAdd(&hist[cell(b[t].rs) * 64 + cell(b[t + 1].rc)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += 256)
+        if (hist[i]) atomicAdd(&out[i], (unsigned long long)hist[i]);
+}
+
 } // namespace b200mc
 using namespace b200mc;
+
+extern "C" int b200mc_normal_hist2d(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths, int32_t n_blocks,
+                                    int lag, uint64_t out[4096])
+{
+    if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
+    if (!out || n_paths <= 0 || n_blocks <= 0 || lag < 0 || lag > 1) return fail(h, B200MC_EINVAL, "bad argument");
+    B200MC_CUDA(h, cudaSetDevice(h->device));
+    // a CTA's shared 32-bit cells must not overflow: at most 2^31 pairs per CTA
+    const int grid = h->sm_count * 8;
+    if ((double)n_paths * n_blocks * 4.0 / grid > 2.0e9) return fail(h, B200MC_EINVAL, "too many draws per launch: split the call");
+    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, 4096 * 8));
+    B200MC_CUDA(h, cudaMemsetAsync(h->d_scratch, 0, 4096 * 8, h->stream));
+    k_normal_hist2d<<<grid, 256, 0, h->stream>>>(philox_make_key(seed), path_offset, n_paths, n_blocks, lag,
+                                                 (unsigned long long *)h->d_scratch);
+    B200MC_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    B200MC_CUDA(h, cudaMemcpyAsync(out, h->d_scratch, 4096 * 8, cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
 
 extern "C" int b200mc_normal_moments(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths,
                                      int32_t n_blocks, double out[6])

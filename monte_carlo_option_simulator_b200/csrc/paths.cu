@@ -21,10 +21,10 @@ namespace b200mc {
 
 constexpr int PT_THREADS = 256;
 #ifndef B200MC_PATHS_DEFAULT_POLY
-#define B200MC_PATHS_DEFAULT_POLY 0
+#define B200MC_PATHS_DEFAULT_POLY 1
 #endif
 #ifndef B200MC_PATHS_DEFAULT_MINB
-#define B200MC_PATHS_DEFAULT_MINB 1
+#define B200MC_PATHS_DEFAULT_MINB 4
 #endif
 constexpr float LOG2E_F = 1.4426950408889634f;
 

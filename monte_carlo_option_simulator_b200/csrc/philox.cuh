@@ -155,34 +155,47 @@ struct JumpStream {
     // Philox stream B200MC_STREAM_SVJ_JUMP, counter block k -> jumps 2k and 2k + 1 of the path:
     //   (w0 -> gap before jump 2k, w1 -> its size), (w2 -> gap before jump 2k + 1, w3 -> its size)
     // size: Z_jump_size = B200MC_BM_SCALE * rc(BM(w)) (the cosine member of the word's Box-Muller pair)
-    int next, next2;            // step index of the next jump and of the one after it
-    uint32_t w_size, w_size2;   // their size words
+    // The next `pf` (2 or 4) jumps of the path are kept in a small ring (thread-local memory, touched only when a jump
+    // fires): the Philox calls and log2 evaluations that fill it run for ALL lanes at the start of the path, so the
+    // divergent branch taken when a lane jumps is a dozen instructions instead of a Philox call -- with lambda T ~ 1
+    // a path rarely needs a refill inside the step loop.  pf only sets how far ahead the stream is read, never WHAT it
+    // holds (the host picks it from lambda T).
+    int next;                   // step index of the next jump
     uint32_t m;                 // jumps consumed so far
+    int jstep[4];               // ring: step index of jump m + i (slot (m + i) & (pf - 1))
+    uint32_t jword[4];          // ring: its size word
 
-    __device__ __forceinline__ void refill(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int from)
+    __device__ __forceinline__ void refill(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int pf, int from)
     {
-        const U4 q = philox4x32_10(c0, c1, m >> 1, B200MC_STREAM_SVJ_JUMP, key);
-        next = from + jump_gap(q.x, inv_lg2_q);
-        w_size = q.y;
-        next2 = next + 1 + jump_gap(q.z, inv_lg2_q);
-        w_size2 = q.w;
+        int at = from;
+        for (int c = 0; c < (pf >> 1); ++c) {
+            const U4 q = philox4x32_10(c0, c1, (m >> 1) + (uint32_t)c, B200MC_STREAM_SVJ_JUMP, key);
+            at += jump_gap(q.x, inv_lg2_q);
+            jstep[2 * c] = at;
+            jword[2 * c] = q.y;
+            at += 1 + jump_gap(q.z, inv_lg2_q);
+            jstep[2 * c + 1] = at;
+            jword[2 * c + 1] = q.w;
+            at += 1;
+        }
+        next = jstep[0];
     }
-    __device__ __forceinline__ void init(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, bool on)
+    __device__ __forceinline__ void init(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int pf, bool on)
     {
         m = 0u;
-        next = next2 = 0x7fffffff;
-        w_size = w_size2 = 0u;
-        if (on) refill(c0, c1, key, inv_lg2_q, 0);
-    }
-    // the jump at step `s` (== next) has been applied: move to the following one
-    __device__ __forceinline__ void advance(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int s)
-    {
-        ++m;
-        if (m & 1u) { next = next2; w_size = w_size2; }
-        else refill(c0, c1, key, inv_lg2_q, s + 1);
+        next = 0x7fffffff;
+        if (on) refill(c0, c1, key, inv_lg2_q, pf, 0);
     }
     // unscaled size draw of the pending jump: Z_jump_size = B200MC_BM_SCALE * size_raw()
-    __device__ __forceinline__ float size_raw() const { return box_muller_word(w_size).rc; }
+    __device__ __forceinline__ float size_raw(int pf) const { return box_muller_word(jword[m & (uint32_t)(pf - 1)]).rc; }
+    // the jump at step `s` (== next) has been applied: move to the following one
+    __device__ __forceinline__ void advance(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int pf, int s)
+    {
+        ++m;
+        const uint32_t slot = m & (uint32_t)(pf - 1);
+        if (slot == 0u) refill(c0, c1, key, inv_lg2_q, pf, s + 1);
+        else next = jstep[slot];
+    }
 };
 
 } // namespace b200mc

@@ -38,7 +38,7 @@ struct ModelArgs {
     double mu_j, sigma_j;
     double sigma_j_s;       // sigma_j BM_SCALE
     int32_t jump_on;        // lambda_j dt > 0                                :233
-    int32_t pad_;
+    int32_t jump_prefetch;  // 2 or 4: jumps of a path read ahead of the step loop (JumpStream)
     double v0[3];           // base, up, down
     double x_drift[3];      // GBM / DETVAR: total drift of x over [0, T] for the three variance starts
     double x_w[3];          // GBM: x_T = x_drift + x_w * sum(raw z);  x_w = sqrt(v0 dt) BM_SCALE
@@ -233,7 +233,8 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         // variance steps of block j.
         JumpStream jmp;
         const float inv_lg2_q = (float)m.jump_inv_lg2q;
-        if constexpr (MODE == MODE_SVJ) jmp.init(c0, c1, key, inv_lg2_q, m.jump_on != 0);
+        const int jpf = m.jump_prefetch;
+        if constexpr (MODE == MODE_SVJ) jmp.init(c0, c1, key, inv_lg2_q, jpf, m.jump_on != 0);
         constexpr uint32_t STREAM = MODE == MODE_HESTON ? B200MC_STREAM_HESTON : B200MC_STREAM_SVJ;
         const int nblk = (n_steps + 3) >> 2;
         U4 u = philox4x32_10(c0, c1, 0u, STREAM, key);
@@ -250,10 +251,10 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                     sv_step<R, ANTI, GREEKS>(x, v, c, zs1, zsc);
                     if constexpr (MODE == MODE_SVJ) {
                         if (s == jmp.next) {                                             // :233-234, rare
-                            const R jsz = c.sigma_j_s * (R)jmp.size_raw();
+                            const R jsz = c.sigma_j_s * (R)jmp.size_raw(jpf);
 #pragma unroll
                             for (int k = 0; k < NS; ++k) x[k] += (ANTI && k == 1) ? c.mu_j - jsz : c.mu_j + jsz;
-                            jmp.advance(c0, c1, key, inv_lg2_q, s);
+                            jmp.advance(c0, c1, key, inv_lg2_q, jpf, s);
                         }
                     }
                     if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }

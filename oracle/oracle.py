@@ -87,6 +87,13 @@ def _load():
     lib.oracle_philox_block_words.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64,
                                               ctypes.c_int32, ctypes.c_uint32, u32p]
     lib.oracle_num_threads.restype = ctypes.c_int
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    lib.oracle_np_standard_normal.restype = ctypes.c_uint64
+    lib.oracle_np_standard_normal.argtypes = [u64p, u64p, dp, dp, ctypes.c_int64, dp]
+    lib.oracle_glibc_log1p_fma.restype = ctypes.c_double
+    lib.oracle_glibc_log1p_fma.argtypes = [ctypes.c_double]
+    lib.oracle_log1p_mismatches.restype = ctypes.c_int64
+    lib.oracle_log1p_mismatches.argtypes = [ctypes.c_int64, ctypes.c_uint64]
     _lib = lib
     return lib
 
@@ -691,6 +698,28 @@ def qmc_draws(seed: int, n_paths: int, steps: int, n_blocks: int, path_offset: i
     Zjs = norm.ppf(blk(2)) if n_blocks >= 4 else np.zeros_like(Z1)
     Zj = blk(3).copy() if n_blocks >= 4 else np.ones_like(Z1)
     return Z1, Z2, Zj, Zjs
+
+
+# --------------------------------------------------------------------------------------------
+# NumPy's PCG64 + Ziggurat standard_normal restated (checker of csrc/np_normal.cu; engine/monte_carlo.py:301-304)
+# --------------------------------------------------------------------------------------------
+def np_standard_normal(seed, n: int, tables):
+    """(normals, generator outputs consumed) of np.random.default_rng(seed).standard_normal(n), computed by the C
+    restatement oracle_np_standard_normal from the generator's initial state and the Ziggurat tables (ki, wi, fi)."""
+    st = np.random.default_rng(seed).bit_generator.state["state"]
+    m = (1 << 64) - 1
+    state = np.array([st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m], dtype=np.uint64)
+    ki, wi, fi = (np.ascontiguousarray(t) for t in tables)
+    out = np.empty(int(n), dtype=np.float64)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    used = _load().oracle_np_standard_normal(state.ctypes.data_as(u64p), ki.ctypes.data_as(u64p), _dptr(wi), _dptr(fi), int(n),
+                                             _dptr(out))
+    return out, int(used)
+
+
+def log1p_mismatches(n: int, seed: int = 0) -> int:
+    """Arguments (of 2n) on which the restated glibc FMA log1p differs from the host's log1p by even one bit."""
+    return int(_load().oracle_log1p_mismatches(int(n), int(seed)))
 
 
 # --------------------------------------------------------------------------------------------

@@ -121,3 +121,135 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * NumPy's pseudo-random front end (a third-party dependency of the reference: numpy 2.3.5 here; the reference calls
+ * np.random.default_rng(seed).standard_normal((n, steps)) x 3 and .random((n, steps)), engine/monte_carlo.py:301-308,
+ * engine/greeks.py:33-41).  Restated from the published algorithm -- PCG64 (pcg64 XSL-RR 128/64) and the 256-layer
+ * Ziggurat of numpy/random/src/distributions/distributions.c (random_standard_normal) -- as the CPU checker of
+ * csrc/np_normal.cu.  Pinned: tests/test_oracle.py compares it bit for bit with NumPy itself in the dev container.
+ * The three tables (ki_double / wi_double / fi_double) are passed in by the caller. */
+static inline uint64_t pcg64_next(unsigned __int128 *s, unsigned __int128 inc)
+{
+    const unsigned __int128 MULT = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    *s = *s * MULT + inc;
+    const uint64_t hi = (uint64_t)(*s >> 64), lo = (uint64_t)*s, x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+static inline double pcg64_double(uint64_t o) { return (double)(o >> 11) * (1.0 / 9007199254740992.0); }
+
+/* state = {state_hi, state_lo, inc_hi, inc_lo} BEFORE the first output wanted.  Returns the generator outputs consumed. */
+uint64_t oracle_np_standard_normal(const uint64_t state[4], const uint64_t *ki, const double *wi, const double *fi,
+                                   int64_t n, double *out)
+{
+    const double R = 3.6541528853610087963519472518, INV_R = 0.27366123732975827203338247596;
+    unsigned __int128 s = ((unsigned __int128)state[0] << 64) | state[1], inc = ((unsigned __int128)state[2] << 64) | state[3];
+    uint64_t used = 0;
+    for (int64_t i = 0; i < n;) {
+        uint64_t r = pcg64_next(&s, inc);
+        ++used;
+        const int idx = (int)(r & 0xff);
+        r >>= 8;
+        const int sign = (int)(r & 1);
+        const uint64_t rabs = (r >> 1) & 0x000fffffffffffffull;
+        double x = (double)rabs * wi[idx];
+        if (sign) x = -x;
+        if (rabs < ki[idx]) { out[i++] = x; continue; }
+        if (idx == 0) {
+            for (;;) {
+                const double xx = -INV_R * log1p(-pcg64_double(pcg64_next(&s, inc)));
+                const double yy = -log1p(-pcg64_double(pcg64_next(&s, inc)));
+                used += 2;
+                if (yy + yy > xx * xx) { out[i++] = ((rabs >> 8) & 1) ? -(R + xx) : R + xx; break; }
+            }
+        } else {
+            const double u = pcg64_double(pcg64_next(&s, inc));
+            ++used;
+            if ((fi[idx - 1] - fi[idx]) * u + fi[idx] < exp(-0.5 * x * x)) out[i++] = x;
+        }
+    }
+    return used;
+}
+
+/* glibc 2.28+ sysdeps/ieee754/dbl-64/s_log1p.c in the operation order and with the fused multiply-adds of its x86-64 FMA
+ * build (the variant the dynamic loader picks on hosts with FMA, hence what NumPy's log1p is there).  csrc/np_normal.cu
+ * carries the same sequence for the tail draws of the Ziggurat; tests/test_oracle.py checks this function bit for bit
+ * against the host's log1p.  (File built with -ffp-contract=off: only the explicit fma() calls fuse.) */
+double oracle_glibc_log1p_fma(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 Lp1 = 6.666666666666735130e-01, Lp2 = 3.999999999940941908e-01, Lp3 = 2.857142874366239149e-01,
+                 Lp4 = 2.222219843214978396e-01, Lp5 = 1.818357216161805012e-01, Lp6 = 1.531383769920937332e-01,
+                 Lp7 = 1.479819860511658591e-01;
+    union { double d; uint64_t u; } b;
+    double f = 0.0, c = 0.0, u;
+    int32_t hu = 0, k = 1;
+    b.d = x;
+    const int32_t hx = (int32_t)(b.u >> 32), ax = hx & 0x7fffffff;
+    if (hx < 0x3FDA827A) {
+        if (ax >= 0x3ff00000) return x == -1.0 ? -INFINITY : NAN;
+        if (ax < 0x3e200000) return ax < 0x3c900000 ? x : fma(-(x * x), 0.5, x);
+        if (hx > 0 || hx <= (int32_t)0xbfd2bec3) { k = 0; f = x; hu = 1; }
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    if (k != 0) {
+        if (hx < 0x43400000) {
+            u = 1.0 + x;
+            b.d = u; hu = (int32_t)(b.u >> 32);
+            k = (hu >> 20) - 1023;
+            c = (k > 0) ? 1.0 - (u - x) : x - (u - 1.0);
+            c /= u;
+        } else {
+            u = x;
+            b.d = u; hu = (int32_t)(b.u >> 32);
+            k = (hu >> 20) - 1023;
+            c = 0;
+        }
+        hu &= 0x000fffff;
+        b.d = u;
+        if (hu < 0x6a09e) {
+            b.u = (b.u & 0xffffffffull) | ((uint64_t)(uint32_t)(hu | 0x3ff00000) << 32);
+        } else {
+            k += 1;
+            b.u = (b.u & 0xffffffffull) | ((uint64_t)(uint32_t)(hu | 0x3fe00000) << 32);
+            hu = (0x00100000 - hu) >> 2;
+        }
+        u = b.d;
+        f = u - 1.0;
+    }
+    const double hfsq = 0.5 * f * f, dk = (double)k;
+    if (hu == 0) {
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            c = fma(dk, ln2_lo, c);
+            return fma(dk, ln2_hi, c);
+        }
+        const double R = hfsq * fma(-0.66666666666666666, f, 1.0);
+        if (k == 0) return f - R;
+        return fma(dk, ln2_hi, -((R - fma(dk, ln2_lo, c)) - f));
+    }
+    const double s = f / (2.0 + f), z = s * s;
+    const double z2 = z * z, R2 = fma(z, Lp3, Lp2), z4 = z2 * z2, R3 = fma(z, Lp5, Lp4), z6 = z4 * z2, R4 = fma(z, Lp7, Lp6);
+    const double R = fma(z6, R4, fma(z4, R3, fma(z, Lp1, z2 * R2)));
+    const double sp = s * (hfsq + R);
+    if (k == 0) return f - (hfsq - sp);
+    return fma(dk, ln2_hi, -((hfsq - (sp + fma(dk, ln2_lo, c))) - f));
+}
+
+/* bitwise mismatches between oracle_glibc_log1p_fma and the host's log1p over n arguments -U, U uniform in [0, 1),
+ * and over the same arguments scaled down by random powers of two (the small-|x| branches) */
+int64_t oracle_log1p_mismatches(int64_t n, uint64_t seed)
+{
+    uint64_t st = seed ? seed : 88172645463325252ull;
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        const double u = (double)(st >> 11) * (1.0 / 9007199254740992.0);
+        const double a = -u, b = -u * ldexp(1.0, -(int)(st & 63));
+        union { double d; uint64_t u; } p, q;
+        p.d = log1p(a); q.d = oracle_glibc_log1p_fma(a); bad += p.u != q.u;
+        p.d = log1p(b); q.d = oracle_glibc_log1p_fma(b); bad += p.u != q.u;
+    }
+    return bad;
+}

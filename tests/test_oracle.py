@@ -2,11 +2,13 @@
 import ctypes
 import hashlib
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
 
-from conftest import assert_tree_close, unnan
+from conftest import ROOT, assert_tree_close, unnan
 from oracle import oracle as O
 
 PNAMES = ["svj_default", "gbm_cfg1", "heston", "jumpy"]
@@ -270,3 +272,43 @@ def test_qmc_draws_blocks():
     assert 0 < Zj.min() and Zj.max() < 1
     Z1b, Z2b, Zjb, Zjsb = O.qmc_draws(3, 64, 10, 1)
     assert not Z2b.any() and (Zjb == 1).all() and not Zjsb.any()
+
+
+# ---------------------------------------------------------------------------------------------- NumPy's RNG front end
+def test_ziggurat_tables_in_the_library_are_numpys():
+    """csrc/np_ziggurat_tables.inc (compiled into libb200mc.so) against numpy's own static library, bit for bit."""
+    import shutil
+    from monte_carlo_option_simulator_b200 import _lib
+    ki, wi, fi = _lib.numpy_ziggurat_tables()
+    assert ki[0] == 0x000EF33D8025EF6A and ki[1] == 0 and wi[0] == 8.68362706080130616677e-16 and fi[0] == 1.0
+    assert np.all(np.diff(fi) < 0) and fi[255] == pytest.approx(np.exp(-0.5 * 3.6541528853610088 ** 2), rel=1e-14)
+    if shutil.which("ar"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import extract_ziggurat_tables as X
+        k2, w2, f2 = X.extract()
+        assert np.array_equal(ki, k2) and np.array_equal(wi.view(np.uint64), w2.view(np.uint64))
+        assert np.array_equal(fi.view(np.uint64), f2.view(np.uint64))
+
+
+@pytest.mark.parametrize("seed,n", [(42, 200_000), (7, 50_000), (2 ** 63 + 5, 1000)])
+def test_np_standard_normal_restatement_equals_numpy(seed, n):
+    """The oracle's PCG64 + Ziggurat (checker of csrc/np_normal.cu) against NumPy itself, bit for bit."""
+    from monte_carlo_option_simulator_b200 import _lib
+    got, used = O.np_standard_normal(seed, n, _lib.numpy_ziggurat_tables())
+    g = np.random.default_rng(seed)
+    want = g.standard_normal(n)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert g.bit_generator.random_raw(1)[0] == np.random.PCG64(seed).random_raw(used + 1)[used]
+
+
+def test_glibc_fma_log1p_restatement_is_the_hosts_log1p():
+    """The tail draws of NumPy's Ziggurat go through the host's log1p; the device carries glibc's FMA build of it.  On a
+    host with FMA (every x86-64 server CPU of the last decade) the restatement must equal libm bit for bit."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    if " fma" not in flags:
+        pytest.skip("host CPU without FMA: glibc selects its non-FMA log1p here")
+    assert O.log1p_mismatches(2_000_000) == 0
+    assert O._load().oracle_glibc_log1p_fma(-0.5) == math.log1p(-0.5)
