@@ -9,6 +9,8 @@
 // Index conventions are the reference's: cutoff = int(n (1 - confidence)) (:128), var = -sorted[cutoff] (:129),
 // cvar = -mean(sorted[:cutoff]) (:130), k = max(int(sqrt(m)), 10) clipped to m - 1 over the m strictly negative
 // returns, tail index only when m > 20 (:147-150,162-173).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200mc {
@@ -109,16 +111,379 @@ k_risk_pass2(const T *__restrict__ x, int64_t n, double mean, int nsel, const Se
     block_finish<6>(v, smem, partials, counter, out);
 }
 
+
+// ---------------------------------------------------------------------------------------------- fused: ONE launch
+// The same exact selection as the kernels above, but as one persistent cooperative kernel: no keys array, no host
+// decision in the middle, the vector is read ONCE PER DIGIT (6 x 11-bit digits for float64 input, 3 for float32) instead
+// of 10 times, and everything else rides on those passes:
+//   pass 0   sum, count of negatives, histogram of the top digit (shared by both selections)
+//   pass d   candidates of each selection (prefix equal so far) -> histogram of digit d; elements that fell BELOW the
+//            prefix at the previous digit are, exactly once, added to that selection's tail sums (count, sum for CVaR,
+//            sum of log|x| for Hill); pass 1 also accumulates the central moments (the mean is known after pass 0)
+//   end      candidates that differ from the threshold only in the last digit all equal value(prefix | b): their tail
+//            contribution comes from the last histogram alone
+// Between passes: a grid barrier, then EVERY CTA picks the digit from the global histogram itself (2048 bins, one block
+// scan) -- no second barrier, no single-thread walk (k_risk_pick above is 10-24 us per pass: 150 of the 283 us a 4M-value
+// call took).  Sums are folded in a fixed order (per-CTA partials, then one ordered sum), so a launch geometry is
+// bitwise reproducible.  Measured on B200: see DESIGN.md section 4.4.
+constexpr int RF_THREADS = 512;
+constexpr int RF_BITS = 11;
+constexpr int RF_BINS = 1 << RF_BITS;
+constexpr int RF_MAXPASS = 6;
+constexpr int RF_NACC = 9;       // c2, c3, c4, cnt0, sum0, cnt1, logsum1, sum, neg
+
+struct FusedState {
+    unsigned int hist[RF_MAXPASS][2][RF_BINS];
+    unsigned int barrier;
+    unsigned int pad_[15];
+    double result[16];           // sum, neg, c2, c3, c4, cnt0, sum0, cnt1, logsum1, thr0, thr1
+};
+
+template <typename T> struct RfKey;
+template <> struct RfKey<double> {
+    using K = unsigned long long;
+    static constexpr int BITS = 64, NPASS = 6;
+    __device__ static __forceinline__ K of(double x) { return key_of(x); }
+    __device__ static __forceinline__ double value(K k) { return value_of(k); }
+};
+template <> struct RfKey<float> {
+    using K = unsigned int;
+    static constexpr int BITS = 32, NPASS = 3;
+    __device__ static __forceinline__ K of(float x)
+    {
+        const unsigned int b = __float_as_uint(x);
+        return (b >> 31) ? ~b : (b | 0x80000000u);
+    }
+    __device__ static __forceinline__ double value(K k)
+    {
+        const unsigned int b = (k >> 31) ? (k & 0x7fffffffu) : ~k;
+        return (double)__uint_as_float(b);
+    }
+};
+// digit d (0 = most significant) occupies bits [shift(d), shift(d) + width(d)): 11 bits each, the last one the remainder
+template <typename T> __device__ __forceinline__ int rf_shift(int d)
+{
+    const int s = RfKey<T>::BITS - RF_BITS * (d + 1);
+    return s > 0 ? s : 0;
+}
+template <typename T> __device__ __forceinline__ int rf_width(int d)
+{
+    const int hi = RfKey<T>::BITS - RF_BITS * d;
+    return hi < RF_BITS ? hi : RF_BITS;
+}
+
+__device__ __forceinline__ void rf_grid_sync(unsigned int *bar, unsigned int &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*(volatile unsigned int *)bar < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// deterministic sum of v over the CTA's threads -> every thread gets it
+__device__ __forceinline__ double rf_block_sum(double v, double *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < RF_THREADS / 32; ++w) t += red[w];
+    return t;
+}
+
+// every CTA: find, in the global histogram h (nbins bins), the bin that holds order statistic `rank`; returns the bin and
+// the number of elements in lower bins.  4 bins per thread + one block scan.
+__device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long long rank, unsigned long long *scan,
+                                        int *bin_out, long long *below_out)
+{
+    const int t = threadIdx.x;
+    unsigned int c[4];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = 4 * t + i;
+        c[i] = b < nbins ? __ldcg(h + b) : 0u;
+        mine += c[i];
+    }
+    // inclusive scan of `mine` over the 512 threads
+    const int lane = t & 31, warp = t >> 5;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nb;
+    }
+    __syncthreads();
+    if (lane == 31) scan[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0;
+    for (int w = 0; w < warp; ++w) before += scan[w];
+    unsigned long long cum = before + inc - mine;                 // elements in bins below 4 t
+    if (t == 0) { *bin_out = -1; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (c[i] != 0u && (long long)cum <= rank && rank < (long long)(cum + c[i])) { *bin_out = 4 * t + i; *below_out = (long long)cum; }
+        cum += c[i];
+    }
+    __syncthreads();
+    if (*bin_out < 0) {                                            // rank beyond the population (cannot happen for valid ranks)
+        if (t == 0) { *bin_out = nbins - 1; *below_out = 0; }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState *st, double *partials /* [grid][RF_NACC] */)
+{
+    using KT = RfKey<T>;
+    using K = typename KT::K;
+    constexpr int NPASS = KT::NPASS;
+    __shared__ unsigned int sh[2][RF_BINS];
+    __shared__ double red[RF_THREADS / 32];
+    __shared__ unsigned long long scan[RF_THREADS / 32];
+    __shared__ int s_bin[2];
+    __shared__ long long s_below[2];
+    __shared__ double s_mean;
+    __shared__ long long s_rank[2];
+    __shared__ int s_nsel;
+    const int tid = threadIdx.x;
+    unsigned int bar_target = 0;
+    const long long stride = (long long)gridDim.x * RF_THREADS, i0 = (long long)blockIdx.x * RF_THREADS + tid;
+
+    // ---- pass 0 -------------------------------------------------------------------------------------------------
+    for (int i = tid; i < RF_BINS; i += RF_THREADS) sh[0][i] = 0u;
+    __syncthreads();
+    double sum = 0.0, neg = 0.0;
+    {
+        const int shift = rf_shift<T>(0);
+        for (long long i = i0; i < n; i += stride) {
+            const T xv = x[i];
+            const double d = (double)xv;
+            sum += d;
+            if (d < 0.0) neg += 1.0;
+            atomicAdd(&sh[0][(unsigned int)(KT::of(xv) >> shift)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < RF_BINS; i += RF_THREADS)
+        if (sh[0][i]) atomicAdd(&st->hist[0][0][i], sh[0][i]);
+    {
+        const double bs = rf_block_sum(sum, red), bn = rf_block_sum(neg, red);
+        if (tid == 0) { partials[(size_t)blockIdx.x * RF_NACC + 7] = bs; partials[(size_t)blockIdx.x * RF_NACC + 8] = bn; }
+    }
+    rf_grid_sync(&st->barrier, bar_target);
+    // every CTA: total sum and count of negatives in a fixed order, then the two ranks (engine/risk.py:128-134,147-166)
+    {
+        double ts = 0.0, tn = 0.0;
+        for (unsigned int b = tid; b < gridDim.x; b += RF_THREADS) {
+            ts += __ldcg(&partials[(size_t)b * RF_NACC + 7]);
+            tn += __ldcg(&partials[(size_t)b * RF_NACC + 8]);
+        }
+        ts = rf_block_sum(ts, red);
+        tn = rf_block_sum(tn, red);
+        if (tid == 0) {
+            s_mean = ts / (double)n;                                             // :137
+            const long long m = (long long)tn;                                   // len(losses), :147
+            long long cutoff = (long long)((double)n * (1.0 - confidence));      // :128
+            if (cutoff < 0) cutoff = 0;
+            s_rank[0] = cutoff < n ? cutoff : 0;                                 // :129
+            long long k = 0;
+            const bool want_hill = m > 20;                                       // :150
+            if (want_hill) {
+                k = (long long)sqrt((double)m);                                  // :165
+                if (k < 10) k = 10;
+                if (k > m - 1) k = m - 1;                                        // :166
+            }
+            s_rank[1] = k;
+            s_nsel = want_hill ? 2 : 1;
+            if (blockIdx.x == 0) { st->result[0] = ts; st->result[1] = tn; }
+        }
+        __syncthreads();
+    }
+    const double mean = s_mean;
+    const int nsel = s_nsel;
+    K prefix[2] = {0, 0};            // decided digits of each selection, in place (lower bits zero)
+    long long rank[2] = {s_rank[0], s_rank[1]};
+    for (int sel = 0; sel < nsel; ++sel) {
+        rf_pick(&st->hist[0][0][0], 1 << rf_width<T>(0), rank[sel], scan, &s_bin[sel], &s_below[sel]);
+        prefix[sel] = (K)s_bin[sel] << rf_shift<T>(0);
+        rank[sel] -= s_below[sel];
+        __syncthreads();
+    }
+
+    // ---- passes 1 .. NPASS - 1 ---------------------------------------------------------------------------------
+    double c2 = 0.0, c3 = 0.0, c4 = 0.0, cnt[2] = {0.0, 0.0}, acc[2] = {0.0, 0.0};     // acc: sum (sel 0), sum log|x| (sel 1)
+#pragma unroll 1
+    for (int d = 1; d < NPASS; ++d) {
+        for (int i = tid; i < 2 * RF_BINS; i += RF_THREADS) (&sh[0][0])[i] = 0u;
+        __syncthreads();
+        const int shift = rf_shift<T>(d), up = rf_shift<T>(d - 1);              // up: everything decided so far sits above it
+        const unsigned int mask = (1u << rf_width<T>(d)) - 1u;
+        const K p0 = prefix[0] >> up, p1 = prefix[1] >> up;
+        // decided before the previous digit (d >= 2): equality there makes an element "newly below" at digit d - 1
+        const int up2 = d >= 2 ? rf_shift<T>(d - 2) : 0;
+        const K q0 = d >= 2 ? (prefix[0] >> up2) : 0, q1 = d >= 2 ? (prefix[1] >> up2) : 0;
+        for (long long i = i0; i < n; i += stride) {
+            const T xv = x[i];
+            const double v = (double)xv;
+            const K key = KT::of(xv);
+            if (d == 1) {
+                const double c = v - mean, cc = c * c;
+                c2 += cc; c3 += cc * c; c4 += cc * cc;
+            }
+            const K hi = key >> up;
+            const unsigned int digit = (unsigned int)(key >> shift) & mask;
+            if (hi == p0) atomicAdd(&sh[0][digit], 1u);
+            else if (hi < p0 && (d == 1 || (key >> up2) == q0)) { cnt[0] += 1.0; acc[0] += v; }
+            if (nsel > 1) {
+                if (hi == p1) atomicAdd(&sh[1][digit], 1u);
+                else if (hi < p1 && (d == 1 || (key >> up2) == q1)) { cnt[1] += 1.0; acc[1] += log(fabs(v)); }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < nsel * RF_BINS; i += RF_THREADS) {
+            const unsigned int c = (&sh[0][0])[i];
+            if (c) atomicAdd(&st->hist[d][0][0] + i, c);
+        }
+        rf_grid_sync(&st->barrier, bar_target);
+        for (int sel = 0; sel < nsel; ++sel) {
+            rf_pick(&st->hist[d][sel][0], 1 << rf_width<T>(d), rank[sel], scan, &s_bin[sel], &s_below[sel]);
+            prefix[sel] |= (K)s_bin[sel] << shift;
+            rank[sel] -= s_below[sel];
+            __syncthreads();
+        }
+    }
+    // ---- the candidates that differ from the threshold in the last digit only: from the last histogram (CTA 0) ------
+    if (blockIdx.x == 0) {
+        constexpr int d = NPASS - 1;
+        const int nb = 1 << rf_width<T>(d);
+        for (int sel = 0; sel < nsel; ++sel) {
+            const int chosen = (int)(prefix[sel] & (K)(nb - 1));
+            const K base = prefix[sel] & ~(K)(nb - 1);
+            for (int b = tid; b < chosen; b += RF_THREADS) {
+                const unsigned int c = __ldcg(&st->hist[d][sel][b]);
+                if (c) {
+                    const double v = KT::value(base | (K)b);
+                    cnt[sel] += (double)c;
+                    acc[sel] += (double)c * (sel == 0 ? v : log(fabs(v)));
+                }
+            }
+        }
+    }
+    // ---- fold: per-CTA partials in a fixed order, then CTA 0 sums them -------------------------------------------
+    {
+        const double v7[7] = {c2, c3, c4, cnt[0], acc[0], cnt[1], acc[1]};
+        for (int j = 0; j < 7; ++j) {
+            const double b = rf_block_sum(v7[j], red);
+            if (tid == 0) partials[(size_t)blockIdx.x * RF_NACC + j] = b;
+        }
+    }
+    rf_grid_sync(&st->barrier, bar_target);
+    if (blockIdx.x == 0) {
+        for (int j = 0; j < 7; ++j) {
+            double t = 0.0;
+            for (unsigned int b = tid; b < gridDim.x; b += RF_THREADS) t += __ldcg(&partials[(size_t)b * RF_NACC + j]);
+            t = rf_block_sum(t, red);
+            if (tid == 0) st->result[2 + j] = t;
+        }
+        if (tid == 0) {
+            st->result[9] = KT::value(prefix[0]);
+            st->result[10] = nsel > 1 ? KT::value(prefix[1]) : 0.0;
+            st->result[11] = (double)nsel;
+        }
+    }
+}
+
 __global__ void k_set_double(double *p, double v) { *p = v; }
 
 // sharded = the vector is the LOCAL shard of a vector spread over the ranks of the handle's peer connection (peer.cu):
 // the two sums of pass 1 (+ the shard length), the histograms of every radix pass and the six sums of pass 2 are
 // all-reduced on the device between the kernels, so every rank takes the same decisions and returns the GLOBAL metrics;
 // the shards never move and the host synchronises twice, as in the single-device case.  n may be 0 on a rank.
+// Single-device case: ONE cooperative launch + one read-back (k_risk_fused).  Returns 1 when the fused path cannot run
+// (no cooperative launch, more than 2^32 - 1 elements) so that the caller takes the multi-kernel path.
+template <typename T>
+static int risk_run_fused(b200mc_handle *h, const T *x_dev, const int64_t n, double confidence, double out[8])
+{
+    if (n >= (int64_t)4294967295ll) return 1;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    if (!coop) return 1;
+    int occ = 0;
+    for (int i = 0; i < h->n_occ; ++i)
+        if (h->occ_kern[i] == (const void *)k_risk_fused<T> && h->occ_smem[i] == 0) occ = h->occ_val[i];
+    if (occ == 0) {
+        B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_risk_fused<T>, RF_THREADS, 0));
+        if (occ < 1) return 1;
+        const int slot = h->n_occ < 64 ? h->n_occ++ : 63;
+        h->occ_kern[slot] = (const void *)k_risk_fused<T>;
+        h->occ_smem[slot] = 0;
+        h->occ_val[slot] = occ;
+    }
+    int64_t grid = (n + RF_THREADS - 1) / RF_THREADS;
+    const int64_t cap = (int64_t)h->sm_count * (occ < 2 ? occ : 2);          // co-resident by construction
+    if (grid > cap) grid = cap;
+    const size_t off_pa = (sizeof(FusedState) + 255) & ~(size_t)255;
+    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, off_pa + (size_t)grid * RF_NACC * 8 + 64));
+    FusedState *st = (FusedState *)h->d_scratch;
+    double *partials = (double *)((char *)h->d_scratch + off_pa);
+    B200MC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(FusedState), h->stream));
+    long long nn = n;
+    void *args[] = {(void *)&x_dev, (void *)&nn, (void *)&confidence, (void *)&st, (void *)&partials};
+    B200MC_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_risk_fused<T>, dim3((unsigned)grid), dim3(RF_THREADS), args, 0,
+                                                h->stream));
+    h->launches += 1;
+    double r[12];
+    B200MC_CUDA(h, cudaMemcpyAsync(r, st->result, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    const double nnd = (double)n, mean = r[0] / nnd;                          // :137
+    const int64_t m = (int64_t)r[1];
+    int64_t cutoff = (int64_t)(nnd * (1.0 - confidence));                     // :128
+    if (cutoff < 0) cutoff = 0;
+    const bool want_hill = m > 20;                                            // :150
+    int64_t k = 0;
+    if (want_hill) {
+        k = (int64_t)sqrt((double)m);                                         // :165
+        if (k < 10) k = 10;
+        if (k > m - 1) k = m - 1;                                             // :166
+    }
+    const double sd = sqrt(r[2] / nnd);                                       // :138 (np.std, ddof = 0)
+    const double sdc = sd > 1e-10 ? sd : 1e-10;                               // :141
+    const double skew = (r[3] / nnd) / (sdc * sdc * sdc);                     // :143
+    const double kurt = (r[4] / nnd) / (sdc * sdc * sdc * sdc);               // :144
+    const double thr0 = r[9], thr1 = r[10];
+    double cvar;
+    if (cutoff <= 0) cvar = -thr0;                                            // :130, else-branch (-sorted[0])
+    else if (cutoff >= n) cvar = -mean;                                       // slice covers everything
+    else cvar = -(r[6] + ((double)cutoff - r[5]) * thr0) / (double)cutoff;    // ties at the threshold
+    double tail = NAN;
+    if (want_hill && thr1 < 0.0) {
+        const double logsum = r[8] - r[7] * log(fabs(thr1));                  // sum over x < thr1 of log(x / thr1)   (:170)
+        if (logsum > 0.0 && r[7] > 0.0) tail = (double)k / logsum;            // :168-173
+    }
+    out[0] = -thr0; out[1] = cvar; out[2] = skew; out[3] = kurt; out[4] = kurt - 3.0; out[5] = tail;
+    out[6] = mean; out[7] = sd;
+    return 0;
+}
+
 template <typename T>
 static int risk_run(b200mc_handle *h, const T *x_dev, const int64_t n_loc, double confidence, double out[8],
                     bool sharded = false)
 {
+    if (!sharded && n_loc > 0 && !getenv("B200MC_RISK_MULTIKERNEL")) {
+        const int rc = risk_run_fused<T>(h, x_dev, n_loc, confidence, out);
+        if (rc != 1) return rc;
+    }
     int64_t n = n_loc;                                 // becomes the GLOBAL length after pass 1 when sharded
     int64_t grid = (n_loc + RK_THREADS - 1) / RK_THREADS;
     const int64_t cap = (int64_t)h->sm_count * 8;

@@ -1,6 +1,6 @@
 """One launch (after one warm-up launch) of every kernel this round's profiles/ summaries cover; run under
 `ncu --set full -k regex:<name> -c <count>` (see tools/gpu_call1.sh).  python tools/ncu_targets.py [target ...]
-Targets: gbm32 gbm64 heston svj paths32 paths64 given risk hedge qmc."""
+Targets: gbm32 gbm64 heston svj paths32 paths64 given risk numpy hedge qmc."""
 import ctypes as C
 import os
 import sys
@@ -61,6 +61,11 @@ if "risk" in want:
     x = torch.from_numpy(np.random.default_rng(0).standard_t(4, size=n) * 0.01).cuda()
     for r in range(REPS):
         h.risk_metrics(x.data_ptr(), 0.99, n=n, dtype=np.float64)
+if "numpy" in want:
+    buf = h.malloc(3 * 50_000 * 250 * 8)
+    for r in range(REPS):
+        h.numpy_fill(42, 3 * 50_000 * 250, out_dev=buf)
+    h.free(buf)
 if "hedge" in want:
     from monte_carlo_option_simulator_b200.risk import HedgingBacktest
     bt = HedgingBacktest(SVJParams(), seed=42, handle=h)
