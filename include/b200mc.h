@@ -61,6 +61,9 @@ extern "C" {
 #define B200MC_GREEKS     0x2u  /* fill the bump / pathwise accumulators of b200mc_sums                  */
 #define B200MC_FP64       0x4u  /* evolve the path state and the payoff in fp64 (draws are unchanged)    */
 #define B200MC_FORCE_SVJ  0x8u  /* use the general SVJ kernel even when xi == 0 and lambda_j == 0        */
+#define B200MC_WIDE_RNG   0x10u /* validation twin of the generator (b200mc_price_european, constant variance, one
+                                 * strike, no GREEKS): one Box-Muller pair per TWO words (radius and angle share no bit),
+                                 * block j -> steps 4j..4j+3.  Half the normals per Philox call; never the default.      */
 
 #define B200MC_STREAM_GBM    0u
 #define B200MC_STREAM_HESTON 1u
@@ -378,6 +381,9 @@ int b200mc_normal_moments(b200mc_handle *h, uint64_t seed, uint64_t path_offset,
  * member of a word with the first member of the next word.  4 (lag 0) or 3 (lag 1) pairs per Philox block. */
 int b200mc_normal_hist2d(b200mc_handle *h, uint64_t seed, uint64_t path_offset, int64_t n_paths, int32_t n_blocks, int lag,
                          uint64_t out[4096]);
+/* lag | B200MC_HIST_WIDE: the same counts for the validation twin (B200MC_WIDE_RNG: 2 pairs per block; lag 1 = the second
+ * member of the first pair with the first member of the second). */
+#define B200MC_HIST_WIDE 0x100
 
 /* ---- device memory helpers for callers without a CUDA runtime of their own (ctypes) ---------------------- */
 int b200mc_malloc(b200mc_handle *h, size_t bytes, void **dev_ptr);

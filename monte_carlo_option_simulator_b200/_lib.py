@@ -17,7 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200mc.so")
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM = 0, 1, 2, 3, 4
-ANTITHETIC, GREEKS, FP64, FORCE_SVJ = 0x1, 0x2, 0x4, 0x8
+ANTITHETIC, GREEKS, FP64, FORCE_SVJ, WIDE_RNG = 0x1, 0x2, 0x4, 0x8, 0x10
+HIST_WIDE = 0x100
 STREAM_GBM, STREAM_HESTON, STREAM_SVJ, STREAM_HEDGE = 0, 1, 2, 3
 Z1, Z2, ZJUMP_U, ZJUMP_SIZE = 0, 1, 2, 3
 F32, F64 = 0, 1

@@ -218,6 +218,7 @@ static int launch_cells(b200mc_handle *h, const b200mc_cell *cells, int32_t n_ce
     if (!strikes || n_strikes <= 0 || n_strikes > CL_THREADS)
         return fail(h, B200MC_EINVAL, "n_strikes must be in [1, 256]");
     if (flags & B200MC_GREEKS) return fail(h, B200MC_EINVAL, "b200mc_price_cells has no Greek sums (use b200mc_price_european)");
+    if (flags & B200MC_WIDE_RNG) return fail(h, B200MC_EINVAL, "B200MC_WIDE_RNG is valid for b200mc_price_european only");
     if (n_cells > (1 << 20)) return fail(h, B200MC_EINVAL, "at most 2^20 cells per call");
     const bool anti = flags & B200MC_ANTITHETIC, fp64 = flags & B200MC_FP64;
 

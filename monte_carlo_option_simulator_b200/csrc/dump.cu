@@ -72,7 +72,7 @@ __global__ void k_dump_jumps(PhiloxKey key, uint64_t path0, int64_t n_paths, int
         const uint64_t path = path0 + (uint64_t)pi;
         const uint32_t c0 = (uint32_t)path, c1 = (uint32_t)(path >> 32);
         JumpStream jmp;
-        jmp.init(c0, c1, key, inv_lg2_q, 2, jump_on != 0);
+        jmp.init(c0, c1, key, inv_lg2_q, jump_on != 0);
         U4 fill = U4{0u, 0u, 0u, 0u};
         for (int s = 0; s < n_steps; ++s) {
             if (which == B200MC_ZJUMP_U && (s & 3) == 0)
@@ -80,9 +80,9 @@ __global__ void k_dump_jumps(PhiloxKey key, uint64_t path0, int64_t n_paths, int
             const uint32_t fw = (s & 3) == 0 ? fill.x : (s & 3) == 1 ? fill.y : (s & 3) == 2 ? fill.z : fill.w;
             double val;
             if (s == jmp.next) {
-                if (which == B200MC_ZJUMP_U) val = jump_prob * word_uniform(jmp.jword[jmp.m & 1u]);      // < jump_prob
-                else val = B200MC_BM_SCALE * (double)jmp.size_raw(2);
-                jmp.advance(c0, c1, key, inv_lg2_q, 2, s);
+                if (which == B200MC_ZJUMP_U) val = jump_prob * word_uniform(jmp.w_size);      // < jump_prob
+                else val = B200MC_BM_SCALE * (double)jmp.size_raw();
+                jmp.advance(c0, c1, key, inv_lg2_q, s);
             } else if (which == B200MC_ZJUMP_U) {
                 val = jump_prob + (1.0 - jump_prob) * word_uniform(fw);
                 if (!(val > jump_prob)) val = 1.0;                                            // never below the threshold
@@ -147,6 +147,17 @@ k_normal_hist2d(const __grid_constant__ PhiloxKey key, uint64_t path0, int64_t n
             const U4 w = philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)j, B200MC_STREAM_GBM, key);
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
             BM2 b[4];
+            if (lag & B200MC_HIST_WIDE) {
+                b[0] = box_muller_wide(ww[0], ww[1]);
+                b[1] = box_muller_wide(ww[2], ww[3]);
+                if ((lag & 1) == 0) {
+                    atomicAdd(&hist[cell(b[0].rc) * 64 + cell(b[0].rs)], 1u);
+                    atomicAdd(&hist[cell(b[1].rc) * 64 + cell(b[1].rs)], 1u);
+                } else {
+                    atomicAdd(&hist[cell(b[0].rs) * 64 + cell(b[1].rc)], 1u);
+                }
+                continue;
+            }
 #pragma unroll
             for (int t = 0; t < 4; ++t) b[t] = box_muller_word(ww[t]);
             if (lag == 0) {
@@ -170,7 +181,7 @@ extern "C" int b200mc_normal_hist2d(b200mc_handle *h, uint64_t seed, uint64_t pa
                                     int lag, uint64_t out[4096])
 {
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
-    if (!out || n_paths <= 0 || n_blocks <= 0 || lag < 0 || lag > 1) return fail(h, B200MC_EINVAL, "bad argument");
+    if (!out || n_paths <= 0 || n_blocks <= 0 || (lag & ~(1 | B200MC_HIST_WIDE))) return fail(h, B200MC_EINVAL, "bad argument");
     B200MC_CUDA(h, cudaSetDevice(h->device));
     // a CTA's shared 32-bit cells must not overflow: at most 2^31 pairs per CTA
     const int grid = h->sm_count * 8;

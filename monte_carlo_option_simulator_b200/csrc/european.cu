@@ -92,7 +92,7 @@ __device__ __forceinline__ void accumulate(A (&acc)[NACC], const EuroArgs &a, R 
 
 // SINGLE = exactly one strike: every thread finishes its own paths, no shared-memory staging and no block barrier
 // inside the path loop.  Otherwise phase A / phase B as described at the top of the file.
-template <int MODE, bool ANTI, bool GREEKS, typename R, bool SINGLE>
+template <int MODE, bool ANTI, bool GREEKS, typename R, bool SINGLE, bool WIDE = false>
 __global__ void __launch_bounds__(EU_THREADS, (sizeof(R) == 4 && MODE <= MODE_DETVAR) ? EU_MIN_BLOCKS : 1)
 k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
            double *__restrict__ out)
@@ -137,8 +137,8 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g
         }
         for (int64_t i = (int64_t)blockIdx.x * EU_THREADS + tid; i < a.n_paths; i += (int64_t)gridDim.x * EU_THREADS) {
             R xT[NS], vT[NS], sumz;
-            simulate_path<MODE, ANTI, GREEKS, R>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT, vT,
-                                                 sumz, NoRec());
+            simulate_path<MODE, ANTI, GREEKS, R, NoRec, WIDE>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT,
+                                                              vT, sumz, NoRec());
             R sv[NS];
 #pragma unroll
             for (int k = 0; k < NS; ++k) sv[k] = S0 * rexp(xT[k]);
@@ -349,6 +349,12 @@ static int launch_european(b200mc_handle *h, const b200mc_svj_params *p, double 
 
     const bool single = n_strikes == 1;
     EuroKernel kern = fp64 ? pick1<double>(pr.mode, anti, greeks, single) : pick1<float>(pr.mode, anti, greeks, single);
+    if (flags & B200MC_WIDE_RNG) {           // validation twin of the generator: constant variance, one strike, no Greeks
+        if (pr.mode != MODE_GBM || !single || greeks)
+            return fail(h, B200MC_EINVAL, "B200MC_WIDE_RNG is the validation twin of the GBM stream: constant variance, one strike, no B200MC_GREEKS");
+        if (fp64) kern = anti ? k_european<MODE_GBM, true, false, double, true, true> : k_european<MODE_GBM, false, false, double, true, true>;
+        else kern = anti ? k_european<MODE_GBM, true, false, float, true, true> : k_european<MODE_GBM, false, false, float, true, true>;
+    }
     const int ns = 1 + (anti ? 1 : 0) + (greeks ? 2 : 0);
     const size_t rsz = fp64 ? 8 : 4;
     size_t smem = (size_t)(EU_THREADS + ((n_strikes + 1) & ~1)) * 8 + (single ? 0 : (size_t)(ns + 1) * EU_THREADS * rsz);

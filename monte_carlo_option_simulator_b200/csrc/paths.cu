@@ -457,6 +457,7 @@ extern "C" int b200mc_simulate_terminal(b200mc_handle *h, const b200mc_svj_param
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
     if (dtype != B200MC_F32 && dtype != B200MC_F64) return fail(h, B200MC_EINVAL, "dtype must be B200MC_F32 or B200MC_F64");
     if (flags & B200MC_GREEKS) return fail(h, B200MC_EINVAL, "B200MC_GREEKS is not valid for simulate_terminal");
+    if (flags & B200MC_WIDE_RNG) return fail(h, B200MC_EINVAL, "B200MC_WIDE_RNG is valid for b200mc_price_european only");
     Prep pr;
     B200MC_TRY(prepare(h, p, S0, T, n_steps, n_paths, seed, flags, nullptr, pr));
     B200MC_CUDA(h, cudaSetDevice(h->device));
@@ -520,7 +521,7 @@ extern "C" int b200mc_generate_paths(b200mc_handle *h, const b200mc_svj_params *
 {
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
     if (dtype != B200MC_F32 && dtype != B200MC_F64) return fail(h, B200MC_EINVAL, "dtype must be B200MC_F32 or B200MC_F64");
-    if (flags & (B200MC_GREEKS | B200MC_ANTITHETIC))
+    if (flags & (B200MC_GREEKS | B200MC_ANTITHETIC | B200MC_WIDE_RNG))
         return fail(h, B200MC_EINVAL, "generate_paths takes only B200MC_FP64 / B200MC_FORCE_SVJ");
     if (!out) return fail(h, B200MC_EINVAL, "out is NULL");
     if (ld < (int64_t)n_steps + 1) return fail(h, B200MC_EINVAL, "ld must be at least n_steps + 1");

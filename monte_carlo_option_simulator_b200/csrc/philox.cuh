@@ -116,6 +116,22 @@ __device__ __forceinline__ BM2 box_muller_word(uint32_t w)
     return o;
 }
 
+// Validation twin (B200MC_WIDE_RNG, never the default): the SAME transform fed by TWO words -- the radius from the low 23
+// bits of one, the angle from the top 23 bits of the other -- so the two fields share no bit (4 normals per Philox call
+// instead of 8).  It exists to show that the bit sharing of the production layout is invisible to the path functionals:
+// tests/test_gpu_rng_quality.py prices the same options with both layouts at 1e9 paths.
+__device__ __forceinline__ BM2 box_muller_wide(uint32_t w_radius, uint32_t w_angle)
+{
+    const float u1 = 2.0f - mant12(w_radius);
+    const float rad = sqrt_approx(-lg2_approx(u1));
+    const float f2 = __uint_as_float(__funnelshift_r(w_angle, 0x7Fu, 9));
+    const float ang = fmaf(f2, 6.283185307179586f, -9.42477796076938f);
+    BM2 o;
+    o.rc = rad * cos_approx(ang);
+    o.rs = rad * sin_approx(ang);
+    return o;
+}
+
 // Same transform with the three factors kept apart: normals = B200MC_BM_SCALE * rad * (cs, sn).  The stochastic-variance
 // kernels (fp32 state) fold their per-step constants into `rad` once instead of scaling both products per state.
 struct BM3 { float rad, cs, sn; };
@@ -155,47 +171,37 @@ struct JumpStream {
     // Philox stream B200MC_STREAM_SVJ_JUMP, counter block k -> jumps 2k and 2k + 1 of the path:
     //   (w0 -> gap before jump 2k, w1 -> its size), (w2 -> gap before jump 2k + 1, w3 -> its size)
     // size: Z_jump_size = B200MC_BM_SCALE * rc(BM(w)) (the cosine member of the word's Box-Muller pair)
-    // The next `pf` (2 or 4) jumps of the path are kept in a small ring (thread-local memory, touched only when a jump
-    // fires): the Philox calls and log2 evaluations that fill it run for ALL lanes at the start of the path, so the
-    // divergent branch taken when a lane jumps is a dozen instructions instead of a Philox call -- with lambda T ~ 1
-    // a path rarely needs a refill inside the step loop.  pf only sets how far ahead the stream is read, never WHAT it
-    // holds (the host picks it from lambda T).
-    int next;                   // step index of the next jump
+    // (Tried: the next 2-4 jumps of a path read ahead into a small ring before the step loop, so that the divergent branch
+    // never holds a Philox call -- 4.30e11 -> 4.02e11 path-steps/s on B200: the read-ahead and the ring's selects cost
+    // more than the rare refills they remove.)
+    int next, next2;            // step index of the next jump and of the one after it
+    uint32_t w_size, w_size2;   // their size words
     uint32_t m;                 // jumps consumed so far
-    int jstep[4];               // ring: step index of jump m + i (slot (m + i) & (pf - 1))
-    uint32_t jword[4];          // ring: its size word
 
-    __device__ __forceinline__ void refill(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int pf, int from)
+    __device__ __forceinline__ void refill(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int from)
     {
-        int at = from;
-        for (int c = 0; c < (pf >> 1); ++c) {
-            const U4 q = philox4x32_10(c0, c1, (m >> 1) + (uint32_t)c, B200MC_STREAM_SVJ_JUMP, key);
-            at += jump_gap(q.x, inv_lg2_q);
-            jstep[2 * c] = at;
-            jword[2 * c] = q.y;
-            at += 1 + jump_gap(q.z, inv_lg2_q);
-            jstep[2 * c + 1] = at;
-            jword[2 * c + 1] = q.w;
-            at += 1;
-        }
-        next = jstep[0];
+        const U4 q = philox4x32_10(c0, c1, m >> 1, B200MC_STREAM_SVJ_JUMP, key);
+        next = from + jump_gap(q.x, inv_lg2_q);
+        w_size = q.y;
+        next2 = next + 1 + jump_gap(q.z, inv_lg2_q);
+        w_size2 = q.w;
     }
-    __device__ __forceinline__ void init(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int pf, bool on)
+    __device__ __forceinline__ void init(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, bool on)
     {
         m = 0u;
-        next = 0x7fffffff;
-        if (on) refill(c0, c1, key, inv_lg2_q, pf, 0);
+        next = next2 = 0x7fffffff;
+        w_size = w_size2 = 0u;
+        if (on) refill(c0, c1, key, inv_lg2_q, 0);
     }
-    // unscaled size draw of the pending jump: Z_jump_size = B200MC_BM_SCALE * size_raw()
-    __device__ __forceinline__ float size_raw(int pf) const { return box_muller_word(jword[m & (uint32_t)(pf - 1)]).rc; }
     // the jump at step `s` (== next) has been applied: move to the following one
-    __device__ __forceinline__ void advance(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int pf, int s)
+    __device__ __forceinline__ void advance(uint32_t c0, uint32_t c1, const PhiloxKey &key, float inv_lg2_q, int s)
     {
         ++m;
-        const uint32_t slot = m & (uint32_t)(pf - 1);
-        if (slot == 0u) refill(c0, c1, key, inv_lg2_q, pf, s + 1);
-        else next = jstep[slot];
+        if (m & 1u) { next = next2; w_size = w_size2; }
+        else refill(c0, c1, key, inv_lg2_q, s + 1);
     }
+    // unscaled size draw of the pending jump: Z_jump_size = B200MC_BM_SCALE * size_raw()
+    __device__ __forceinline__ float size_raw() const { return box_muller_word(w_size).rc; }
 };
 
 } // namespace b200mc

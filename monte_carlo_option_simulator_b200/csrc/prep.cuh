@@ -61,7 +61,6 @@ inline int prepare(b200mc_handle *h, const b200mc_svj_params *p, double S0, doub
     m.sigma_j = p->sigma_j;
     m.sigma_j_s = p->sigma_j * B200MC_BM_SCALE;
     m.jump_on = jump_setup(p->lambda_j * dt, &m.jump_inv_lg2q);             // :233
-    m.jump_prefetch = (p->lambda_j * T > 0.6) ? 4 : 2;                      // expected jumps per path decide the read-ahead
     m.v0[0] = p->v0;
     m.v0[1] = (flags & B200MC_GREEKS) ? bumps->v0_up : p->v0;
     m.v0[2] = (flags & B200MC_GREEKS) ? bumps->v0_dn : p->v0;

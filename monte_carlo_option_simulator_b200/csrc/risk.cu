@@ -126,6 +126,9 @@ k_risk_pass2(const T *__restrict__ x, int64_t n, double mean, int nsel, const Se
 // scan) -- no second barrier, no single-thread walk (k_risk_pick above is 10-24 us per pass: 150 of the 283 us a 4M-value
 // call took).  Sums are folded in a fixed order (per-CTA partials, then one ordered sum), so a launch geometry is
 // bitwise reproducible.  Measured on B200: see DESIGN.md section 4.4.
+#ifndef B200MC_RISK_DEFAULT_CTAS
+#define B200MC_RISK_DEFAULT_CTAS 2
+#endif
 constexpr int RF_THREADS = 512;
 constexpr int RF_BITS = 11;
 constexpr int RF_BINS = 1 << RF_BITS;
@@ -185,6 +188,27 @@ __device__ __forceinline__ void rf_grid_sync(unsigned int *bar, unsigned int &ta
     __syncthreads();
 }
 
+// One vote per DISTINCT bin and warp: lanes that hit the same bin (ties; the top digit of doubles, which is little more
+// than sign + exponent) are counted with one shared-memory atomic instead of a serialised chain of them.
+__device__ __forceinline__ void rf_vote(unsigned int *h, unsigned int digit)
+{
+    const unsigned int peers = __match_any_sync(__activemask(), digit);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[digit], (unsigned int)__popc(peers));
+}
+
+// grid-stride loop with four independent loads in flight per thread (the passes are latency bound otherwise: one
+// 8-byte load per thread and iteration keeps ~1 MB in flight on the whole device)
+template <typename T, typename F>
+__device__ __forceinline__ void rf_foreach(const T *__restrict__ x, long long n, long long i0, long long stride, F body)
+{
+    long long i = i0;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const T a = x[i], b = x[i + stride], c = x[i + 2 * stride], d = x[i + 3 * stride];
+        body(a); body(b); body(c); body(d);
+    }
+    for (; i < n; i += stride) body(x[i]);
+}
+
 // deterministic sum of v over the CTA's threads -> every thread gets it
 __device__ __forceinline__ double rf_block_sum(double v, double *red)
 {
@@ -241,8 +265,8 @@ __device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long l
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(RF_THREADS)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(RF_THREADS, MINB)
 k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState *st, double *partials /* [grid][RF_NACC] */)
 {
     using KT = RfKey<T>;
@@ -266,13 +290,12 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
     double sum = 0.0, neg = 0.0;
     {
         const int shift = rf_shift<T>(0);
-        for (long long i = i0; i < n; i += stride) {
-            const T xv = x[i];
+        rf_foreach<T>(x, n, i0, stride, [&](const T xv) {
             const double d = (double)xv;
             sum += d;
             if (d < 0.0) neg += 1.0;
-            atomicAdd(&sh[0][(unsigned int)(KT::of(xv) >> shift)], 1u);
-        }
+            rf_vote(&sh[0][0], (unsigned int)(KT::of(xv) >> shift));
+        });
     }
     __syncthreads();
     for (int i = tid; i < RF_BINS; i += RF_THREADS)
@@ -333,8 +356,8 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         // decided before the previous digit (d >= 2): equality there makes an element "newly below" at digit d - 1
         const int up2 = d >= 2 ? rf_shift<T>(d - 2) : 0;
         const K q0 = d >= 2 ? (prefix[0] >> up2) : 0, q1 = d >= 2 ? (prefix[1] >> up2) : 0;
-        for (long long i = i0; i < n; i += stride) {
-            const T xv = x[i];
+        double cnt0 = 0.0, acc0 = 0.0, cnt1 = 0.0, acc1 = 0.0;                   // this pass's tail sums, in registers
+        rf_foreach<T>(x, n, i0, stride, [&](const T xv) {
             const double v = (double)xv;
             const K key = KT::of(xv);
             if (d == 1) {
@@ -343,13 +366,14 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             }
             const K hi = key >> up;
             const unsigned int digit = (unsigned int)(key >> shift) & mask;
-            if (hi == p0) atomicAdd(&sh[0][digit], 1u);
-            else if (hi < p0 && (d == 1 || (key >> up2) == q0)) { cnt[0] += 1.0; acc[0] += v; }
+            if (hi == p0) rf_vote(&sh[0][0], digit);
+            else if (hi < p0 && (d == 1 || (key >> up2) == q0)) { cnt0 += 1.0; acc0 += v; }
             if (nsel > 1) {
-                if (hi == p1) atomicAdd(&sh[1][digit], 1u);
-                else if (hi < p1 && (d == 1 || (key >> up2) == q1)) { cnt[1] += 1.0; acc[1] += log(fabs(v)); }
+                if (hi == p1) rf_vote(&sh[1][0], digit);
+                else if (hi < p1 && (d == 1 || (key >> up2) == q1)) { cnt1 += 1.0; acc1 += log(fabs(v)); }
             }
-        }
+        });
+        cnt[0] += cnt0; acc[0] += acc0; cnt[1] += cnt1; acc[1] += acc1;
         __syncthreads();
         for (int i = tid; i < nsel * RF_BINS; i += RF_THREADS) {
             const unsigned int c = (&sh[0][0])[i];
@@ -419,14 +443,18 @@ static int risk_run_fused(b200mc_handle *h, const T *x_dev, const int64_t n, dou
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
     if (!coop) return 1;
+    // 1 CTA per SM with ~110 registers (no spills) or 2 with 64 (more loads in flight): tuning knob B200MC_RISK_CTAS
+    const char *e = getenv("B200MC_RISK_CTAS");
+    const bool two = e ? atoi(e) == 2 : (B200MC_RISK_DEFAULT_CTAS == 2);
+    const void *kern = two ? (const void *)k_risk_fused<T, 2> : (const void *)k_risk_fused<T, 1>;
     int occ = 0;
     for (int i = 0; i < h->n_occ; ++i)
-        if (h->occ_kern[i] == (const void *)k_risk_fused<T> && h->occ_smem[i] == 0) occ = h->occ_val[i];
+        if (h->occ_kern[i] == kern && h->occ_smem[i] == 0) occ = h->occ_val[i];
     if (occ == 0) {
-        B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k_risk_fused<T>, RF_THREADS, 0));
+        B200MC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RF_THREADS, 0));
         if (occ < 1) return 1;
         const int slot = h->n_occ < 64 ? h->n_occ++ : 63;
-        h->occ_kern[slot] = (const void *)k_risk_fused<T>;
+        h->occ_kern[slot] = kern;
         h->occ_smem[slot] = 0;
         h->occ_val[slot] = occ;
     }
@@ -440,7 +468,7 @@ static int risk_run_fused(b200mc_handle *h, const T *x_dev, const int64_t n, dou
     B200MC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(FusedState), h->stream));
     long long nn = n;
     void *args[] = {(void *)&x_dev, (void *)&nn, (void *)&confidence, (void *)&st, (void *)&partials};
-    B200MC_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_risk_fused<T>, dim3((unsigned)grid), dim3(RF_THREADS), args, 0,
+    B200MC_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0,
                                                 h->stream));
     h->launches += 1;
     double r[12];

@@ -38,7 +38,7 @@ struct ModelArgs {
     double mu_j, sigma_j;
     double sigma_j_s;       // sigma_j BM_SCALE
     int32_t jump_on;        // lambda_j dt > 0                                :233
-    int32_t jump_prefetch;  // 2 or 4: jumps of a path read ahead of the step loop (JumpStream)
+    int32_t pad_;
     double v0[3];           // base, up, down
     double x_drift[3];      // GBM / DETVAR: total drift of x over [0, T] for the three variance starts
     double x_w[3];          // GBM: x_T = x_drift + x_w * sum(raw z);  x_w = sqrt(v0 dt) BM_SCALE
@@ -121,7 +121,7 @@ __device__ __forceinline__ void scaled_draws(uint32_t w, const Consts<R> &c, R &
 // (GBM / DETVAR: vT is left untouched); sumz_out = sum of the raw draws (GBM only; feeds the pathwise vega).
 // wtab: DETVAR weights, wtab[k * wld + s] = sqrt(v_s^{(k)} dt) * BM_SCALE in shared memory (wld = steps rounded up to 8,
 // zero padded).  rec: after every step s, rec(s, x0) gets the primary state's log return (path store).
-template <int MODE, bool ANTI, bool GREEKS, typename R, typename Rec>
+template <int MODE, bool ANTI, bool GREEKS, typename R, typename Rec, bool WIDE = false>
 __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKey &key, uint64_t path, int n_steps,
                                               const R *wtab, int wld,
                                               R (&xT)[StateLayout<ANTI, GREEKS>::NS],
@@ -151,6 +151,25 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         }
         sumz_out = (R)0;
         xT[0] = x;
+    } else if constexpr (MODE == MODE_GBM && WIDE) {
+        // validation twin: one Box-Muller pair per TWO words (philox.cuh, box_muller_wide), block j -> steps 4j..4j+3
+        R sumz = (R)0;
+        const int nb = (n_steps + 3) >> 2;
+        for (int j = 0; j < nb; ++j) {
+            const U4 u = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+            const BM2 b0 = box_muller_wide(u.x, u.y), b1 = box_muller_wide(u.z, u.w);
+            const R z[4] = {(R)b0.rc, (R)b0.rs, (R)b1.rc, (R)b1.rs};
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (4 * j + t < n_steps) sumz += z[t];
+        }
+        sumz_out = sumz;
+        xT[0] = (R)m.x_drift[0] + (R)m.x_w[0] * sumz;
+        if constexpr (ANTI) xT[1] = (R)m.x_drift[0] - (R)m.x_w[0] * sumz;
+        if constexpr (GREEKS) {
+            xT[L::UP_IDX] = (R)m.x_drift[1] + (R)m.x_w[1] * sumz;
+            xT[L::DN_IDX] = (R)m.x_drift[2] + (R)m.x_w[2] * sumz;
+        }
     } else if constexpr (MODE == MODE_GBM) {
         // Software-pipelined: the Philox rounds of block j+1 (IMAD.WIDE / LOP3) are issued in the same loop body as
         // the Box-Muller transforms of block j (MUFU), so every warp feeds the XU pipe at an even rate instead of
@@ -233,8 +252,7 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         // variance steps of block j.
         JumpStream jmp;
         const float inv_lg2_q = (float)m.jump_inv_lg2q;
-        const int jpf = m.jump_prefetch;
-        if constexpr (MODE == MODE_SVJ) jmp.init(c0, c1, key, inv_lg2_q, jpf, m.jump_on != 0);
+        if constexpr (MODE == MODE_SVJ) jmp.init(c0, c1, key, inv_lg2_q, m.jump_on != 0);
         constexpr uint32_t STREAM = MODE == MODE_HESTON ? B200MC_STREAM_HESTON : B200MC_STREAM_SVJ;
         const int nblk = (n_steps + 3) >> 2;
         U4 u = philox4x32_10(c0, c1, 0u, STREAM, key);
@@ -251,10 +269,10 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                     sv_step<R, ANTI, GREEKS>(x, v, c, zs1, zsc);
                     if constexpr (MODE == MODE_SVJ) {
                         if (s == jmp.next) {                                             // :233-234, rare
-                            const R jsz = c.sigma_j_s * (R)jmp.size_raw(jpf);
+                            const R jsz = c.sigma_j_s * (R)jmp.size_raw();
 #pragma unroll
                             for (int k = 0; k < NS; ++k) x[k] += (ANTI && k == 1) ? c.mu_j - jsz : c.mu_j + jsz;
-                            jmp.advance(c0, c1, key, inv_lg2_q, jpf, s);
+                            jmp.advance(c0, c1, key, inv_lg2_q, s);
                         }
                     }
                     if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }

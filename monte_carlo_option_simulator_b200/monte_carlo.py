@@ -307,6 +307,8 @@ class MonteCarloEngine:
 
     def price(self, spot: float, strike: float, T: float, is_call: bool = True) -> Dict[str, float]:
         """Price a European option; same keys as monte_carlo.py:345-373."""
+        if T == 0:
+            return self._expired(spot, strike, is_call)
         if self.rng == "reference":
             return self._price_reference(spot, strike, T, is_call)
         steps = steps_for(self.num_steps, T)                                   # :287
@@ -330,6 +332,22 @@ class MonteCarloEngine:
             result["std_error"] = discount * math.sqrt(dvar) / math.sqrt(n)
         result.update(self._spot_cv(row, spot, T, discount, p))
         return result
+
+    def _expired(self, spot, strike, is_call, batch=False):
+        """T == 0: the reference still walks its minimum of 10 steps with dt = 0 (monte_carlo.py:287), so every path ends at
+        the spot and the result is the intrinsic value with zero standard error (its control-variate terms cancel:
+        bs_price(T <= 0) is the intrinsic value too, :31-34).  No launch is needed for that.  (T < 0 has no meaning in the
+        reference either -- sqrt(dt) is NaN there -- and raises here.)"""
+        intrinsic = max(float(spot) - strike, 0.0) if is_call else max(strike - float(spot), 0.0)
+        if batch:
+            res = {"strike": strike, "price": intrinsic, "std_error": 0.0}
+            if self.use_control_variate:
+                res["bs_ref"] = intrinsic
+            return res
+        res = {"price": intrinsic, "std_error": 0.0, "num_paths_used": self.num_paths, "num_steps": steps_for(self.num_steps, 0.0)}
+        if self.use_control_variate:
+            res.update({"bs_cv_adjustment": 0.0, "bs_ref": intrinsic, "raw_mc_price": intrinsic})
+        return res
 
     def price_many(self, spots, strikes, Ts, is_call=True, *, params=None, seeds=None) -> List[Dict[str, float]]:
         """NEW: many independent price() problems in ONE launch over a (cell x path) grid
@@ -445,6 +463,8 @@ class MonteCarloEngine:
 
     def price_batch(self, spot: float, strikes, T: float, is_call: bool = True) -> list:
         """Price multiple strikes with shared path simulation (monte_carlo.py:377-450)."""
+        if T == 0:
+            return [self._expired(spot, K, is_call, batch=True) for K in strikes]
         if self.rng == "reference":
             return self._price_batch_reference(spot, strikes, T, is_call)
         p = self.params

@@ -41,12 +41,15 @@ def test_single_rank_exchange_is_the_identity_and_checks_arguments():
         got = np.empty((1, _lib.NSUMS))
         h.d2h(got, buf)
         np.testing.assert_array_equal(got, want)
-        # sharded tail metrics with a single shard == the single-device metrics (same kernels + the exchange in between)
+        # sharded tail metrics with a single shard == the single-device metrics (multi-kernel select + the exchange in
+        # between vs the one-launch select: same order statistics, sums folded in a different order)
         x = g.standard_t(3, size=200_001) * 0.01
         for conf in (0.99, 0.5):
-            np.testing.assert_array_equal(h.risk_metrics_sharded(x, conf), h.risk_metrics(x, conf))
+            a, b = h.risk_metrics_sharded(x, conf), h.risk_metrics(x, conf)
+            assert a[0] == b[0]                                        # VaR: an order statistic, exact
+            np.testing.assert_allclose(a, b, rtol=1e-11, equal_nan=True)
         x32 = x[:5000].astype(np.float32)
-        np.testing.assert_array_equal(h.risk_metrics_sharded(x32), h.risk_metrics(x32))
+        np.testing.assert_allclose(h.risk_metrics_sharded(x32), h.risk_metrics(x32), rtol=1e-11, equal_nan=True)
         with pytest.raises(_lib.B200MCError, match="empty"):
             h.risk_metrics_sharded(np.zeros(0))
         h.peer_close()

@@ -507,3 +507,19 @@ def test_surface_closed_forms_match_the_oracle():
         assert SF.bs_put_price(S, K, T, r, q, sig) == pytest.approx(O.bs_put_price(S, K, T, r, q, sig), rel=1e-13, abs=1e-13)
     assert SF.bs_vega(100.0, 100.0, 1e-11, 0.05, 0.0, 0.2) == 0.0
     assert SF.bs_vega(100.0, 100.0, 1.0, 0.05, 0.0, 0.2) == pytest.approx(37.524, abs=1e-3)
+
+
+def test_expired_option_returns_the_intrinsic_value_like_the_reference():
+    """T == 0: the reference walks 10 steps of dt = 0 and returns the intrinsic value with zero standard error
+    (engine/monte_carlo.py:287, bs_price :31-34); the mirror answers without a launch (no GPU needed)."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams
+    for rng in ("philox", "reference"):
+        e = MonteCarloEngine(SVJParams(), 1000, 252, 42, rng=rng)
+        r = e.price(105.0, 100.0, 0.0, True)
+        assert r == {"price": 5.0, "std_error": 0.0, "num_paths_used": 1000, "num_steps": 10, "bs_cv_adjustment": 0.0,
+                     "bs_ref": 5.0, "raw_mc_price": 5.0}
+        assert e.price(105.0, 100.0, 0.0, False)["price"] == 0.0
+        b = e.price_batch(105.0, [100.0, 110.0], 0.0, True)
+        assert [x["price"] for x in b] == [5.0, 0.0] and b[0]["strike"] == 100.0 and b[0]["bs_ref"] == 5.0
+    e = MonteCarloEngine(SVJParams(), 1000, 252, 42, use_control_variate=False, rng="philox")
+    assert set(e.price(95.0, 100.0, 0.0, False)) == {"price", "std_error", "num_paths_used", "num_steps"}
