@@ -27,6 +27,7 @@ struct b200mc_handle {
     bool own_stream;                                   // false after b200mc_set_stream
     int smem_optin;                                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
     const void *occ_kern[64]; size_t occ_smem[64]; int occ_val[64]; int n_occ;   // (kernel, smem) -> resident CTAs per SM
+    void *risk_state; bool risk_state_clean; unsigned long long risk_barrier;            // state of the one-launch tail-metric select (risk.cu), zeroed by the kernel itself
     const void *risk_x; int64_t risk_n; int risk_dtype; // vector of the multi-rank tail-metric primitives (risk.cu)
     unsigned int *d_counter;                           // "last block reduces" ticket
     void *peer_local; void *peer_ptr[B200MC_PEER_MAX_RANKS]; int peer_rank, peer_world;   // peer.cu: exchange buffers

@@ -70,6 +70,7 @@ extern "C" int b200mc_destroy(b200mc_handle *h)
     if (h->h_result) cudaFreeHost(h->h_result);
     if (h->h_pool) cudaFreeHost(h->h_pool);
     if (h->d_counter) cudaFree(h->d_counter);
+    if (h->risk_state) cudaFree(h->risk_state);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);

@@ -137,8 +137,8 @@ constexpr int RF_NACC = 9;       // c2, c3, c4, cnt0, sum0, cnt1, logsum1, sum, 
 
 struct FusedState {
     unsigned int hist[RF_MAXPASS][2][RF_BINS];
-    unsigned int barrier;
-    unsigned int pad_[15];
+    unsigned long long barrier;  // monotonic across launches (the host passes the value it starts from)
+    unsigned long long pad_[7];
     double result[16];           // sum, neg, c2, c3, c4, cnt0, sum0, cnt1, logsum1, thr0, thr1
 };
 
@@ -175,14 +175,14 @@ template <typename T> __device__ __forceinline__ int rf_width(int d)
     return hi < RF_BITS ? hi : RF_BITS;
 }
 
-__device__ __forceinline__ void rf_grid_sync(unsigned int *bar, unsigned int &target)
+__device__ __forceinline__ void rf_grid_sync(unsigned long long *bar, unsigned long long &target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         __threadfence();
-        atomicAdd(bar, 1u);
-        while (*(volatile unsigned int *)bar < target) { }
+        atomicAdd(bar, 1ull);
+        while (*(volatile unsigned long long *)bar < target) { }
         __threadfence();
     }
     __syncthreads();
@@ -267,7 +267,8 @@ __device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long l
 
 template <typename T, int MINB>
 __global__ void __launch_bounds__(RF_THREADS, MINB)
-k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState *st, double *partials /* [grid][RF_NACC] */)
+k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState *st, double *partials /* [grid][RF_NACC] */,
+             unsigned long long bar_base)
 {
     using KT = RfKey<T>;
     using K = typename KT::K;
@@ -281,7 +282,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
     __shared__ long long s_rank[2];
     __shared__ int s_nsel;
     const int tid = threadIdx.x;
-    unsigned int bar_target = 0;
+    unsigned long long bar_target = bar_base;
     const long long stride = (long long)gridDim.x * RF_THREADS, i0 = (long long)blockIdx.x * RF_THREADS + tid;
 
     // ---- pass 0 -------------------------------------------------------------------------------------------------
@@ -413,6 +414,9 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         }
     }
     rf_grid_sync(&st->barrier, bar_target);
+    // leave the histograms zeroed for the next launch (all CTAs are past their last read of them; the barrier counter
+    // is monotonic and is never reset while CTAs may still be spinning on it)
+    for (long long i = i0; i < (long long)(RF_MAXPASS * 2 * RF_BINS); i += stride) (&st->hist[0][0][0])[i] = 0u;
     if (blockIdx.x == 0) {
         for (int j = 0; j < 7; ++j) {
             double t = 0.0;
@@ -462,18 +466,31 @@ static int risk_run_fused(b200mc_handle *h, const T *x_dev, const int64_t n, dou
     const int64_t cap = (int64_t)h->sm_count * (occ < 2 ? occ : 2);          // co-resident by construction
     if (grid > cap) grid = cap;
     const size_t off_pa = (sizeof(FusedState) + 255) & ~(size_t)255;
-    B200MC_TRY(ensure(h, &h->d_scratch, &h->scratch_bytes, off_pa + (size_t)grid * RF_NACC * 8 + 64));
-    FusedState *st = (FusedState *)h->d_scratch;
-    double *partials = (double *)((char *)h->d_scratch + off_pa);
-    B200MC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(FusedState), h->stream));
+    // the select's state has its own buffer: the kernel leaves it zeroed when it ends, so only the first call (and a call
+    // after a failed launch) pays for a memset
+    if (!h->risk_state) {
+        B200MC_CUDA(h, cudaMalloc(&h->risk_state, off_pa + (size_t)h->sm_count * 2 * RF_NACC * 8 + 64));
+        h->risk_state_clean = false;
+    }
+    FusedState *st = (FusedState *)h->risk_state;
+    double *partials = (double *)((char *)h->risk_state + off_pa);
+    if (!h->risk_state_clean) {
+        B200MC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(FusedState), h->stream));
+        h->risk_barrier = 0;
+    }
+    h->risk_state_clean = false;
     long long nn = n;
-    void *args[] = {(void *)&x_dev, (void *)&nn, (void *)&confidence, (void *)&st, (void *)&partials};
+    unsigned long long bar_base = h->risk_barrier;
+    h->risk_barrier += (unsigned long long)(RfKey<T>::NPASS + 1) * (unsigned long long)grid;     // grid barriers of this launch
+    void *args[] = {(void *)&x_dev, (void *)&nn, (void *)&confidence, (void *)&st, (void *)&partials, (void *)&bar_base};
     B200MC_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0,
                                                 h->stream));
     h->launches += 1;
-    double r[12];
-    B200MC_CUDA(h, cudaMemcpyAsync(r, st->result, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+    B200MC_TRY(ensure(h, &h->h_result, &h->h_result_bytes, 4096, true));
+    double *r = (double *)h->h_result;                                        // pinned landing buffer
+    B200MC_CUDA(h, cudaMemcpyAsync(r, st->result, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->risk_state_clean = true;                                               // the kernel ran to its end
     const double nnd = (double)n, mean = r[0] / nnd;                          // :137
     const int64_t m = (int64_t)r[1];
     int64_t cutoff = (int64_t)(nnd * (1.0 - confidence));                     // :128
