@@ -73,7 +73,10 @@ def test_same_word_pair_marginals_exact_joint_structure_bounded(H, seed):
     e = n / c.size
     excess = max(float(((c - e) ** 2).sum() / e) / (c.size - 1) - 1.0, 0.0) * (c.size / n)
     assert 0.03 < math.sqrt(excess) < 0.05, math.sqrt(excess)          # rms relative deviation of the cell probabilities
-    assert np.abs(c / e - 1).max() < 0.25
+    # the worst cells are the thin ones next to an axis in the outermost rows (|z_a| > 2.15, |z_b| < 0.02): their angular
+    # width (0.009 rad) is below the spacing of the 512 arms (0.0123 rad), so zero or one arm crosses them: up to 53 % off
+    dev = np.abs(c / e - 1)
+    assert dev.max() < 0.8 and np.quantile(dev, 0.99) < 0.2, (dev.max(), np.quantile(dev, 0.99))
 
 
 @pytest.mark.parametrize("lag", [0, 1])
