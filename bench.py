@@ -384,16 +384,23 @@ def hbm_roofline(h, torch, rates, n_paths=4_000_000, reps=3):
                      "bytes_per_launch": nbytes, "ms": best, "peak_source": src, "shape": [n_paths, N_STEPS + 1], "ld": ld,
                      "note": note}
         del buf
-    # the fp32 store carries ~21 instructions per 4 stored bytes (Philox + Box-Muller + exp + the shared-memory fill): its
-    # binding roof is the SAME instruction-issue model as the fused kernel, not HBM -- state both
-    a = {"imad_wide": 18.5 / 8, "alu": (20 + 4 * 2) / 8 + 0.5, "fp32": 4 * 3 / 8 + 4.0, "xu": 3.0, "lsu": 1.1, "loop": 0.6}
+    # the fp32 store carries ~24 instructions per 4 stored bytes (Philox + Box-Muller + the polynomial growth factor + the
+    # shared-memory fill): its binding roof is the SAME instruction-issue model as the fused kernel, not HBM -- state both.
+    # Algorithmic count per stored value: the draw (2.3 wide, 3.5 ALU, 2.5 FP32, 2 MUFU) + delta FMA + degree-4 expm1 (3 FMA +
+    # FMUL) + running product FMA + scaling FMUL + STS (+ the chunk totals) + loop.
+    a = {"imad_wide": 18.5 / 8, "alu": (20 + 4 * 2) / 8, "fp32": 4 * 5 / 8 + 7.0, "xu": 2.0, "lsu": 1.1, "loop": 0.6}
     other = a["alu"] + a["fp32"] + a["xu"] + a["lsu"] + a["loop"]
     b = pipe_bounds(rates, a["imad_wide"], other, a["alu"], a["xu"])
     issue_gbs = min(b.values()) * 4.016 / 1e9
+    ncu_instr_per_value = 23.8          # smsp__inst_executed.sum * 32 / 1e9 values, profiles/r02_ncu_k_paths_tma_poly4_minb4.txt
+    sass_gbs = 4.016 / 1e9 / (a["imad_wide"] / rates["imad_wide"] + (ncu_instr_per_value - a["imad_wide"]) / rates["ffma"])
     out["f32"]["instruction_bound"] = {"algorithmic_per_path_step": a, "pipe_bounds_path_steps_per_s": b,
                                        "as_GB_per_s": issue_gbs, "frac_of_binding_roof": out["f32"]["achieved"] / min(issue_gbs, peak),
-                                       "note": "min(HBM, issue, XU): 3 MUFU + ~18 issue slots per stored float put the fp32 store on the "
-                                               "issue/XU roof below the HBM roof; the float64-output variant is HBM-bound"}
+                                       "executed_instructions_per_value_ncu": ncu_instr_per_value,
+                                       "executed_mix_bound_GB_per_s": sass_gbs, "frac_of_executed_mix_bound": out["f32"]["achieved"] / sass_gbs,
+                                       "note": "min(HBM, issue, XU): ~24 issue slots (+3 per IMAD.WIDE) per stored float put the fp32 store "
+                                               "on the instruction-issue roof below the HBM roof (ncu: issue port 94 % occupied); the "
+                                               "float64-output variant is HBM-bound"}
     return out
 
 
