@@ -135,11 +135,16 @@ constexpr int RF_BINS = 1 << RF_BITS;
 constexpr int RF_MAXPASS = 6;
 constexpr int RF_NACC = 9;       // c2, c3, c4, cnt0, sum0, cnt1, logsum1, sum, neg
 
+constexpr int RF_CAP = 2048;     // a selection with at most this many candidates left is finished by gathering them
+
 struct FusedState {
     unsigned int hist[RF_MAXPASS][2][RF_BINS];
-    unsigned long long barrier;  // monotonic across launches (the host passes the value it starts from)
-    unsigned long long pad_[7];
+    unsigned long long barrier;  // grid barrier counter; the last CTA to leave the kernel resets it (and ncand, done)
+    unsigned int ncand[2];
+    unsigned int done;
+    unsigned int pad_[11];
     double result[16];           // sum, neg, c2, c3, c4, cnt0, sum0, cnt1, logsum1, thr0, thr1
+    unsigned long long cand[2][RF_CAP];
 };
 
 template <typename T> struct RfKey;
@@ -226,7 +231,7 @@ __device__ __forceinline__ double rf_block_sum(double v, double *red)
 // every CTA: find, in the global histogram h (nbins bins), the bin that holds order statistic `rank`; returns the bin and
 // the number of elements in lower bins.  4 bins per thread + one block scan.
 __device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long long rank, unsigned long long *scan,
-                                        int *bin_out, long long *below_out)
+                                        int *bin_out, long long *below_out, long long *count_out)
 {
     const int t = threadIdx.x;
     unsigned int c[4];
@@ -255,12 +260,12 @@ __device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long l
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (c[i] != 0u && (long long)cum <= rank && rank < (long long)(cum + c[i])) { *bin_out = 4 * t + i; *below_out = (long long)cum; }
+        if (c[i] != 0u && (long long)cum <= rank && rank < (long long)(cum + c[i])) { *bin_out = 4 * t + i; *below_out = (long long)cum; *count_out = (long long)c[i]; }
         cum += c[i];
     }
     __syncthreads();
     if (*bin_out < 0) {                                            // rank beyond the population (cannot happen for valid ranks)
-        if (t == 0) { *bin_out = nbins - 1; *below_out = 0; }
+        if (t == 0) { *bin_out = nbins - 1; *below_out = 0; *count_out = 0x7fffffffffffffffll; }
         __syncthreads();
     }
 }
@@ -277,7 +282,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
     __shared__ double red[RF_THREADS / 32];
     __shared__ unsigned long long scan[RF_THREADS / 32];
     __shared__ int s_bin[2];
-    __shared__ long long s_below[2];
+    __shared__ long long s_below[2], s_cnt[2];
     __shared__ double s_mean;
     __shared__ long long s_rank[2];
     __shared__ int s_nsel;
@@ -338,17 +343,24 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
     const int nsel = s_nsel;
     K prefix[2] = {0, 0};            // decided digits of each selection, in place (lower bits zero)
     long long rank[2] = {s_rank[0], s_rank[1]};
+    // gather: once every selection has at most RF_CAP candidates left, the next pass collects them instead of counting
+    // a digit and CTA 0 finishes the selections with a sort in shared memory -- 3 reads of the vector for 4e6 continuous
+    // values instead of 6.  Heavy ties (an option P&L vector is 45 % one value) never get there and take all the digits.
+    bool gather = true;
     for (int sel = 0; sel < nsel; ++sel) {
-        rf_pick(&st->hist[0][0][0], 1 << rf_width<T>(0), rank[sel], scan, &s_bin[sel], &s_below[sel]);
+        rf_pick(&st->hist[0][0][0], 1 << rf_width<T>(0), rank[sel], scan, &s_bin[sel], &s_below[sel], &s_cnt[sel]);
         prefix[sel] = (K)s_bin[sel] << rf_shift<T>(0);
         rank[sel] -= s_below[sel];
+        gather = gather && s_cnt[sel] <= RF_CAP;
         __syncthreads();
     }
+    bool finished = false;
 
     // ---- passes 1 .. NPASS - 1 ---------------------------------------------------------------------------------
     double c2 = 0.0, c3 = 0.0, c4 = 0.0, cnt[2] = {0.0, 0.0}, acc[2] = {0.0, 0.0};     // acc: sum (sel 0), sum log|x| (sel 1)
 #pragma unroll 1
     for (int d = 1; d < NPASS; ++d) {
+        const bool gpass = gather;                                               // the same on every CTA
         for (int i = tid; i < 2 * RF_BINS; i += RF_THREADS) (&sh[0][0])[i] = 0u;
         __syncthreads();
         const int shift = rf_shift<T>(d), up = rf_shift<T>(d - 1);              // up: everything decided so far sits above it
@@ -367,29 +379,76 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             }
             const K hi = key >> up;
             const unsigned int digit = (unsigned int)(key >> shift) & mask;
-            if (hi == p0) rf_vote(&sh[0][0], digit);
-            else if (hi < p0 && (d == 1 || (key >> up2) == q0)) { cnt0 += 1.0; acc0 += v; }
+            if (hi == p0) {
+                if (gpass) st->cand[0][atomicAdd(&st->ncand[0], 1u)] = (unsigned long long)key;
+                else rf_vote(&sh[0][0], digit);
+            } else if (hi < p0 && (d == 1 || (key >> up2) == q0)) { cnt0 += 1.0; acc0 += v; }
             if (nsel > 1) {
-                if (hi == p1) rf_vote(&sh[1][0], digit);
-                else if (hi < p1 && (d == 1 || (key >> up2) == q1)) { cnt1 += 1.0; acc1 += log(fabs(v)); }
+                if (hi == p1) {
+                    if (gpass) st->cand[1][atomicAdd(&st->ncand[1], 1u)] = (unsigned long long)key;
+                    else rf_vote(&sh[1][0], digit);
+                } else if (hi < p1 && (d == 1 || (key >> up2) == q1)) { cnt1 += 1.0; acc1 += log(fabs(v)); }
             }
         });
         cnt[0] += cnt0; acc[0] += acc0; cnt[1] += cnt1; acc[1] += acc1;
         __syncthreads();
-        for (int i = tid; i < nsel * RF_BINS; i += RF_THREADS) {
-            const unsigned int c = (&sh[0][0])[i];
-            if (c) atomicAdd(&st->hist[d][0][0] + i, c);
+        if (!gpass) {
+            for (int i = tid; i < nsel * RF_BINS; i += RF_THREADS) {
+                const unsigned int c = (&sh[0][0])[i];
+                if (c) atomicAdd(&st->hist[d][0][0] + i, c);
+            }
         }
         rf_grid_sync(&st->barrier, bar_target);
+        if (gpass) {
+            // CTA 0 sorts each selection's candidates (bitonic, shared memory) and reads the order statistic off
+            if (blockIdx.x == 0) {
+                unsigned long long *buf = reinterpret_cast<unsigned long long *>(&sh[0][0]);      // 2048 x 8 B
+                for (int sel = 0; sel < nsel; ++sel) {
+                    const int nc = (int)__ldcg(&st->ncand[sel]);
+                    __syncthreads();
+                    for (int i = tid; i < RF_CAP; i += RF_THREADS) buf[i] = i < nc ? __ldcg(&st->cand[sel][i]) : ~0ull;
+                    __syncthreads();
+                    for (int k = 2; k <= RF_CAP; k <<= 1) {
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            for (int i = tid; i < RF_CAP; i += RF_THREADS) {
+                                const int o = i ^ j;
+                                if (o > i) {
+                                    const unsigned long long a = buf[i], b = buf[o];
+                                    if ((a > b) == ((i & k) == 0)) { buf[i] = b; buf[o] = a; }
+                                }
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    const unsigned long long thr_key = buf[rank[sel] < nc ? rank[sel] : (nc > 0 ? nc - 1 : 0)];
+                    double cb = 0.0, ab = 0.0;
+                    for (int i = tid; i < nc; i += RF_THREADS) {
+                        if (buf[i] < thr_key) {
+                            const double v = KT::value((K)buf[i]);
+                            cb += 1.0;
+                            ab += sel == 0 ? v : log(fabs(v));
+                        }
+                    }
+                    cnt[sel] += cb;
+                    acc[sel] += ab;
+                    prefix[sel] = (K)thr_key;
+                }
+                __syncthreads();
+            }
+            finished = true;
+            break;
+        }
+        gather = true;
         for (int sel = 0; sel < nsel; ++sel) {
-            rf_pick(&st->hist[d][sel][0], 1 << rf_width<T>(d), rank[sel], scan, &s_bin[sel], &s_below[sel]);
+            rf_pick(&st->hist[d][sel][0], 1 << rf_width<T>(d), rank[sel], scan, &s_bin[sel], &s_below[sel], &s_cnt[sel]);
             prefix[sel] |= (K)s_bin[sel] << shift;
             rank[sel] -= s_below[sel];
+            gather = gather && s_cnt[sel] <= RF_CAP;
             __syncthreads();
         }
     }
     // ---- the candidates that differ from the threshold in the last digit only: from the last histogram (CTA 0) ------
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && !finished) {
         constexpr int d = NPASS - 1;
         const int nb = 1 << rf_width<T>(d);
         for (int sel = 0; sel < nsel; ++sel) {
@@ -414,8 +473,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         }
     }
     rf_grid_sync(&st->barrier, bar_target);
-    // leave the histograms zeroed for the next launch (all CTAs are past their last read of them; the barrier counter
-    // is monotonic and is never reset while CTAs may still be spinning on it)
+    // leave the histograms zeroed for the next launch (all CTAs are past their last read of them)
     for (long long i = i0; i < (long long)(RF_MAXPASS * 2 * RF_BINS); i += stride) (&st->hist[0][0][0])[i] = 0u;
     if (blockIdx.x == 0) {
         for (int j = 0; j < 7; ++j) {
@@ -428,6 +486,18 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             st->result[9] = KT::value(prefix[0]);
             st->result[10] = nsel > 1 ? KT::value(prefix[1]) : 0.0;
             st->result[11] = (double)nsel;
+            st->result[12] = finished ? 1.0 : 0.0;
+        }
+    }
+    // the last CTA to get here re-arms the barrier and the candidate counters (nobody can still be spinning: every CTA
+    // has left the final barrier before it signs off)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&st->done, 1u) == gridDim.x - 1) {
+            st->barrier = 0ull;
+            st->ncand[0] = st->ncand[1] = 0u;
+            st->done = 0u;
         }
     }
 }
@@ -474,21 +544,17 @@ static int risk_run_fused(b200mc_handle *h, const T *x_dev, const int64_t n, dou
     }
     FusedState *st = (FusedState *)h->risk_state;
     double *partials = (double *)((char *)h->risk_state + off_pa);
-    if (!h->risk_state_clean) {
-        B200MC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(FusedState), h->stream));
-        h->risk_barrier = 0;
-    }
+    if (!h->risk_state_clean) B200MC_CUDA(h, cudaMemsetAsync(st, 0, sizeof(FusedState), h->stream));
     h->risk_state_clean = false;
     long long nn = n;
-    unsigned long long bar_base = h->risk_barrier;
-    h->risk_barrier += (unsigned long long)(RfKey<T>::NPASS + 1) * (unsigned long long)grid;     // grid barriers of this launch
+    unsigned long long bar_base = 0;                       // the kernel re-arms its barrier before it ends
     void *args[] = {(void *)&x_dev, (void *)&nn, (void *)&confidence, (void *)&st, (void *)&partials, (void *)&bar_base};
     B200MC_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0,
                                                 h->stream));
     h->launches += 1;
     B200MC_TRY(ensure(h, &h->h_result, &h->h_result_bytes, 4096, true));
     double *r = (double *)h->h_result;                                        // pinned landing buffer
-    B200MC_CUDA(h, cudaMemcpyAsync(r, st->result, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    B200MC_CUDA(h, cudaMemcpyAsync(r, st->result, 13 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
     h->risk_state_clean = true;                                               // the kernel ran to its end
     const double nnd = (double)n, mean = r[0] / nnd;                          // :137
