@@ -16,7 +16,7 @@ e2e    = the same metric through the public Python API (GreeksEngine.delta/vega/
          arguments and a host result per step: strikes go host->device, the b200mc_sums struct device->host).
 roofline = instruction roofline of the fused kernel (it moves no data): per-path-step instruction counts of the
          kernel's hot loop (read from the SASS of the shipped .so) against issue rates of the same pipes measured
-         in this run by b200mc_microbench.  roofline_hbm = the path-store kernel against MEASURED_PEAKS.json.
+         in this run by the probe library (tools/probe).  roofline_hbm = the path-store kernel against MEASURED_PEAKS.json.
 roofline_fp64 / roofline_heston / roofline_svj = the same model for the fp64 leg of cfg2 and for the reference's default
          model (Heston + jumps) and its jump-free special case.
 cfg5_strong_scaling, cfg4_sharded_path_store, cfg2_fp64_greeks, check.allreduce = the multi-GPU configurations of
@@ -266,11 +266,17 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ roofline
 def measured_rates(h):
-    """Issue rates of the pipes the fused kernels live on, measured on this device in this run (csrc/microbench.cu)."""
-    r = {"ffma": h.microbench(0), "imad_wide": h.microbench(1), "lop3": h.microbench(2),
-         "mufu_ex2": h.microbench(3), "mufu_sin": h.microbench(4), "mufu_lg2": h.microbench(9),
-         "mufu_sqrt": h.microbench(10), "ffma_lop3_pairs": h.microbench(11), "f2f_f32_f64": h.microbench(16),
-         "dadd": h.microbench(17), "philox_calls": h.microbench(6), "philox_bm_calls": h.microbench(7)}
+    """Issue rates of the pipes the fused kernels live on, measured on this device in this run by the probe library
+    (tools/probe/libb200mc_probe.so -- a measurement tool with its own C ABI, not part of libb200mc.so)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from probe import probe as P
+    dev = h.device
+    r = {"ffma": P.rate(P.FFMA, device=dev), "imad_wide": P.rate(P.IMAD_WIDE, device=dev), "lop3": P.rate(P.LOP3, device=dev),
+         "mufu_ex2": P.rate(P.MUFU_EX2, device=dev), "mufu_sin": P.rate(P.MUFU_SIN, device=dev),
+         "mufu_lg2": P.rate(P.MUFU_LG2, device=dev), "mufu_sqrt": P.rate(P.MUFU_SQRT, device=dev),
+         "ffma_lop3_pairs": P.rate(P.FFMA_LOP3, device=dev), "f2f_f32_f64": P.rate(P.F2F, device=dev),
+         "dadd": P.rate(P.DADD, device=dev), "philox_calls": P.rate(P.PHILOX, device=dev),
+         "philox_bm_calls": P.rate(P.PHILOX_BM, device=dev)}
     r["xu"] = min(r["mufu_ex2"], r["mufu_sin"], r["mufu_lg2"], r["mufu_sqrt"])
     return r
 
@@ -330,7 +336,7 @@ def instruction_roofline(which, rates, achieved, steps_per_call):
            "kind": "instruction roofline (the kernel moves no data): algorithmic instructions per path-step over issue rates "
                    "measured in this run; the binding pipe is the smallest of pipe_bounds_algorithmic",
            "algorithmic_per_path_step": a, "pipe_bounds_algorithmic": b_algo,
-           "peak_source": "b200mc_microbench on this device in this run (MEASURED_PEAKS.json holds no pipe rates)"}
+           "peak_source": "tools/probe/libb200mc_probe.so on this device in this run (MEASURED_PEAKS.json holds no pipe rates)"}
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import sass_mix

@@ -396,16 +396,6 @@ int b200mc_free_host(b200mc_handle *h, void *host_ptr);
 int b200mc_timer_begin(b200mc_handle *h);
 int b200mc_timer_end(b200mc_handle *h, float *elapsed_ms);
 
-/* ---- issue-rate probes: the denominators of the fused kernel's instruction roofline --------------------------
- * which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox call + two
- * Box-Muller pairs, 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 pairs, 12 mul.lo.u32, 13 mul.hi.u32, 14 mul.lo + mul.hi of
- * the same product (+ xor).  *ops_per_s: thread-level operations per
- * second over the whole device (CUDA events, best of 3 after a warm-up launch). */
-int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s);
-/* Mixed probe: per thread-iteration counts[0] IMAD.WIDE + counts[1] LOP3 + counts[2] MUFU + counts[3] FFMA (a fixed
- * table indexed by combo); *iters_per_s = thread-iterations per second.  Shows which pipes overlap. */
-int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, double *iters_per_s, int counts[4]);
-
 #ifdef __cplusplus
 }
 #endif

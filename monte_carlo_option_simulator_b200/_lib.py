@@ -157,8 +157,6 @@ _PROTOS = {
     "b200mc_free_host": (C.c_int, [_vp, _vp]),
     "b200mc_timer_begin": (C.c_int, [_vp]),
     "b200mc_timer_end": (C.c_int, [_vp, C.POINTER(C.c_float)]),
-    "b200mc_microbench": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
-    "b200mc_microbench_mix": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int)]),
 }
 EXPORTS = tuple(_PROTOS)
 
@@ -310,17 +308,6 @@ class Handle:
         ms = C.c_float()
         self._check(self.lib.b200mc_timer_end(self.h, C.byref(ms)))
         return float(ms.value)
-
-    def microbench(self, which: int, iters: int = 4096) -> float:
-        v = C.c_double()
-        self._check(self.lib.b200mc_microbench(self.h, int(which), int(iters), C.byref(v)))
-        return float(v.value)
-
-    def microbench_mix(self, combo: int, iters: int = 2048):
-        v = C.c_double()
-        cnt = (C.c_int * 4)()
-        self._check(self.lib.b200mc_microbench_mix(self.h, int(combo), int(iters), C.byref(v), cnt))
-        return float(v.value), tuple(cnt)
 
     def malloc(self, nbytes: int) -> int:
         p = _vp()

@@ -145,6 +145,7 @@ struct FusedState {
     unsigned int pad_[11];
     double result[16];           // sum, neg, c2, c3, c4, cnt0, sum0, cnt1, logsum1, thr0, thr1
     unsigned long long cand[2][RF_CAP];
+    unsigned long long trace[16];    // %globaltimer of CTA 0 at the phase boundaries (B200MC_RISK_TRACE=1 prints them)
 };
 
 template <typename T> struct RfKey;
@@ -287,6 +288,15 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
     __shared__ long long s_rank[2];
     __shared__ int s_nsel;
     const int tid = threadIdx.x;
+    int trace_n = 0;
+    auto mark = [&]() {
+        if (blockIdx.x == 0 && tid == 0 && trace_n < 16) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            st->trace[trace_n++] = t;
+        }
+    };
+    mark();
     unsigned long long bar_target = bar_base;
     const long long stride = (long long)gridDim.x * RF_THREADS, i0 = (long long)blockIdx.x * RF_THREADS + tid;
 
@@ -304,6 +314,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         });
     }
     __syncthreads();
+    mark();                                                                      // 1: pass 0 read
     for (int i = tid; i < RF_BINS; i += RF_THREADS)
         if (sh[0][i]) atomicAdd(&st->hist[0][0][i], sh[0][i]);
     {
@@ -311,6 +322,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         if (tid == 0) { partials[(size_t)blockIdx.x * RF_NACC + 7] = bs; partials[(size_t)blockIdx.x * RF_NACC + 8] = bn; }
     }
     rf_grid_sync(&st->barrier, bar_target);
+    mark();                                                                      // 2: first grid barrier passed
     // every CTA: total sum and count of negatives in a fixed order, then the two ranks (engine/risk.py:128-134,147-166)
     {
         double ts = 0.0, tn = 0.0;
@@ -355,6 +367,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         __syncthreads();
     }
     bool finished = false;
+    mark();                                                                      // 3: ranks + digit-0 pick
 
     // ---- passes 1 .. NPASS - 1 ---------------------------------------------------------------------------------
     double c2 = 0.0, c3 = 0.0, c4 = 0.0, cnt[2] = {0.0, 0.0}, acc[2] = {0.0, 0.0};     // acc: sum (sel 0), sum log|x| (sel 1)
@@ -392,6 +405,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         });
         cnt[0] += cnt0; acc[0] += acc0; cnt[1] += cnt1; acc[1] += acc1;
         __syncthreads();
+        mark();                                                                  // pass d read
         if (!gpass) {
             for (int i = tid; i < nsel * RF_BINS; i += RF_THREADS) {
                 const unsigned int c = (&sh[0][0])[i];
@@ -399,6 +413,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             }
         }
         rf_grid_sync(&st->barrier, bar_target);
+        mark();                                                                  // barrier after pass d
         if (gpass) {
             // CTA 0 sorts each selection's candidates (bitonic, shared memory) and reads the order statistic off
             if (blockIdx.x == 0) {
@@ -435,6 +450,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
                 }
                 __syncthreads();
             }
+            mark();                                                              // candidates sorted
             finished = true;
             break;
         }
@@ -446,6 +462,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             gather = gather && s_cnt[sel] <= RF_CAP;
             __syncthreads();
         }
+        mark();                                                                  // digit d picked
     }
     // ---- the candidates that differ from the threshold in the last digit only: from the last histogram (CTA 0) ------
     if (blockIdx.x == 0 && !finished) {
@@ -473,6 +490,7 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         }
     }
     rf_grid_sync(&st->barrier, bar_target);
+    mark();                                                                      // final barrier passed
     // leave the histograms zeroed for the next launch (all CTAs are past their last read of them)
     for (long long i = i0; i < (long long)(RF_MAXPASS * 2 * RF_BINS); i += stride) (&st->hist[0][0][0])[i] = 0u;
     if (blockIdx.x == 0) {
@@ -489,6 +507,8 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             st->result[12] = finished ? 1.0 : 0.0;
         }
     }
+    mark();                                                                      // end of CTA 0
+    if (blockIdx.x == 0 && tid == 0) { for (int i = trace_n; i < 16; ++i) st->trace[i] = 0ull; }
     // the last CTA to get here re-arms the barrier and the candidate counters (nobody can still be spinning: every CTA
     // has left the final barrier before it signs off)
     __syncthreads();
@@ -557,6 +577,13 @@ static int risk_run_fused(b200mc_handle *h, const T *x_dev, const int64_t n, dou
     B200MC_CUDA(h, cudaMemcpyAsync(r, st->result, 13 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
     h->risk_state_clean = true;                                               // the kernel ran to its end
+    if (getenv("B200MC_RISK_TRACE")) {
+        unsigned long long tr[16];
+        B200MC_CUDA(h, cudaMemcpy(tr, st->trace, sizeof(tr), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[k_risk_fused n=%lld grid=%lld] us since start:", (long long)n, (long long)grid);
+        for (int i = 1; i < 16 && tr[i]; ++i) fprintf(stderr, " %.1f", (double)(tr[i] - tr[0]) * 1e-3);
+        fprintf(stderr, "\n");
+    }
     const double nnd = (double)n, mean = r[0] / nnd;                          // :137
     const int64_t m = (int64_t)r[1];
     int64_t cutoff = (int64_t)(nnd * (1.0 - confidence));                     // :128

@@ -1,10 +1,16 @@
-// microbench.cu -- issue-rate probes for the pipes the fused kernel lives on.  The roofline of a kernel that moves
+// microbench.cu -- issue-rate probes for the pipes the fused kernel lives on.  MEASUREMENT TOOL, not product: built into its
+// own library (tools/probe/libb200mc_probe.so, tools/probe/Makefile) with its own two-function C ABI; libb200mc.so neither
+// contains nor links it.  It includes the product's philox.cuh only to time the very Philox / Box-Muller code that ships.  The roofline of a kernel that moves
 // no data is an instruction-throughput roofline; its denominators (FP32 FMA, 32x32->64 integer multiply, 3-input
 // logic, MUFU) are not in MEASURED_PEAKS.json, so bench.py measures them on the same device, in the same run,
 // with these kernels ("the builder must microbenchmark FFMA, IMAD.WIDE, LOP3, MUFU").
 // Each thread runs 8 independent dependency chains of one instruction type; with 2048 threads per SM resident the
 // pipe, not latency, is the limit.
-#include "common.cuh"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200mc.h"
+#include "../../monte_carlo_option_simulator_b200/csrc/philox.cuh"
 
 namespace b200mc {
 
@@ -218,16 +224,46 @@ template <int W> static void mb_launch(int grid, int iters, uint32_t seed, const
 using namespace b200mc;
 
 // Mixed probe: combo selects (NW, NL, NM, NF) from a fixed table; *iters_per_s = thread-iterations per second.
-extern "C" int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, double *iters_per_s, int counts[4])
+namespace {
+struct Probe {                      // one device context per call: stream, two events, a sink word
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t *sink = nullptr;
+    int open(int device)
+    {
+        cudaDeviceProp prop;
+        if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 1;
+        if (prop.major != 10) return 2;                                   // sm_100a code only
+        sm_count = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+        if (cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess) return 1;
+        if (cudaMalloc(&sink, 64) != cudaSuccess) return 1;
+        return 0;
+    }
+    ~Probe()
+    {
+        if (sink) cudaFree(sink);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+#define PROBE_CUDA(call) do { if ((call) != cudaSuccess) { cudaGetLastError(); return 3; } } while (0)
+} // namespace
+
+// Returns 0, or 1 (CUDA set-up failed), 2 (not an sm_100 device), 3 (CUDA error), 4 (bad argument).
+extern "C" int b200mc_probe_mix(int device, int combo, int iters, double *iters_per_s, int counts[4])
 {
-    if (!h || !iters_per_s || !counts) return fail(h, B200MC_EINVAL, "NULL argument");
-    if (iters <= 0) return fail(h, B200MC_EINVAL, "iters must be positive");
-    B200MC_CUDA(h, cudaSetDevice(h->device));
+    if (!iters_per_s || !counts || iters <= 0) return 4;
+    Probe pb;
+    if (int rc = pb.open(device)) return rc;
+    Probe *h = &pb;
     const int grid = h->sm_count * 8;
-    uint32_t *sink = (uint32_t *)h->d_counter + 4;
+    uint32_t *sink = h->sink;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
-        B200MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        PROBE_CUDA(cudaEventRecord(h->ev0, h->stream));
 #define MIXCASE(id, a, b, c, d) case id: k_mix<a, b, c, d><<<grid, 256, 0, h->stream>>>(iters, rep, sink); counts[0] = a; counts[1] = b; counts[2] = c; counts[3] = d; break;
         switch (combo) {
         MIXCASE(0, 8, 0, 0, 0)
@@ -247,16 +283,15 @@ extern "C" int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, dou
         MIXCASE(14, 8, 16, 4, 8)
         MIXCASE(15, 0, 16, 0, 16)
         MIXCASE(16, 4, 8, 4, 4)
-        default: return fail(h, B200MC_EINVAL, "unknown mix combo");
+        default: return 4;
         }
 #undef MIXCASE
-        B200MC_CUDA(h, cudaGetLastError());
-        B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-        B200MC_CUDA(h, cudaEventSynchronize(h->ev1));
+        PROBE_CUDA(cudaGetLastError());
+        PROBE_CUDA(cudaEventRecord(h->ev1, h->stream));
+        PROBE_CUDA(cudaEventSynchronize(h->ev1));
         float ms = 0.f;
-        B200MC_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        PROBE_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         if (rep > 0 && ms < best) best = ms;
-        h->launches += 1;
     }
     *iters_per_s = (double)grid * 256.0 * (double)iters / ((double)best * 1e-3);
     return 0;
@@ -266,43 +301,43 @@ extern "C" int b200mc_microbench_mix(b200mc_handle *h, int combo, int iters, dou
 // pairs = 8 normals (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs),
 // 12-14 IMAD lo / hi / lo+hi, 15 FFMA2, 16 fp32<->fp64 conversions, 17 DADD.
 // *ops_per_s = thread-level operations per second over the whole device (kernel time by CUDA events, best of 3).
-extern "C" int b200mc_microbench(b200mc_handle *h, int which, int iters, double *ops_per_s)
+extern "C" int b200mc_probe_rate(int device, int which, int iters, double *ops_per_s)
 {
-    if (!h || !ops_per_s) return fail(h, B200MC_EINVAL, "NULL argument");
-    if (which < 0 || which >= MB_COUNT || iters <= 0) return fail(h, B200MC_EINVAL, "bad microbench selector");
-    B200MC_CUDA(h, cudaSetDevice(h->device));
+    if (!ops_per_s || which < 0 || which >= MB_COUNT || iters <= 0) return 4;
+    Probe pb;
+    if (int rc = pb.open(device)) return rc;
+    Probe *h = &pb;
     const int grid = h->sm_count * 8;
     const PhiloxKey key = philox_make_key(0x9E3779B97F4A7C15ull);
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
-        B200MC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        PROBE_CUDA(cudaEventRecord(h->ev0, h->stream));
         switch (which) {
-        case 0: mb_launch<0>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 1: mb_launch<1>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 2: mb_launch<2>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 3: mb_launch<3>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 4: mb_launch<4>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 5: mb_launch<5>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 6: mb_launch<6>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 7: mb_launch<7>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 8: mb_launch<8>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 9: mb_launch<9>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 10: mb_launch<10>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 11: mb_launch<11>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 12: mb_launch<12>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 13: mb_launch<13>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 14: mb_launch<14>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 15: mb_launch<15>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        case 16: mb_launch<16>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
-        default: mb_launch<17>(grid, iters, rep, key, (uint32_t *)h->d_counter + 4, h->stream); break;
+        case 0: mb_launch<0>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 1: mb_launch<1>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 2: mb_launch<2>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 3: mb_launch<3>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 4: mb_launch<4>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 5: mb_launch<5>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 6: mb_launch<6>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 7: mb_launch<7>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 8: mb_launch<8>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 9: mb_launch<9>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 10: mb_launch<10>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 11: mb_launch<11>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 12: mb_launch<12>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 13: mb_launch<13>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 14: mb_launch<14>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 15: mb_launch<15>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 16: mb_launch<16>(grid, iters, rep, key, h->sink, h->stream); break;
+        default: mb_launch<17>(grid, iters, rep, key, h->sink, h->stream); break;
         }
-        B200MC_CUDA(h, cudaGetLastError());
-        B200MC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-        B200MC_CUDA(h, cudaEventSynchronize(h->ev1));
+        PROBE_CUDA(cudaGetLastError());
+        PROBE_CUDA(cudaEventRecord(h->ev1, h->stream));
+        PROBE_CUDA(cudaEventSynchronize(h->ev1));
         float ms = 0.f;
-        B200MC_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        PROBE_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         if (rep > 0 && ms < best) best = ms;
-        h->launches += 1;
     }
     const double per_thread = (which == MB_PHILOX || which == MB_PHILOX_BM) ? (double)iters
                             : (which == MB_MIX_FFMA_LOP3 ? 4.0 * iters : (which == MB_F2F ? 16.0 * iters : 8.0 * iters));

@@ -33,7 +33,5 @@ h.risk_metrics(rng.standard_t(3, size=100_000) * 0.01, 0.99)
 h.risk_metrics((rng.standard_t(3, size=5_000) * 0.01).astype(np.float32), 0.95)
 h.dump_philox(1, 100, 5, 0)
 h.normal_moments(1, 1000, 4)
-h.microbench(7, 16)
-h.microbench_mix(9, 16)
 print("sanitize smoke done, launches:", h.launches)
 h.close()
