@@ -252,6 +252,10 @@ class Handle:
 
     def close(self):
         if getattr(self, "h", None):
+            pool = getattr(self, "_draws_pool", None)
+            if pool is not None:                      # buffer handed back by a closed ReferenceDraws
+                self._draws_pool = None
+                self.lib.b200mc_free(self.h, _vp(pool[1]))
             self.lib.b200mc_destroy(self.h)
             self.h = None
 
@@ -654,7 +658,8 @@ class ReferenceDraws:
     def __init__(self, handle, seed, n_paths: int, n_steps: int, uniform_seed="seed+1"):
         self.h, self.n, self.steps = handle, int(n_paths), int(n_steps)
         N = self.n * self.steps
-        self.buf = handle.malloc(4 * N * 8 + 16 * self.n * 8)
+        self.nbytes = 4 * N * 8 + 16 * self.n * 8
+        self.buf = self._take(handle, self.nbytes)
         self.Z1, self.Z2, self.Zjs, self.Zj = (self.buf + i * N * 8 for i in range(4))
         self.S = self.buf + 4 * N * 8
         self.v = self.S + self.n * 8
@@ -693,10 +698,30 @@ class ReferenceDraws:
             out.append(a)
         return out
 
+    # cudaMalloc / cudaFree of a 400 MB buffer cost milliseconds each: a closed ReferenceDraws hands its buffer back to a
+    # one-slot pool on the handle, and the next one of the same or a smaller size takes it (calibration-style loops build
+    # a new engine per candidate)
+    @staticmethod
+    def _take(handle, nbytes):
+        slot = getattr(handle, "_draws_pool", None)
+        if slot is not None and slot[0] >= nbytes:
+            handle._draws_pool = None
+            return slot[1]
+        if slot is not None:
+            handle._draws_pool = None
+            handle.free(slot[1])
+        return handle.malloc(nbytes)
+
     def close(self):
         if self.buf:
-            self.h.free(self.buf)
+            if getattr(self.h, "h", None) is None:          # handle already destroyed: nothing to give back
+                self.buf = 0
+                return
+            old = getattr(self.h, "_draws_pool", None)
+            self.h._draws_pool = (self.nbytes, self.buf)
             self.buf = 0
+            if old is not None:
+                self.h.free(old[1])
 
     def __del__(self):
         try:

@@ -231,6 +231,7 @@ __device__ __forceinline__ double rf_block_sum(double v, double *red)
 
 // every CTA: find, in the global histogram h (nbins bins), the bin that holds order statistic `rank`; returns the bin and
 // the number of elements in lower bins.  4 bins per thread + one block scan.
+template <bool GLOBAL = true>
 __device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long long rank, unsigned long long *scan,
                                         int *bin_out, long long *below_out, long long *count_out)
 {
@@ -240,7 +241,7 @@ __device__ __forceinline__ void rf_pick(const unsigned int *h, int nbins, long l
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int b = 4 * t + i;
-        c[i] = b < nbins ? __ldcg(h + b) : 0u;
+        c[i] = b < nbins ? (GLOBAL ? __ldcg(h + b) : h[b]) : 0u;
         mine += c[i];
     }
     // inclusive scan of `mine` over the 512 threads
@@ -415,42 +416,44 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
         rf_grid_sync(&st->barrier, bar_target);
         mark();                                                                  // barrier after pass d
         if (gpass) {
-            // CTA 0 sorts each selection's candidates (bitonic, shared memory) and reads the order statistic off
+            // CTA 0 finishes each selection on its <= RF_CAP candidates alone: the remaining digits are counted in shared
+            // memory (at most 4 keys per thread), a microsecond per digit.  (A bitonic sort of the 2048 keys in
+            // shared memory took 23 us per selection.)
             if (blockIdx.x == 0) {
-                unsigned long long *buf = reinterpret_cast<unsigned long long *>(&sh[0][0]);      // 2048 x 8 B
                 for (int sel = 0; sel < nsel; ++sel) {
                     const int nc = (int)__ldcg(&st->ncand[sel]);
-                    __syncthreads();
-                    for (int i = tid; i < RF_CAP; i += RF_THREADS) buf[i] = i < nc ? __ldcg(&st->cand[sel][i]) : ~0ull;
-                    __syncthreads();
-                    for (int k = 2; k <= RF_CAP; k <<= 1) {
-                        for (int j = k >> 1; j > 0; j >>= 1) {
-                            for (int i = tid; i < RF_CAP; i += RF_THREADS) {
-                                const int o = i ^ j;
-                                if (o > i) {
-                                    const unsigned long long a = buf[i], b = buf[o];
-                                    if ((a > b) == ((i & k) == 0)) { buf[i] = b; buf[o] = a; }
-                                }
-                            }
-                            __syncthreads();
+                    for (int dd = d; dd < NPASS; ++dd) {
+                        __syncthreads();
+                        for (int i = tid; i < RF_BINS; i += RF_THREADS) sh[0][i] = 0u;
+                        __syncthreads();
+                        const int sh_d = rf_shift<T>(dd), up_d = rf_shift<T>(dd - 1);
+                        const unsigned int mask_d = (1u << rf_width<T>(dd)) - 1u;
+                        for (int i = tid; i < nc; i += RF_THREADS) {           // the keys are re-read from L2: <= 4 per thread
+                            const K key = (K)__ldcg(&st->cand[sel][i]);
+                            if ((key >> up_d) == (prefix[sel] >> up_d))
+                                atomicAdd(&sh[0][(unsigned int)(key >> sh_d) & mask_d], 1u);
                         }
+                        __syncthreads();
+                        rf_pick<false>(&sh[0][0], 1 << rf_width<T>(dd), rank[sel], scan, &s_bin[sel], &s_below[sel], &s_cnt[sel]);
+                        prefix[sel] |= (K)s_bin[sel] << sh_d;
+                        rank[sel] -= s_below[sel];
                     }
-                    const unsigned long long thr_key = buf[rank[sel] < nc ? rank[sel] : (nc > 0 ? nc - 1 : 0)];
+                    const K thr_key = prefix[sel];
                     double cb = 0.0, ab = 0.0;
                     for (int i = tid; i < nc; i += RF_THREADS) {
-                        if (buf[i] < thr_key) {
-                            const double v = KT::value((K)buf[i]);
+                        const K key = (K)__ldcg(&st->cand[sel][i]);
+                        if (key < thr_key) {
+                            const double v = KT::value(key);
                             cb += 1.0;
                             ab += sel == 0 ? v : log(fabs(v));
                         }
                     }
                     cnt[sel] += cb;
                     acc[sel] += ab;
-                    prefix[sel] = (K)thr_key;
                 }
                 __syncthreads();
             }
-            mark();                                                              // candidates sorted
+            mark();                                                              // candidates resolved
             finished = true;
             break;
         }
