@@ -726,8 +726,12 @@ def run_b200(args):
             extras["fp32_svj_antithetic"] = rate(SVJParams(), 22500.0, n // 4, _lib.ANTITHETIC, [22500.0])
             extras["fp32_heston_price_only"] = rate(SVJParams(lambda_j=0.0), 22500.0, n // 4, 0, [22500.0])
             extras["fp32_svj_price_only"] = rate(SVJParams(), 22500.0, n // 4, 0, [22500.0])
+            # SURVEY 8(d) counts the antithetic twin as a path of its own; this file counts a PAIR as one path everywhere
+            # else, so the pair rates are also given with the twin counted (2 x)
+            for k in ("fp32_antithetic", "fp32_heston_antithetic", "fp32_svj_antithetic"):
+                extras[k + "_twin_counted_as_a_path"] = 2.0 * extras[k]
             # the reference's default model (SVJParams(): Heston + jumps) and its jump-free special case: antithetic pairs,
-            # a pair counted as ONE path as everywhere in this file
+            # a pair counted as ONE path in the rooflines
             line["roofline_heston"] = instruction_roofline("heston_f32_antithetic", rates, extras["fp32_heston_antithetic"], 4.0)
             line["roofline_svj"] = instruction_roofline("svj_f32_antithetic", rates, extras["fp32_svj_antithetic"], 4.0)
             # BASELINE cfg3, API-parity reading: 64 strikes x 16 expiries, 1M paths per expiry shared across strikes

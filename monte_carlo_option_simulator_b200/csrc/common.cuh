@@ -66,6 +66,12 @@ inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pi
 {
     if (*have >= want) return 0;
     if (*p) {
+        // work queued on the handle's stream may still read the old buffer (an asynchronous copy out of the pinned bounce
+        // buffer, a kernel on the scratch): drain it before the buffer goes away
+        if (h && h->stream) cudaStreamSynchronize(h->stream);
+        // the multi-rank tail-metric primitives keep their vector in d_stage and its keys in d_scratch between calls: once
+        // either buffer is replaced, b200mc_risk_hist / _finish must fail loudly instead of reading freed memory
+        if (h && (p == &h->d_stage || p == &h->d_scratch)) h->risk_x = nullptr;
         if (pinned) cudaFreeHost(*p); else cudaFree(*p);
         *p = nullptr;
         *have = 0;

@@ -309,6 +309,13 @@ class MonteCarloEngine:
         """Price a European option; same keys as monte_carlo.py:345-373."""
         if T == 0:
             return self._expired(spot, strike, is_call)
+        if self.num_paths <= 0:              # the reference reduces empty arrays: NaN price and error, no exception
+            res = {"price": float("nan"), "std_error": float("nan"), "num_paths_used": self.num_paths,
+                   "num_steps": steps_for(self.num_steps, T)}
+            if self.use_control_variate:
+                res.update({"bs_cv_adjustment": float("nan"), "raw_mc_price": float("nan"),
+                            "bs_ref": bs_price(float(spot), strike, T, self.params.r, self.params.q, math.sqrt(self.params.v0), is_call)})
+            return res
         if self.rng == "reference":
             return self._price_reference(spot, strike, T, is_call)
         steps = steps_for(self.num_steps, T)                                   # :287
