@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200mc.so")
+LIB_PATH = os.environ.get("B200MC_LIB") or os.path.join(_HERE, "libb200mc.so")     # B200MC_LIB: an alternative build (tuning runs)
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM = 0, 1, 2, 3, 4
 ANTITHETIC, GREEKS, FP64, FORCE_SVJ, WIDE_RNG = 0x1, 0x2, 0x4, 0x8, 0x10

@@ -27,6 +27,9 @@ constexpr int EU_THREADS = 256;
 #ifndef EU_PARK
 #define EU_PARK 1
 #endif
+#ifndef EU_MIN_BLOCKS_SV
+#define EU_MIN_BLOCKS_SV 1     // resident CTAs per SM asked of ptxas for the fp32 Heston / SVJ kernels without Greeks
+#endif
 constexpr int NACC = 16;   // doubles per strike after b200mc_sums.n
 
 struct EuroArgs {
@@ -93,7 +96,8 @@ __device__ __forceinline__ void accumulate(A (&acc)[NACC], const EuroArgs &a, R 
 // SINGLE = exactly one strike: every thread finishes its own paths, no shared-memory staging and no block barrier
 // inside the path loop.  Otherwise phase A / phase B as described at the top of the file.
 template <int MODE, bool ANTI, bool GREEKS, typename R, bool SINGLE, bool WIDE = false>
-__global__ void __launch_bounds__(EU_THREADS, (sizeof(R) == 4 && MODE <= MODE_DETVAR) ? EU_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(EU_THREADS, (sizeof(R) == 4 && MODE <= MODE_DETVAR) ? EU_MIN_BLOCKS
+                                              : ((sizeof(R) == 4 && !GREEKS && SINGLE) ? EU_MIN_BLOCKS_SV : 1))
 k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g, double *__restrict__ partials, unsigned int *counter,
            double *__restrict__ out)
 {

@@ -253,6 +253,21 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         JumpStream jmp;
         const float inv_lg2_q = (float)m.jump_inv_lg2q;
         if constexpr (MODE == MODE_SVJ) jmp.init(c0, c1, key, inv_lg2_q, m.jump_on != 0);
+        // Terminal values only (nothing records the path): the jumps add to the log spot and touch nothing else -- the
+        // variance recurrence never sees them (monte_carlo.py:229-238) -- so their total, n_J mu_J + sigma_J sum Z_i, is
+        // accumulated HERE, before the step loop, by walking the path's jump times.  Inside the step loop a jump is a
+        // divergent branch that costs the whole warp ~100 cycles for ONE lane (12 % of the warp-steps at lambda dt = 0.004:
+        // 12 of the 54 instructions per pair-step); here every lane walks its own jumps at the same time, with the refills
+        // of all lanes in the same iteration: max-over-lanes(n_J) short iterations per path instead of one divergent
+        // excursion per jump and lane.  The draws are unchanged; only the order of the additions into x differs.
+        R jump_mu = (R)0, jump_z = (R)0;
+        if constexpr (MODE == MODE_SVJ && !Rec::enabled) {
+            while (jmp.next < n_steps) {                                                 // :233-234
+                jump_z += (R)jmp.size_raw();
+                jump_mu += c.mu_j;
+                jmp.advance(c0, c1, key, inv_lg2_q, jmp.next);
+            }
+        }
         constexpr uint32_t STREAM = MODE == MODE_HESTON ? B200MC_STREAM_HESTON : B200MC_STREAM_SVJ;
         const int nblk = (n_steps + 3) >> 2;
         U4 u = philox4x32_10(c0, c1, 0u, STREAM, key);
@@ -267,7 +282,7 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                     R zs1, zsc;
                     scaled_draws<R>(ww[t], c, zs1, zsc);
                     sv_step<R, ANTI, GREEKS>(x, v, c, zs1, zsc);
-                    if constexpr (MODE == MODE_SVJ) {
+                    if constexpr (MODE == MODE_SVJ && Rec::enabled) {             // a recorded path takes its jumps in place
                         if (s == jmp.next) {                                             // :233-234, rare
                             const R jsz = c.sigma_j_s * (R)jmp.size_raw();
 #pragma unroll
@@ -282,8 +297,12 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         }
         {
             const R total_drift = (R)((double)n_steps * m.drift_dt);
+            const R jsz = c.sigma_j_s * jump_z;                                          // 0 unless SVJ terminal mode
 #pragma unroll
-            for (int k = 0; k < NS; ++k) { x[k] += total_drift; v[k] = rmax(v[k], (R)0); }
+            for (int k = 0; k < NS; ++k) {
+                x[k] += total_drift + ((ANTI && k == 1) ? jump_mu - jsz : jump_mu + jsz);
+                v[k] = rmax(v[k], (R)0);
+            }
         }
         sumz_out = (R)0;
 #pragma unroll
