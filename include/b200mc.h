@@ -22,8 +22,10 @@
  * Random numbers (fused modes): counter-based Philox4x32-10, key = (seed_lo, seed_hi),
  * counter = (path_lo, path_hi, block, stream) with `path` the GLOBAL path index (path_offset + i), so a
  * path draws the same numbers whatever the launch geometry or the number of GPUs.  Every 32-bit output word w
- * yields one Box-Muller pair BM(w) = (R cos a, R sin a):  u1 = 2 - f(w & 0x7fffff) in (0,1],  R = sqrt(-2 ln u1),
- * a = 2 pi f(w >> 9) - 3 pi,  f(m) = the float in [1,2) with mantissa m  (fp32, MUFU lg2/sqrt/sin/cos).  Streams:
+ * yields one Box-Muller pair BM(w) = (R cos a, R sin a):  u1 = 2 - f(w >> 9) in (0,1],  R = sqrt(-2 ln u1),
+ * a = 2 pi f((w * 0x9E3779B9 mod 2^32) >> 9) - 3 pi,  f(m) = the float in [1,2) with mantissa m  (fp32, MUFU
+ * lg2/sqrt/sin/cos; the angle field is the word hashed by the golden-ratio multiplier, so that (radius, angle) is a
+ * well-spread rank-1 lattice instead of two overlapping bit fields).  Streams:
  *   B200MC_STREAM_GBM    block j -> steps 8j..8j+7: word i gives the normals of steps 8j+2i and 8j+2i+1
  *   B200MC_STREAM_HESTON block j -> steps 4j..4j+3: word i gives (Z1, Z2) of step 4j+i
  *   B200MC_STREAM_SVJ    block j -> steps 4j..4j+3 like B200MC_STREAM_HESTON (the diffusion of the SVJ model)
@@ -384,6 +386,9 @@ int b200mc_normal_hist2d(b200mc_handle *h, uint64_t seed, uint64_t path_offset, 
 /* lag | B200MC_HIST_WIDE: the same counts for the validation twin (B200MC_WIDE_RNG: 2 pairs per block; lag 1 = the second
  * member of the first pair with the first member of the second). */
 #define B200MC_HIST_WIDE 0x100
+/* lag | B200MC_HIST_R01: the same counts for round 1's field layout (radius = low 23 bits, angle = top 23 bits of the word,
+ * 14 bits shared), which no pricing kernel uses any more: keeps the measurement that retired it reproducible. */
+#define B200MC_HIST_R01 0x200
 
 /* ---- device memory helpers for callers without a CUDA runtime of their own (ctypes) ---------------------- */
 int b200mc_malloc(b200mc_handle *h, size_t bytes, void **dev_ptr);

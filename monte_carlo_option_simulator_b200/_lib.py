@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("B200MC_LIB") or os.path.join(_HERE, "libb200mc.so")  
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM = 0, 1, 2, 3, 4
 ANTITHETIC, GREEKS, FP64, FORCE_SVJ, WIDE_RNG = 0x1, 0x2, 0x4, 0x8, 0x10
-HIST_WIDE = 0x100
+HIST_WIDE, HIST_R01 = 0x100, 0x200
 STREAM_GBM, STREAM_HESTON, STREAM_SVJ, STREAM_HEDGE = 0, 1, 2, 3
 Z1, Z2, ZJUMP_U, ZJUMP_SIZE = 0, 1, 2, 3
 F32, F64 = 0, 1

@@ -159,8 +159,8 @@ k_normal_hist2d(const __grid_constant__ PhiloxKey key, uint64_t path0, int64_t n
                 continue;
             }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) b[t] = box_muller_word(ww[t]);
-            if (lag == 0) {
+            for (int t = 0; t < 4; ++t) b[t] = (lag & B200MC_HIST_R01) ? box_muller_word_r01(ww[t]) : box_muller_word(ww[t]);
+            if ((lag & 1) == 0) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) atomicAdd(&hist[cell(b[t].rc) * 64 + cell(b[t].rs)], 1u);
             } else {
@@ -181,7 +181,7 @@ extern "C" int b200mc_normal_hist2d(b200mc_handle *h, uint64_t seed, uint64_t pa
                                     int lag, uint64_t out[4096])
 {
     if (!h) return fail(nullptr, B200MC_EINVAL, "handle is NULL");
-    if (!out || n_paths <= 0 || n_blocks <= 0 || (lag & ~(1 | B200MC_HIST_WIDE))) return fail(h, B200MC_EINVAL, "bad argument");
+    if (!out || n_paths <= 0 || n_blocks <= 0 || (lag & ~(1 | B200MC_HIST_WIDE | B200MC_HIST_R01))) return fail(h, B200MC_EINVAL, "bad argument");
     B200MC_CUDA(h, cudaSetDevice(h->device));
     // a CTA's shared 32-bit cells must not overflow: at most 2^31 pairs per CTA
     const int grid = h->sm_count * 8;

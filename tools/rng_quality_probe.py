@@ -29,13 +29,13 @@ def stats(c):
     return out
 
 
-print("layout      lag   pairs       chi2 z    rms cell dev   marg1 z  KS1*sqrtN  marg2 z  KS2*sqrtN")
-for name, wide in (("production", 0), ("wide twin", _lib.HIST_WIDE)):
+print("layout         lag   pairs       chi2 z    rms cell dev   marg1 z  KS1*sqrtN  marg2 z  KS2*sqrtN")
+for name, wide in (("production", 0), ("round-1 layout", _lib.HIST_R01), ("wide twin", _lib.HIST_WIDE)):
     for lag in (0, 1):
         for paths, blocks in ((250_000, 10), (2_500_000, 10), (4_000_000, 32)):
             c = h.normal_hist2d(42, paths, blocks, lag | wide).astype(np.float64)
             s = stats(c)
-            print(f"{name:11s} {lag:3d} {int(c.sum()):11d} {s[0]:10.2f} {s[1]:12.3e} {s[2]:9.2f} {s[3]:9.3f} {s[4]:9.2f} {s[5]:9.3f}", flush=True)
+            print(f"{name:14s} {lag:3d} {int(c.sum()):11d} {s[0]:10.2f} {s[1]:12.3e} {s[2]:9.2f} {s[3]:9.3f} {s[4]:9.2f} {s[5]:9.3f}", flush=True)
 
 p = SVJParams.gbm(0.30, r=0.065, q=0.0)
 for steps, T, n in ((10, 0.04, 1_000_000_000), (250, 1.0, 200_000_000)):
