@@ -321,8 +321,8 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
         // ---- chunk-local log returns of steps 32c .. 32c + 31 ----------------------------------------------------
         R xl[32];
         R x = DEG ? (R)1 : (R)0;
-        auto growth = [&](R z) {                 // DEG > 0: x <- x exp(wc z + dc), chunk-local running product
-            const R d = fmaf((float)wc, (float)z, (float)dc);
+        auto growth = [&](R radw, R trig) {      // DEG > 0: x <- x exp(wc rad trig + dc), chunk-local running product
+            const R d = fmaf((float)radw, (float)trig, (float)dc);
             R q = DEG >= 5 ? (R)(1.0 / 120.0) : (R)(1.0 / 24.0);
             if (DEG >= 5) q = fmaf(d, q, (R)(1.0 / 24.0));
             q = fmaf(d, q, (R)(1.0 / 6.0));
@@ -336,13 +336,16 @@ k_paths_tma(const __grid_constant__ PathArgs a, const double *__restrict__ wtab_
             const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const BM2 bm = box_muller_word(ww[t]);
                 if constexpr (DEG > 0) {
-                    growth((R)bm.rc);
+                    // the step weight is folded into the radius once per pair (one FMUL instead of two products)
+                    const BM3 bp = box_muller_parts(ww[t]);
+                    const R radw = (R)bp.rad * wc;
+                    growth(radw, (R)bp.cs);
                     xl[8 * b + 2 * t] = x;
-                    growth((R)bm.rs);
+                    growth(radw, (R)bp.sn);
                     xl[8 * b + 2 * t + 1] = x;
                 } else {
+                    const BM2 bm = box_muller_word(ww[t]);
                     R wa, wb, da, db;
                     if constexpr (TAB) {
                         const int s = 32 * c + 8 * b + 2 * t;
