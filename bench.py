@@ -398,14 +398,14 @@ def hbm_roofline(h, torch, rates, n_paths=4_000_000, reps=3):
     other = a["alu"] + a["fp32"] + a["xu"] + a["lsu"] + a["loop"]
     b = pipe_bounds(rates, a["imad_wide"], other, a["alu"], a["xu"])
     issue_gbs = min(b.values()) * 4.016 / 1e9
-    ncu_instr_per_value = 23.8          # smsp__inst_executed.sum * 32 / 1e9 values, profiles/r02_ncu_k_paths_tma_poly4_minb4.txt
+    ncu_instr_per_value = 23.3          # smsp__inst_executed.sum * 32 / 1e9 values, profiles/r02_ncu_k_paths_tma_poly4_minb4.txt
     sass_gbs = 4.016 / 1e9 / (a["imad_wide"] / rates["imad_wide"] + (ncu_instr_per_value - a["imad_wide"]) / rates["ffma"])
     out["f32"]["instruction_bound"] = {"algorithmic_per_path_step": a, "pipe_bounds_path_steps_per_s": b,
                                        "as_GB_per_s": issue_gbs, "frac_of_binding_roof": out["f32"]["achieved"] / min(issue_gbs, peak),
                                        "executed_instructions_per_value_ncu": ncu_instr_per_value,
                                        "executed_mix_bound_GB_per_s": sass_gbs, "frac_of_executed_mix_bound": out["f32"]["achieved"] / sass_gbs,
                                        "note": "min(HBM, issue, XU): ~24 issue slots (+3 per IMAD.WIDE) per stored float put the fp32 store "
-                                               "on the instruction-issue roof below the HBM roof (ncu: issue port 94 % occupied); the "
+                                               "on the instruction-issue roof below the HBM roof (ncu: issue port 91 % occupied); the "
                                                "float64-output variant is HBM-bound"}
     return out
 
