@@ -2,7 +2,8 @@
 
     python tools/install_reference.py [/root/reference]
 
-Copies the reference's `engine/` package (pure Python, no packaging metadata: there is nothing to pip-install) into the
+Copies the reference's `engine/` package and its `verify.py` (pure Python, no packaging metadata: there is nothing to
+pip-install) into the
 git-ignored `baseline/_ref/engine/`.  The GPU box receives only this working tree, so the copy is what lets
 `bench.py --impl reference` and the `cpu_baseline` leg time the reference ITSELF there (`cpu_baseline.kind =
 "reference"`): its Numba kernel `_simulate_svj_paths_numba` and `MonteCarloEngine.price`, imported from the copy and
@@ -27,7 +28,12 @@ def install(src_root: str = "/root/reference") -> str:
         shutil.rmtree(dst)
     os.makedirs(DST, exist_ok=True)
     shutil.copytree(src, dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "*.nbi", "*.nbc"))
-    for dp, _, fs in os.walk(dst):                       # the reference tree is read-only; the copy must be removable
+    for extra in ("verify.py",):                        # the reference's own smoke script: tools/verify_dropin.py runs it patched
+        if os.path.exists(os.path.join(src_root, extra)):
+            shutil.copy(os.path.join(src_root, extra), os.path.join(DST, extra))
+    for d in ("js", "css"):                              # engine/app.py mounts these static folders at import time; the
+        os.makedirs(os.path.join(DST, d), exist_ok=True)  # browser assets themselves are not needed (and not copied)
+    for dp, _, fs in os.walk(DST):                       # the reference tree is read-only; the copy must be removable
         os.chmod(dp, 0o755)
         for f in fs:
             os.chmod(os.path.join(dp, f), 0o644)

@@ -48,6 +48,16 @@ t0 = time.time()
 ref_default = RefEngine(svj, num_paths=50_000).price(22500.0, 22500.0, 0.25, True)
 ref_default_put = RefEngine(svj, num_paths=50_000, seed=7).price(22500.0, 23000.0, 0.08, False)
 t_ref_default = (time.time() - t0) / 2
+# the reference's PSEUDO-random configuration (NumPy PCG64 Ziggurat normals), unpatched: price, Greeks, sample paths
+t0 = time.time()
+ref_pcg = RefEngine(svj, num_paths=50_000, use_sobol=False).price(22500.0, 22500.0, 0.25, True)
+t_ref_pcg = time.time() - t0
+from engine.greeks import GreeksEngine as RefGreeks  # noqa: E402
+t0 = time.time()
+_rg = RefGreeks(svj, num_paths=50_000)
+ref_greeks = (_rg.delta(22500.0, 22500.0, 0.25, True), _rg.vega(22500.0, 22500.0, 0.25, True), _rg.gamma(22500.0, 22500.0, 0.25, True))
+t_ref_greeks = time.time() - t0
+ref_paths = RefEngine(svj, num_paths=50_000).get_sample_paths(22500.0, 0.25, 50)
 from engine.risk import StressTestEngine as RefStress  # noqa: E402
 ref_stress = RefStress(svj, num_paths=20_000).full_stress_report(22500.0, 22500.0, 0.08, True)
 
@@ -87,6 +97,28 @@ for k, v in ref_stress["jump_scenario"].items():
 print(f"[exact] default-flag price() (Sobol + antithetic + CV, 50k paths): reference {ref_default['price']:.9f} "
       f"({t_ref_default:.2f} s per call, CPU)   patched rng=reference {ours_default['price']:.9f} ({t_ours_default * 1e3:.1f} ms per call)"
       f"   every key of two price() dicts and of a full stress report equal to 1e-9 / 1e-8")
+
+# the pseudo-random configuration: NumPy's PCG64 Ziggurat normals regenerated on the device bit for bit (csrc/np_normal.cu)
+from engine.greeks import GreeksEngine  # noqa: E402
+t0 = time.time()
+ours_pcg = MonteCarloEngine(svj, num_paths=50_000, use_sobol=False, rng="reference").price(22500.0, 22500.0, 0.25, True)
+t_ours_pcg = time.time() - t0
+for k, v in ref_pcg.items():
+    assert abs(ours_pcg[k] - v) <= 1e-9 * max(1.0, abs(v)), (k, v, ours_pcg[k])
+t0 = time.time()
+_og = GreeksEngine(svj, num_paths=50_000, rng="reference")
+ours_greeks = (_og.delta(22500.0, 22500.0, 0.25, True), _og.vega(22500.0, 22500.0, 0.25, True), _og.gamma(22500.0, 22500.0, 0.25, True))
+t_ours_greeks = time.time() - t0
+for a, b in zip(ref_greeks, ours_greeks):
+    for k, v in a.items():
+        assert abs(b[k] - v) <= 1e-8 * max(1.0, abs(v)), (k, v, b[k])
+ours_paths = MonteCarloEngine(svj, num_paths=50_000, rng="reference").get_sample_paths(22500.0, 0.25, 50)
+import numpy as _np  # noqa: E402
+assert ours_paths.shape == ref_paths.shape and _np.allclose(ours_paths, ref_paths, rtol=1e-10, atol=0)
+print(f"[exact] use_sobol=False price() (PCG64 Ziggurat draws, 50k x 63): reference {ref_pcg['price']:.9f} ({t_ref_pcg:.2f} s, CPU)   "
+      f"patched rng=reference {ours_pcg['price']:.9f} ({t_ours_pcg * 1e3:.1f} ms)   every key equal to 1e-9; "
+      f"GreeksEngine delta/vega/gamma: reference {t_ref_greeks:.2f} s, patched {t_ours_greeks * 1e3:.1f} ms, every key equal to 1e-8 "
+      f"(delta {ours_greeks[0]['pathwise']:.9f} vs {ref_greeks[0]['pathwise']:.9f}); get_sample_paths 50 x {ref_paths.shape[1]} equal to 1e-10")
 
 app = engine.app
 calls = (("price", app.price_option, app.PriceRequest(spot=22500.0, strike=22500.0, T=0.08, num_paths=50_000)),
