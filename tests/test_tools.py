@@ -34,3 +34,21 @@ def test_ptxas_logs_report_no_spills_in_the_hot_kernels():
     for name, spill, regs in blocks:
         if "k_europeanILi0E" in name and "EfLb1E" in name:            # GBM, fp32, single strike: the headline family
             assert int(spill) == 0 and int(regs) <= 128, (name, spill, regs)
+
+
+def test_probe_library_is_separate_from_the_product_abi():
+    """The pipe-rate probes bench.py's rooflines divide by live in their own library (tools/probe), not in libb200mc.so:
+    it loads without a GPU, exports exactly its two entry points, and the product exports none of them."""
+    import ctypes
+    from monte_carlo_option_simulator_b200 import _lib
+    path = os.path.join(ROOT, "tools", "probe", "libb200mc_probe.so")
+    if not os.path.exists(path):
+        pytest.skip("probe library was not built in this checkout (python __graft_entry__.py build)")
+    lib = ctypes.CDLL(path)
+    assert hasattr(lib, "b200mc_probe_rate") and hasattr(lib, "b200mc_probe_mix")
+    prod = _lib.load()
+    assert not hasattr(prod, "b200mc_microbench") and not hasattr(prod, "b200mc_probe_rate")
+    assert not any("microbench" in n or "probe" in n for n in _lib.EXPORTS)
+    import ctypes as C
+    v = C.c_double()
+    assert lib.b200mc_probe_rate(0, 999, 16, C.byref(v)) == 4          # bad selector is refused before any CUDA call
