@@ -59,35 +59,8 @@ __device__ __forceinline__ void load_tile(double *tile, const double *__restrict
     }
 }
 
-// The same tile, fetched ASYNCHRONOUSLY: every lane issues its 8-byte copies global -> shared (cp.async, LDGSTS: no
-// staging registers) and returns; the warp waits for the group only when it needs the tile.  Out-of-range elements are
-// zero-filled by the copy itself (src-size 0), their address replaced by a valid one.
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-template <int TS>
-__device__ __forceinline__ void load_tile_async(double *tile, const double *__restrict__ base, const double *__restrict__ rowptr,
-                                                size_t stride_r, int s0, int rows_left, int cols_left, int lane)
-{
-    constexpr int RPI = 32 / TS, PITCH = TS + 1;
-    const int col = lane % TS, sub = lane / TS;
-    const double *p = rowptr + s0;
-#pragma unroll
-    for (int it = 0; it < TS; ++it) {
-        const int row = RPI * it + sub;
-        const bool valid = row < rows_left && col < cols_left;
-        cp_async8(&tile[row * PITCH + col], valid ? p : base, valid);
-        p += stride_r;
-    }
-}
-
-// ASYNC: two stages of tiles per warp; the copies of tile k+1 are in flight while the warp computes tile k (the kernel is
-// load-latency bound otherwise: ncu long_scoreboard 2.2, issue slots 36 % busy with 12 warps per SM).
-template <int GN_TS, bool ASYNC = false>
-__global__ void __launch_bounds__(GN_WARPS * 32, (GN_TS == 8 && !ASYNC) ? 6 : 3)
+template <int GN_TS>
+__global__ void __launch_bounds__(GN_WARPS * 32, GN_TS == 8 ? 6 : 3)
 k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ Z1, const double *__restrict__ Z2,
                 const double *__restrict__ Zj, const double *__restrict__ Zjs, double *__restrict__ S_final,
                 double *__restrict__ v_final, double *__restrict__ all_paths)
@@ -95,13 +68,11 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
     extern __shared__ __align__(16) double gn_tiles[];          // [GN_WARPS][tiles in use][32 * GN_PITCH]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int GN_PITCH = GN_TS + 1, TILE = 32 * GN_PITCH;
-    const int nin = 1 + a.need_z2 + 2 * a.need_jump;          // input tiles per stage
-    const int ntile = (ASYNC ? 2 : 1) * nin + a.record;
+    const int ntile = 1 + a.need_z2 + 2 * a.need_jump + a.record;
     double *t1 = gn_tiles + (size_t)warp * ntile * TILE;
     double *t2 = t1 + TILE;                                   // valid only when need_z2
     double *tj = t1 + (1 + a.need_z2) * TILE, *tjs = tj + TILE;   // valid only when need_jump
     double *tout = t1 + (ntile - 1) * TILE;                   // valid only when record
-    const int stage_doubles = nin * TILE;                     // ASYNC: stage 1 sits right behind stage 0
     const int64_t n_groups = (a.n_paths + 31) / 32;
     for (int64_t g = (int64_t)blockIdx.x * GN_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * GN_WARPS) {
         const int64_t path0 = g * 32, me = path0 + lane;
@@ -112,61 +83,33 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
         const int rows_left = (int)((a.n_paths - path0) < 32 ? (a.n_paths - path0) : 32);
         const size_t lane_off = (size_t)(path0 + lane / GN_TS) * a.n_steps + (lane % GN_TS),
                      stride4 = (size_t)(32 / GN_TS) * a.n_steps;
-        auto issue = [&](int s0, int stage) {                  // ASYNC: queue the copies of the tile that starts at step s0
+        for (int s0 = 0; s0 < a.n_steps; s0 += GN_TS) {
             const int cols_left = a.n_steps - s0;
-            double *b = t1 + stage * stage_doubles;
-            load_tile_async<GN_TS>(b, Z1, Z1 + lane_off, stride4, s0, rows_left, cols_left, lane);
-            if (a.need_z2) load_tile_async<GN_TS>(b + TILE, Z2, Z2 + lane_off, stride4, s0, rows_left, cols_left, lane);
+            const bool full = rows_left == 32 && cols_left >= GN_TS;
+            __syncwarp();
+            load_tile<GN_TS>(t1, Z1 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+            if (a.need_z2) load_tile<GN_TS>(t2, Z2 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
             if (a.need_jump) {
-                load_tile_async<GN_TS>(b + (1 + a.need_z2) * TILE, Zj, Zj + lane_off, stride4, s0, rows_left, cols_left, lane);
-                load_tile_async<GN_TS>(b + (2 + a.need_z2) * TILE, Zjs, Zjs + lane_off, stride4, s0, rows_left, cols_left, lane);
+                load_tile<GN_TS>(tj, Zj + lane_off, stride4, s0, full, rows_left, cols_left, lane);
+                load_tile<GN_TS>(tjs, Zjs + lane_off, stride4, s0, full, rows_left, cols_left, lane);
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        if constexpr (ASYNC) {
-            __syncwarp();                                      // the previous group's last tile has been consumed
-            issue(0, 0);
-        }
-        for (int s0 = 0, kt = 0; s0 < a.n_steps; s0 += GN_TS, ++kt) {
-            const int cols_left = a.n_steps - s0;
-            const double *c1 = t1, *c2 = t2, *cj = tj, *cjs = tjs;
-            if constexpr (ASYNC) {
-                if (s0 + GN_TS < a.n_steps) {
-                    issue(s0 + GN_TS, (kt + 1) & 1);
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                } else {
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                }
-                __syncwarp();
-                const int off = (kt & 1) * stage_doubles;
-                c1 = t1 + off; c2 = t2 + off; cj = tj + off; cjs = tjs + off;
-            } else {
-                const bool full = rows_left == 32 && cols_left >= GN_TS;
-                __syncwarp();
-                load_tile<GN_TS>(t1, Z1 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
-                if (a.need_z2) load_tile<GN_TS>(t2, Z2 + lane_off, stride4, s0, full, rows_left, cols_left, lane);
-                if (a.need_jump) {
-                    load_tile<GN_TS>(tj, Zj + lane_off, stride4, s0, full, rows_left, cols_left, lane);
-                    load_tile<GN_TS>(tjs, Zjs + lane_off, stride4, s0, full, rows_left, cols_left, lane);
-                }
-                __syncwarp();
-            }
+            __syncwarp();
             const int ns = min(GN_TS, a.n_steps - s0);
             for (int t = 0; t < ns; ++t) {
-                const double z1 = __dmul_rn(a.zsign, c1[lane * GN_PITCH + t]);
+                const double z1 = __dmul_rn(a.zsign, t1[lane * GN_PITCH + t]);
                 const double v_pos = fmax(v, 0.0);                               // :223
                 const double sqrt_v = sqrt(v_pos);                               // :224
                 const double dW1 = __dmul_rn(z1, a.sqrt_dt);                     // :226
                 double dW2 = 0.0;                                                // :227 (unused when xi == 0)
                 if (a.need_z2)
                     dW2 = __dadd_rn(__dmul_rn(__dmul_rn(a.rho, z1), a.sqrt_dt),
-                                    __dmul_rn(__dmul_rn(a.sq1mr2, __dmul_rn(a.zsign, c2[lane * GN_PITCH + t])), a.sqrt_dt));
+                                    __dmul_rn(__dmul_rn(a.sq1mr2, __dmul_rn(a.zsign, t2[lane * GN_PITCH + t])), a.sqrt_dt));
                 const double log_drift = __dmul_rn(__dadd_rn(a.drift_comp, -__dmul_rn(0.5, v_pos)), a.dt);   // :229
                 const double log_diff = __dmul_rn(sqrt_v, dW1);                  // :230
                 double jump = 0.0;                                               // :232
                 if (a.need_jump) {
-                    if (cj[lane * GN_PITCH + t] < a.jump_thr)                    // :233
-                        jump = __dadd_rn(a.mu_j, __dmul_rn(a.sigma_j, __dmul_rn(a.zsign, cjs[lane * GN_PITCH + t])));   // :234
+                    if (tj[lane * GN_PITCH + t] < a.jump_thr)                    // :233
+                        jump = __dadd_rn(a.mu_j, __dmul_rn(a.sigma_j, __dmul_rn(a.zsign, tjs[lane * GN_PITCH + t])));   // :234
                 }
                 S = __dmul_rn(S, exp(__dadd_rn(__dadd_rn(log_drift, log_diff), jump)));              // :236
                 const double mr = __dmul_rn(__dmul_rn(a.kappa, __dadd_rn(a.theta, -v_pos)), a.dt);
@@ -284,9 +227,6 @@ static GivenArgs make_args(const b200mc_svj_params *p, double S0, double T, int6
     return a;
 }
 
-#ifndef B200MC_GN_DEFAULT_ASYNC
-#define B200MC_GN_DEFAULT_ASYNC 0
-#endif
 static int launch_given(b200mc_handle *h, const GivenArgs &a, const double *Z1, const double *Z2, const double *Zj,
                         const double *Zjs, double *S_final, double *v_final, double *all_paths)
 {
@@ -295,20 +235,15 @@ static int launch_given(b200mc_handle *h, const GivenArgs &a, const double *Z1, 
     int64_t grid = (groups + GN_WARPS - 1) / GN_WARPS;
     const int64_t cap = (int64_t)h->sm_count * 16;
     if (grid > cap) grid = cap;
-    const int nin = 1 + a.need_z2 + 2 * a.need_jump;
+    const int ntile = 1 + a.need_z2 + 2 * a.need_jump + a.record;
     // 8-step tiles (64-byte row segments, 2.3 KB of shared memory per warp and array => more resident warps) unless the
     // run is memory heavy (jump arrays in use: 32 B per path-step) AND the rows are not 64-byte multiples: then 128-byte
     // segments waste fewer sectors (measured, 1M x 250 SVJ: 2.0 -> 2.5 TB/s; 4M x 64: 3.4 vs 2.9 TB/s the other way)
     const char *force = getenv("B200MC_GN_TILE");
     const bool wide = force ? atoi(force) == 16 : (a.need_jump != 0 && (a.n_steps % 8) != 0);
     const int ts = wide ? 16 : 8;
-    // B200MC_GN_ASYNC=1: two cp.async stages of input tiles per warp (A/B switch)
-    const char *as = getenv("B200MC_GN_ASYNC");
-    const bool async = as ? atoi(as) != 0 : B200MC_GN_DEFAULT_ASYNC;
-    const int ntile = (async ? 2 : 1) * nin + a.record;
     const size_t smem = (size_t)GN_WARPS * ntile * 32 * (ts + 1) * sizeof(double);
-    auto kern = async ? (wide ? k_given_normals<16, true> : k_given_normals<8, true>)
-                      : (wide ? k_given_normals<16, false> : k_given_normals<8, false>);
+    auto kern = wide ? k_given_normals<16> : k_given_normals<8>;
     B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, GN_WARPS * 32, smem, h->stream>>>(a, Z1, Z2, Zj, Zjs, S_final, v_final, all_paths);
     B200MC_CUDA(h, cudaGetLastError());
