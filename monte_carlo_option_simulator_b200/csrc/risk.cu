@@ -202,17 +202,35 @@ __device__ __forceinline__ void rf_vote(unsigned int *h, unsigned int digit)
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[digit], (unsigned int)__popc(peers));
 }
 
-// grid-stride loop with four independent loads in flight per thread (the passes are latency bound otherwise: one
-// 8-byte load per thread and iteration keeps ~1 MB in flight on the whole device)
+// grid-stride loop over x[0, n) with four independent 16-byte loads in flight per thread (the passes are latency bound
+// otherwise: one 8-byte load per thread and iteration keeps ~1 MB in flight on the whole device, four keep 3.5-4 TB/s,
+// four 16-byte ones 64 B per thread = 9.7 MB; requesting the next four before the current ones are consumed was measured
+// and changes nothing, profiles/r02_risk_vec_probe.txt).  Elements before the first 16-byte boundary and after the last full
+// vector are visited one by one.  The visiting ORDER of a thread is fixed by (n, alignment, grid) only, so the fp64 tail
+// sums stay reproducible run to run.
+template <typename T> struct RfVec;
+template <> struct RfVec<double> { using V = double2; static constexpr int N = 2; };
+template <> struct RfVec<float> { using V = float4; static constexpr int N = 4; };
+template <typename F> __device__ __forceinline__ void rf_each(const double2 &v, F &body) { body(v.x); body(v.y); }
+template <typename F> __device__ __forceinline__ void rf_each(const float4 &v, F &body) { body(v.x); body(v.y); body(v.z); body(v.w); }
+
 template <typename T, typename F>
 __device__ __forceinline__ void rf_foreach(const T *__restrict__ x, long long n, long long i0, long long stride, F body)
 {
+    using V = typename RfVec<T>::V;
+    constexpr int NV = RfVec<T>::N;
+    long long head = (long long)(((16u - (unsigned)((uintptr_t)x & 15u)) & 15u) / sizeof(T));
+    if (head > n) head = n;
+    const long long nvec = (n - head) / NV;
+    const V *__restrict__ xv = reinterpret_cast<const V *>(x + head);
     long long i = i0;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        const T a = x[i], b = x[i + stride], c = x[i + 2 * stride], d = x[i + 3 * stride];
-        body(a); body(b); body(c); body(d);
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const V a = xv[i], b = xv[i + stride], c = xv[i + 2 * stride], d = xv[i + 3 * stride];
+        rf_each(a, body); rf_each(b, body); rf_each(c, body); rf_each(d, body);
     }
-    for (; i < n; i += stride) body(x[i]);
+    for (; i < nvec; i += stride) { const V a = xv[i]; rf_each(a, body); }
+    for (long long j = i0; j < head; j += stride) body(x[j]);
+    for (long long j = head + nvec * NV + i0; j < n; j += stride) body(x[j]);
 }
 
 // deterministic sum of v over the CTA's threads -> every thread gets it

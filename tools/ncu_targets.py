@@ -1,6 +1,6 @@
 """One launch (after one warm-up launch) of every kernel this round's profiles/ summaries cover; run under
 `ncu --set full -k regex:<name> -c <count>` (see tools/gpu_call1.sh).  python tools/ncu_targets.py [target ...]
-Targets: gbm32 gbm64 heston svj paths32 paths64 given risk numpy hedge qmc."""
+Targets: gbm32 gbm64 heston svj paths32 paths64 given risk risk40m numpy hedge qmc."""
 import ctypes as C
 import os
 import sys
@@ -56,8 +56,8 @@ if "given" in want:
                                                         0, C.c_void_p(S.data_ptr()), C.c_void_p(V.data_ptr()), None))
     h.synchronize()
     del d
-if "risk" in want:
-    n = 4_000_000
+if "risk" in want or "risk40m" in want:
+    n = 40_000_000 if "risk40m" in want else 4_000_000
     x = torch.from_numpy(np.random.default_rng(0).standard_t(4, size=n) * 0.01).cuda()
     for r in range(REPS):
         h.risk_metrics(x.data_ptr(), 0.99, n=n, dtype=np.float64)
