@@ -788,6 +788,28 @@ def test_risk_metrics_random(H, case):
             assert v == pytest.approx(w, rel=1e-9, abs=1e-12), (k, n, kind)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_risk_metrics_device_vectors_at_any_alignment(H, dtype):
+    """The passes read 16 bytes per load: a device vector that starts off a 16-byte boundary (a view into a path matrix, a
+    shard) or is shorter than one vector takes the peeled head / tail loops -- same metrics as the oracle either way."""
+    g = np.random.default_rng(77)
+    host = (g.standard_t(4, size=200_003) * 0.01).astype(dtype)
+    item = np.dtype(dtype).itemsize
+    buf = H.malloc(host.nbytes)
+    try:
+        H.h2d(buf, host)
+        for off, n in ((0, 200_003), (1, 200_000), (2, 199_999), (3, 65_537), (1, 1), (1, 2), (3, 5), (0, 3), (1, 31), (2, 4097)):
+            got = H.risk_metrics(buf + off * item, 0.99, n=n, dtype=dtype)
+            want = O.risk_metrics(host[off:off + n].astype(np.float64), 0.99)
+            for k, v in zip(("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std"), got):
+                if math.isnan(want[k]):
+                    assert math.isnan(v), (off, n, k)
+                else:
+                    assert v == pytest.approx(want[k], rel=1e-9, abs=1e-12), (off, n, k)
+    finally:
+        H.free(buf)
+
+
 def test_risk_metrics_edge_cases(H, L):
     from monte_carlo_option_simulator_b200 import compute_risk_metrics
     with pytest.raises(IndexError):

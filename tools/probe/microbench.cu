@@ -15,7 +15,8 @@
 namespace b200mc {
 
 enum { MB_FFMA = 0, MB_IMAD_WIDE = 1, MB_LOP3 = 2, MB_MUFU_EX2 = 3, MB_MUFU_SIN = 4, MB_IADD3 = 5, MB_PHILOX = 6,
-       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_FFMA2 = 15, MB_F2F = 16, MB_DADD = 17, MB_COUNT = 18 };
+       MB_PHILOX_BM = 7, MB_FMUL = 8, MB_MUFU_LG2 = 9, MB_MUFU_SQRT = 10, MB_MIX_FFMA_LOP3 = 11, MB_IMAD_LO = 12, MB_IMAD_HI = 13, MB_IMAD_LOHI = 14, MB_FFMA2 = 15, MB_F2F = 16, MB_DADD = 17,
+       MB_MIX_FFMA2_LOP3 = 18, MB_MIX_FFMA2_MUFU = 19, MB_MIX_FFMA2_WIDE = 20, MB_MIX_FFMA2_FFMA = 21, MB_COUNT = 22 };
 
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, const __grid_constant__ PhiloxKey key,
@@ -52,6 +53,36 @@ __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, co
 #pragma unroll
         for (int k = 0; k < 8; ++k) s ^= a[k];
         if (s == 0x12345ull) sink[0] = t;
+    } else if constexpr (WHICH >= MB_MIX_FFMA2_LOP3 && WHICH <= MB_MIX_FFMA2_FFMA) {
+        // does a packed FFMA2 hold the ISSUE port for its two FMA-pipe cycles, or only the pipe?  Four independent chains
+        // of (FFMA2, partner) with the partner on another pipe: LOP3 (ALU), MUFU.EX2 (XU), IMAD.WIDE (heavy) or a plain
+        // FFMA (same pipe, the control).  Counted as PAIRS.
+        unsigned long long a[4];
+        uint32_t u[4];
+        float f[4];
+        unsigned long long wd[4];
+        const unsigned long long b = 0x3f8000013f800001ull + (seed & 1), c = 0x3380000033800000ull;
+        const float fb = __uint_as_float(0x3f800001u + (seed & 1)), fc = __uint_as_float(0x33800000u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = ((unsigned long long)__float_as_uint((float)(t + k)) << 32) | __float_as_uint((float)(t + k + 1));
+            u[k] = t * 4u + k; f[k] = 1.0f + (float)((t + k) & 7) * 0.125f; wd[k] = t + k;
+        }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[k]) : "l"(b), "l"(c));
+                if constexpr (WHICH == MB_MIX_FFMA2_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[k]) : "r"(seed + i), "r"(~seed));
+                else if constexpr (WHICH == MB_MIX_FFMA2_MUFU) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[k]));
+                else if constexpr (WHICH == MB_MIX_FFMA2_WIDE) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(wd[k]) : "r"((uint32_t)(wd[k] >> 32) + (uint32_t)wd[k]), "r"(0xD2511F53u));
+                else asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[k]) : "f"(fb), "f"(fc));
+            }
+        }
+        unsigned long long s = 0;
+        float fs = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s ^= a[k] ^ u[k] ^ wd[k]; fs += f[k]; }
+        if (s == 0x12345ull && fs == 1.5f) sink[0] = t;
     } else if constexpr (WHICH == MB_F2F) {
         // fp32 <-> fp64 conversions (the fp64 path state consumes fp32 draws): one widening + one narrowing per
         // link of the chain, counted as TWO conversions
@@ -189,15 +220,21 @@ __global__ void __launch_bounds__(256) k_microbench(int iters, uint32_t seed, co
 
 // Mixed probe: per iteration NW IMAD.WIDE + NL LOP3 + NM MUFU + NF FFMA over independent chains -- shows which pipes
 // overlap and which share a dispatch port (the fused kernel's hot loop is such a mix).
-template <int NW, int NL, int NM, int NF>
+// PACK: the NF FMAs are issued as NF/2 packed FFMA2 (fma.rn.f32x2) -- the same arithmetic in half the instructions.
+template <int NW, int NL, int NM, int NF, bool PACK = false>
 __global__ void __launch_bounds__(256) k_mix(int iters, uint32_t seed, uint32_t *sink)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t w[8], l[8];
     float m[8], f[8];
+    unsigned long long pf[8];
     const float b = __uint_as_float(0x3f800001u + (seed & 1)), c = __uint_as_float(0x33800000u);
+    const unsigned long long pb = 0x3f8000013f800001ull + (seed & 1), pc = 0x3380000033800000ull;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { w[k] = t * 8u + k + seed; l[k] = t + k; m[k] = 0.5f + 1e-3f * (float)((t + k) & 255); f[k] = (float)(t + k); }
+    for (int k = 0; k < 8; ++k) {
+        w[k] = t * 8u + k + seed; l[k] = t + k; m[k] = 0.5f + 1e-3f * (float)((t + k) & 255); f[k] = (float)(t + k);
+        pf[k] = ((unsigned long long)__float_as_uint((float)(t + k)) << 32) | __float_as_uint((float)(t + k + 1));
+    }
     for (int i = 0; i < iters; ++i) {
         constexpr int NMAX = NW > NL ? (NW > NM ? (NW > NF ? NW : NF) : (NM > NF ? NM : NF)) : (NL > NM ? (NL > NF ? NL : NF) : (NM > NF ? NM : NF));
 #pragma unroll
@@ -205,13 +242,14 @@ __global__ void __launch_bounds__(256) k_mix(int iters, uint32_t seed, uint32_t 
             if (k < NW) { uint64_t p; asm volatile("mul.wide.u32 %0, %1, 0xD2511F53;" : "=l"(p) : "r"(w[k & 7])); w[k & 7] = (uint32_t)(p >> 32); }
             if (k < NL) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(l[k & 7]) : "r"(seed + i), "r"(~seed));
             if (k < NM) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(m[k & 7]));
-            if (k < NF) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[k & 7]) : "f"(b), "f"(c));
+            if constexpr (PACK) { if (k < NF / 2) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(pf[k & 7]) : "l"(pb), "l"(pc)); }
+            else if (k < NF) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[k & 7]) : "f"(b), "f"(c));
         }
     }
     float s = 0.f;
     uint32_t x = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s += m[k] + f[k]; x ^= w[k] ^ l[k]; }
+    for (int k = 0; k < 8; ++k) { s += m[k] + f[k]; x ^= w[k] ^ l[k] ^ (uint32_t)pf[k] ^ (uint32_t)(pf[k] >> 32); }
     if (s == 123.456f && x == 77u) sink[0] = t;
 }
 
@@ -265,6 +303,7 @@ extern "C" int b200mc_probe_mix(int device, int combo, int iters, double *iters_
     for (int rep = 0; rep < 4; ++rep) {
         PROBE_CUDA(cudaEventRecord(h->ev0, h->stream));
 #define MIXCASE(id, a, b, c, d) case id: k_mix<a, b, c, d><<<grid, 256, 0, h->stream>>>(iters, rep, sink); counts[0] = a; counts[1] = b; counts[2] = c; counts[3] = d; break;
+#define MIXPACK(id, a, b, c, d) case id: k_mix<a, b, c, d, true><<<grid, 256, 0, h->stream>>>(iters, rep, sink); counts[0] = a; counts[1] = b; counts[2] = c; counts[3] = d; break;
         switch (combo) {
         MIXCASE(0, 8, 0, 0, 0)
         MIXCASE(1, 0, 8, 0, 0)
@@ -283,9 +322,17 @@ extern "C" int b200mc_probe_mix(int device, int combo, int iters, double *iters_
         MIXCASE(14, 8, 16, 4, 8)
         MIXCASE(15, 0, 16, 0, 16)
         MIXCASE(16, 4, 8, 4, 4)
+        // the fused kernels' mixes with plain and with packed FMAs (counts[3] stays the number of FMAs)
+        MIXCASE(17, 8, 12, 4, 8)
+        MIXPACK(18, 8, 12, 4, 8)
+        MIXCASE(19, 4, 9, 6, 16)
+        MIXPACK(20, 4, 9, 6, 16)
+        MIXCASE(21, 2, 4, 2, 10)
+        MIXPACK(22, 2, 4, 2, 10)
         default: return 4;
         }
 #undef MIXCASE
+#undef MIXPACK
         PROBE_CUDA(cudaGetLastError());
         PROBE_CUDA(cudaEventRecord(h->ev1, h->stream));
         PROBE_CUDA(cudaEventSynchronize(h->ev1));
@@ -299,7 +346,8 @@ extern "C" int b200mc_probe_mix(int device, int combo, int iters, double *iters_
 
 // which: 0 FFMA, 1 IMAD.WIDE.U32, 2 LOP3, 3 MUFU.EX2, 4 MUFU.SIN, 5 IADD, 6 Philox4x32-10 calls, 7 Philox + 4 Box-Muller
 // pairs = 8 normals (counted as calls), 8 FMUL, 9 MUFU.LG2, 10 MUFU.SQRT, 11 FFMA+LOP3 interleaved (counted as pairs),
-// 12-14 IMAD lo / hi / lo+hi, 15 FFMA2, 16 fp32<->fp64 conversions, 17 DADD.
+// 12-14 IMAD lo / hi / lo+hi, 15 FFMA2, 16 fp32<->fp64 conversions, 17 DADD, 18-21 FFMA2 paired with LOP3 / MUFU.EX2 /
+// IMAD.WIDE / FFMA (counted as pairs).
 // *ops_per_s = thread-level operations per second over the whole device (kernel time by CUDA events, best of 3).
 extern "C" int b200mc_probe_rate(int device, int which, int iters, double *ops_per_s)
 {
@@ -330,7 +378,11 @@ extern "C" int b200mc_probe_rate(int device, int which, int iters, double *ops_p
         case 14: mb_launch<14>(grid, iters, rep, key, h->sink, h->stream); break;
         case 15: mb_launch<15>(grid, iters, rep, key, h->sink, h->stream); break;
         case 16: mb_launch<16>(grid, iters, rep, key, h->sink, h->stream); break;
-        default: mb_launch<17>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 17: mb_launch<17>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 18: mb_launch<18>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 19: mb_launch<19>(grid, iters, rep, key, h->sink, h->stream); break;
+        case 20: mb_launch<20>(grid, iters, rep, key, h->sink, h->stream); break;
+        default: mb_launch<21>(grid, iters, rep, key, h->sink, h->stream); break;
         }
         PROBE_CUDA(cudaGetLastError());
         PROBE_CUDA(cudaEventRecord(h->ev1, h->stream));
@@ -340,7 +392,7 @@ extern "C" int b200mc_probe_rate(int device, int which, int iters, double *ops_p
         if (rep > 0 && ms < best) best = ms;
     }
     const double per_thread = (which == MB_PHILOX || which == MB_PHILOX_BM) ? (double)iters
-                            : (which == MB_MIX_FFMA_LOP3 ? 4.0 * iters : (which == MB_F2F ? 16.0 * iters : 8.0 * iters));
+                            : ((which == MB_MIX_FFMA_LOP3 || which >= MB_MIX_FFMA2_LOP3) ? 4.0 * iters : (which == MB_F2F ? 16.0 * iters : 8.0 * iters));
     *ops_per_s = (double)grid * 256.0 * per_thread / ((double)best * 1e-3);
     return 0;
 }

@@ -10,7 +10,7 @@ _lib = None
 
 # selector -> what one "operation" is (tools/probe/microbench.cu)
 FFMA, IMAD_WIDE, LOP3, MUFU_EX2, MUFU_SIN, IADD3, PHILOX, PHILOX_BM, FMUL, MUFU_LG2, MUFU_SQRT, FFMA_LOP3, IMAD_LO, IMAD_HI, \
-    IMAD_LOHI, FFMA2, F2F, DADD = range(18)
+    IMAD_LOHI, FFMA2, F2F, DADD, FFMA2_LOP3, FFMA2_MUFU, FFMA2_WIDE, FFMA2_FFMA = range(22)
 
 
 def load():
