@@ -261,7 +261,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "sample": f"{arm.n} paths x {N_STEPS} steps per step (BASELINE cfg1 size)"},
             "cpu_baseline": cpu_baseline_block(arm, v, dt, steps, readings),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ roofline
@@ -574,10 +574,12 @@ def run_b200(args):
 
         # ---- BASELINE cfg5: STRONG scaling -- one pricing call of n_total paths split over the ranks by shard_range ----
         cfg5 = {}
-        for n_total in (100_000_000, 1_000_000_000):
+        for n_total in (100_000_000, 1_000_000_000, 10_000_000_000):
+            big = n_total > 1_000_000_000                  # 1e10 paths: 1.4 s per call on one GPU -- one timed repetition
             lo, hi = shard_range(n_total, rank, world)
-            step(0, 0, hi - lo, lo)
-            ms_n = device_ms(lambda r: step(7 + r, 0, hi - lo, lo), reps=3)
+            if not big:
+                step(0, 0, hi - lo, lo)
+            ms_n = device_ms(lambda r: step(7 + r, 0, hi - lo, lo), reps=1 if big else 3)
             sums5 = out.cpu().numpy()
             entry = {"n_total": n_total, "ms": ms_n, "path_steps_per_s": n_total * N_STEPS / (ms_n * 1e-3),
                      "paths_this_rank": hi - lo, "n_accumulated": float(sums5[0]),
@@ -588,13 +590,15 @@ def run_b200(args):
 
                 def single(r, loc=loc, n_total=n_total):
                     h.price_european(p, SPOT, T, N_STEPS, n_total, 7 + r, [STRIKE], True, 0, None, path_offset=0, out_dev=loc.data_ptr())
-                single(0)
-                ms_1 = device_ms(single, reps=2)
+                if not big:
+                    single(0)
+                ms_1 = device_ms(single, reps=1 if big else 2)
                 entry.update({"single_gpu_ms_same_run": ms_1, "efficiency": ms_1 / (world * ms_n),
                               "overhead_ms_vs_ideal": ms_n - ms_1 / world})
             eng5 = MonteCarloEngine(p, n_total, N_STEPS, 42, use_sobol=False, use_antithetic=False, use_control_variate=False,
                                     rng="philox", handle=h, comm=comm)
-            eng5.price(SPOT, STRIKE, T, True)
+            if not big:
+                eng5.price(SPOT, STRIKE, T, True)
             barrier()
             t0 = time.perf_counter()
             r5 = eng5.price(SPOT, STRIKE, T, True)
@@ -603,7 +607,7 @@ def run_b200(args):
             entry["api_price"] = r5["price"]
             cfg5[f"{n_total:.0e}".replace("+0", "").replace("+", "")] = entry
         line["cfg5_strong_scaling"] = {"what": "one European call priced with n_total paths x 250 steps, global path range split "
-                                               "contiguously over the ranks, one exchange of 17 sums; CUDA events, max over ranks, best of 3",
+                                               "contiguously over the ranks, one exchange of 17 sums; CUDA events, max over ranks, best of 3 (1e10: one repetition)",
                                        "runs": cfg5}
 
         # ---- BASELINE cfg4: 4M x 251 path store SHARDED over the ranks (no exchange) + VaR / CVaR over the shards -------
@@ -801,14 +805,32 @@ def run_b200(args):
                 line["cpu_baseline"] = cpu_baseline_block(arm, arm.n * N_STEPS / dtc, dtc, 1, arm.readings(3))
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     h.close()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE line of stdout.  main() points file descriptor 1 at stderr for the rest of the run, so that nothing a
+    library prints from C (NCCL's version banner on its first collective, Numba / OpenMP notices) can land in front of it."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100, help="timed steps (100 x 1.4 ms: the clock samples fall inside the region)")
