@@ -12,6 +12,12 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def cases(n: int):
+    """Seeds of a randomised test: range(n), or range(n * B200MC_SOAK) for a soak run on the GPU box
+    (`B200MC_SOAK=20 python -m pytest tests -m gpu -k random`; profiles/r02_soak.txt)."""
+    return range(n * max(1, int(os.environ.get("B200MC_SOAK", "1"))))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
     # The CUDA library is a build artefact (git-ignored).  A fresh checkout has none: build it once (nvcc cross-compiles

@@ -7,6 +7,8 @@ price residual instead."""
 import numpy as np
 import pytest
 
+from conftest import cases
+
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -73,7 +75,7 @@ def test_scalar_implied_vol_and_bounds(H, iv_golden):
     assert H.implied_vol(np.zeros((0, 3)), S, np.zeros(3), 0.25, r, q).shape == (0, 3)
 
 
-@pytest.mark.parametrize("case", range(4))
+@pytest.mark.parametrize("case", cases(4))
 def test_random_chains_vs_oracle(H, case):
     g = np.random.default_rng(900 + case)
     S, r, q = float(g.uniform(50, 30000)), float(g.uniform(0, 0.1)), float(g.uniform(0, 0.05))

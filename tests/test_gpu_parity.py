@@ -11,7 +11,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import unnan
+from conftest import unnan, cases
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -178,7 +178,7 @@ def test_fused_terminal_identical_draws(H, L, golden, mode, steps):
     np.testing.assert_allclose(V32, vo, rtol=2e-3, atol=2e-6)   # variance near the zero boundary amplifies fp32 rounding
 
 
-@pytest.mark.parametrize("case", range(24))
+@pytest.mark.parametrize("case", cases(24))
 def test_fused_random_configurations(H, L, case):
     """Randomised deterministic-mode parity: random SVJ parameters (every mode), shapes, offsets (also across the
     2^32 path-index carry), flags; terminal values, variance, sums and the path matrix against the oracle fed the
@@ -395,7 +395,7 @@ def test_strike_count_sequence_regression(H, L, golden):
         assert rows.shape == (nk, L.NSUMS) and np.all(rows[:, 0] == 700)
 
 
-@pytest.mark.parametrize("case", range(12))
+@pytest.mark.parametrize("case", cases(12))
 def test_greek_sums_random_configurations(H, L, case):
     """Randomised parameters / bumps / strike counts: every bump accumulator of the fused launch against oracle
     re-simulation on the identical draws (the reference's CRN construction), antithetic on or off."""
@@ -758,7 +758,7 @@ def test_risk_metrics_large_and_fp32(H):
     assert got32[0] == pytest.approx(want32["var"], rel=1e-12) and got32[1] == pytest.approx(want32["cvar"], rel=1e-9)
 
 
-@pytest.mark.parametrize("case", range(16))
+@pytest.mark.parametrize("case", cases(16))
 def test_risk_metrics_random(H, case):
     """Randomised: sizes from 1 to 3e5, heavy tails, heavy ties, few or no losses, float32 input, several confidence
     levels -- device radix select against the oracle's sort (engine/risk.py:117-173 conventions)."""

@@ -4,6 +4,8 @@ far below plain Monte Carlo's at equal path counts."""
 import numpy as np
 import pytest
 
+from conftest import cases
+
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -187,7 +189,7 @@ def _sobol_model(tables, n, off):
     return out
 
 
-@pytest.mark.parametrize("case", range(12))
+@pytest.mark.parametrize("case", cases(12))
 def test_device_draws_random_shapes(H, L, case):
     """Random step counts (the bridge over non-powers of two, tiles of 32 / 16 / 8 / fewer paths), path counts and offsets
     deep into the sequence: bridged normals, plain normals and uniforms against the textbook bridge over the points of the
