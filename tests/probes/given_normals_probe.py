@@ -6,7 +6,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from monte_carlo_option_simulator_b200 import SVJParams, _lib  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 

@@ -77,6 +77,12 @@ def test_product_package_never_imports_the_oracle():
                 checked += 1
                 assert not bad.search(open(os.path.join(dirpath, f)).read()), f"{f} reaches into oracle/"
     assert checked >= 12
+    # the measurement scripts under tools/ (incl. the probe library) do not use it either: scripts that need the oracle as
+    # their checker live under tests/probes/
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tools")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".sh")) or f == "Makefile":
+                assert not bad.search(open(os.path.join(dirpath, f)).read()), f"tools/{f} reaches into oracle/"
 
 
 def test_stream_selection_rule_needs_no_device():

@@ -1,5 +1,5 @@
 """Tail-metric kernel after the move to 16-byte loads: ms per call for 1 / 2 CTAs per SM, float32 / float64, aligned and
-misaligned vectors, each checked against the oracle's restatement of engine/risk.py:117-173."""
+misaligned vectors (parity of exactly these cases: tests/test_gpu_parity.py::test_risk_metrics_device_vectors_at_any_alignment)."""
 import os
 import sys
 import subprocess
@@ -10,7 +10,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from monte_carlo_option_simulator_b200 import _lib  # noqa: E402
-from oracle import oracle  # noqa: E402  (checker only)
 
 if len(sys.argv) > 1:                                   # child: one configuration (the env knob is read per call)
     h = _lib.Handle(0)
@@ -30,12 +29,7 @@ if len(sys.argv) > 1:                                   # child: one configurati
                     e1.record(); torch.cuda.synchronize()
                     best = min(best, e0.elapsed_time(e1))
                 line = f"CTAs/SM={os.environ.get('B200MC_RISK_CTAS')} n={n} {np.dtype(dt).name} offset {off}: {best:.3f} ms"
-                if off in (0, 1) and n == 4_000_000:
-                    w = oracle.risk_metrics(host[off:off + n].astype(np.float64), 0.99)
-                    want = [w[k] for k in ("var", "cvar", "skewness", "kurtosis", "excess_kurtosis", "tail_index", "mean", "std")]
-                    err = max(abs(g - w) / max(abs(w), 1e-300) for g, w in zip(got, want))
-                    line += f"  max rel deviation from the oracle {err:.1e}"
-                    assert err < 1e-9, (got, want)
+                line += f"  VaR {got[0]:.9f} CVaR {got[1]:.9f}"
                 print(line, flush=True)
     h.close()
 else:
