@@ -59,8 +59,16 @@ __device__ __forceinline__ void load_tile(double *tile, const double *__restrict
     }
 }
 
-template <int GN_TS>
-__global__ void __launch_bounds__(GN_WARPS * 32, GN_TS == 8 ? 6 : 3)
+// ILP: a full tile is walked in three unrolled sweeps -- the variance recurrence and the exponent of every step (the
+// only chain that runs from step to step besides one multiply), then the GN_TS exponentials (independent of each other:
+// the fp64 pipe sees GN_TS chains per lane instead of one), then the running product.  The same separately rounded
+// operations per path in the same order as the step-by-step loop, which partial tiles still take: results are bitwise
+// the same.
+#ifndef GN_ILP_MINB8
+#define GN_ILP_MINB8 6
+#endif
+template <int GN_TS, bool ILP>
+__global__ void __launch_bounds__(GN_WARPS * 32, GN_TS == 8 ? (ILP ? GN_ILP_MINB8 : 6) : 3)
 k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ Z1, const double *__restrict__ Z2,
                 const double *__restrict__ Zj, const double *__restrict__ Zjs, double *__restrict__ S_final,
                 double *__restrict__ v_final, double *__restrict__ all_paths)
@@ -95,6 +103,38 @@ k_given_normals(const __grid_constant__ GivenArgs a, const double *__restrict__ 
             }
             __syncwarp();
             const int ns = min(GN_TS, a.n_steps - s0);
+            if (ILP && ns == GN_TS) {
+                double e[GN_TS];
+#pragma unroll
+                for (int t = 0; t < GN_TS; ++t) {
+                    const double z1 = __dmul_rn(a.zsign, t1[lane * GN_PITCH + t]);
+                    const double v_pos = fmax(v, 0.0);                           // :223
+                    const double sqrt_v = sqrt(v_pos);                           // :224
+                    const double dW1 = __dmul_rn(z1, a.sqrt_dt);                 // :226
+                    double dW2 = 0.0;                                            // :227
+                    if (a.need_z2)
+                        dW2 = __dadd_rn(__dmul_rn(__dmul_rn(a.rho, z1), a.sqrt_dt),
+                                        __dmul_rn(__dmul_rn(a.sq1mr2, __dmul_rn(a.zsign, t2[lane * GN_PITCH + t])), a.sqrt_dt));
+                    const double log_drift = __dmul_rn(__dadd_rn(a.drift_comp, -__dmul_rn(0.5, v_pos)), a.dt);   // :229
+                    const double log_diff = __dmul_rn(sqrt_v, dW1);              // :230
+                    double jump = 0.0;                                           // :232
+                    if (a.need_jump) {
+                        if (tj[lane * GN_PITCH + t] < a.jump_thr)                // :233
+                            jump = __dadd_rn(a.mu_j, __dmul_rn(a.sigma_j, __dmul_rn(a.zsign, tjs[lane * GN_PITCH + t])));
+                    }
+                    e[t] = __dadd_rn(__dadd_rn(log_drift, log_diff), jump);
+                    const double mr = __dmul_rn(__dmul_rn(a.kappa, __dadd_rn(a.theta, -v_pos)), a.dt);
+                    const double vv = __dmul_rn(__dmul_rn(a.xi, sqrt_v), dW2);
+                    v = fmax(__dadd_rn(__dadd_rn(v_pos, mr), vv), 0.0);          // :237-238
+                }
+#pragma unroll
+                for (int t = 0; t < GN_TS; ++t) e[t] = exp(e[t]);
+#pragma unroll
+                for (int t = 0; t < GN_TS; ++t) {
+                    S = __dmul_rn(S, e[t]);                                      // :236
+                    if (a.record) tout[lane * GN_PITCH + t] = S;
+                }
+            } else
             for (int t = 0; t < ns; ++t) {
                 const double z1 = __dmul_rn(a.zsign, t1[lane * GN_PITCH + t]);
                 const double v_pos = fmax(v, 0.0);                               // :223
@@ -243,7 +283,13 @@ static int launch_given(b200mc_handle *h, const GivenArgs &a, const double *Z1, 
     const bool wide = force ? atoi(force) == 16 : (a.need_jump != 0 && (a.n_steps % 8) != 0);
     const int ts = wide ? 16 : 8;
     const size_t smem = (size_t)GN_WARPS * ntile * 32 * (ts + 1) * sizeof(double);
-    auto kern = wide ? k_given_normals<16> : k_given_normals<8>;
+    // three-sweep tile walk where the fp64 chain binds (one or two arrays: 1.18 -> 1.04 ms GBM, 1.41 -> 1.33 ms Heston at
+    // 2.5e8 path-steps); with the jump arrays the kernel waits on memory and the sweeps cost 2-5 %
+    // (profiles/r02_given_ilp_probe.txt).  B200MC_GN_ILP=0/1 forces either.
+    const char *ie = getenv("B200MC_GN_ILP");
+    const bool ilp = ie ? atoi(ie) != 0 : (a.need_jump == 0);
+    auto kern = ilp ? (wide ? k_given_normals<16, true> : k_given_normals<8, true>)
+                    : (wide ? k_given_normals<16, false> : k_given_normals<8, false>);
     B200MC_CUDA(h, cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, GN_WARPS * 32, smem, h->stream>>>(a, Z1, Z2, Zj, Zjs, S_final, v_final, all_paths);
     B200MC_CUDA(h, cudaGetLastError());
