@@ -117,6 +117,34 @@ def test_given_normals_ragged(H, golden, n, steps):
     np.testing.assert_allclose(paths, po, rtol=RTOL64)
 
 
+@pytest.mark.parametrize("mode", ["gbm", "heston", "svj"])
+def test_given_normals_tile_walks_agree_bitwise(H, mode, monkeypatch):
+    """The kernel walks a full tile either step by step or in three sweeps (recurrence + exponents, the tile's
+    exponentials side by side, running product), with 8- or 16-step tiles: the same separately rounded operations per
+    path, so all four variants must agree bit for bit -- and with the oracle to rounding -- on ragged shapes too."""
+    from monte_carlo_option_simulator_b200 import SVJParams
+    p = {"gbm": SVJParams.gbm(0.3), "heston": SVJParams(lambda_j=0.0), "svj": SVJParams()}[mode]
+    for n, steps in ((1, 1), (33, 7), (64, 8), (257, 41), (1000, 250)):
+        g = np.random.default_rng(n + steps)
+        Z1, Z2, Zjs = (g.standard_normal((n, steps)) for _ in range(3))
+        Zj = g.random((n, steps))
+        out = []
+        for ilp in ("0", "1"):
+            for tile in ("8", "16"):
+                monkeypatch.setenv("B200MC_GN_ILP", ilp)
+                monkeypatch.setenv("B200MC_GN_TILE", tile)
+                out.append(H.simulate_given_normals(p, 2500.0, 1.0, Z1, Z2, Zj, Zjs, steps, True))
+        monkeypatch.delenv("B200MC_GN_ILP")
+        monkeypatch.delenv("B200MC_GN_TILE")
+        for o in out[1:]:
+            for a, b in zip(o, out[0]):
+                np.testing.assert_array_equal(a, b)
+        So, vo, po = O.simulate_svj(2500.0, p.v0, p.r, p.q, 1.0, p.kappa, p.theta, p.xi, p.rho, p.lambda_j, p.mu_j, p.sigma_j,
+                                    Z1, Z2, Zj, Zjs, steps, True)
+        np.testing.assert_allclose(out[0][0], So, rtol=RTOL64)
+        np.testing.assert_allclose(out[0][2], po, rtol=RTOL64)
+
+
 def test_given_normals_empty_and_errors(H, L, golden):
     p = P(golden, "svj_default")
     e = np.zeros((0, 5))
