@@ -73,22 +73,45 @@ k_risk_hist(const unsigned long long *__restrict__ keys, int64_t n, int pass, in
     }
 }
 
-__global__ void k_risk_pick(int pass, int nsel, SelectState *st)
+// One CTA of 256 threads, one bin each: block scan of the (global) histogram, the thread whose bin holds order statistic
+// `rank` publishes it.  (A single thread walking the 256 bins took 10-24 us per digit: 8 digits = half of a sharded call.)
+__global__ void __launch_bounds__(256) k_risk_pick(int pass, int nsel, SelectState *st)
 {
-    const int s = threadIdx.x;
-    if (s >= nsel) return;
-    long long r = st->rank[s];
-    unsigned long long cum = 0;
-    int bin = 255;
-    for (int b = 0; b < 256; ++b) {
-        const unsigned long long c = st->hist[s][b];
-        if ((long long)(cum + c) > r) { bin = b; break; }
-        cum += c;
+    __shared__ unsigned long long wsum[8];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_below;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int s = 0; s < nsel; ++s) {
+        const unsigned long long c = st->hist[s][t];
+        const long long r = st->rank[s];
+        unsigned long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        if (lane == 31) wsum[w] = inc;
+        if (t == 0) s_bin = -1;
+        __syncthreads();
+        unsigned long long base = 0, total = 0;
+        for (int i = 0; i < 8; ++i) {
+            if (i < w) base += wsum[i];
+            total += wsum[i];
+        }
+        inc += base;
+        const unsigned long long exc = inc - c;
+        if ((long long)exc <= r && (long long)inc > r) { s_bin = t; s_below = exc; }      // at most one thread
+        __syncthreads();
+        st->hist[s][t] = 0ull;
+        if (t == 0) {
+            const int bin = s_bin < 0 ? 255 : s_bin;                 // rank beyond the total: as the sequential walk ended
+            const unsigned long long below = s_bin < 0 ? total : s_below;
+            st->rank[s] = r - (long long)below;
+            st->prefix[s] |= (unsigned long long)bin << (8 * pass);
+            if (pass == 0) st->thr[s] = value_of(st->prefix[s]);
+        }
+        __syncthreads();
     }
-    st->rank[s] = r - (long long)cum;
-    st->prefix[s] |= (unsigned long long)bin << (8 * pass);
-    for (int b = 0; b < 256; ++b) st->hist[s][b] = 0ull;
-    if (pass == 0) st->thr[s] = value_of(st->prefix[s]);
 }
 
 template <typename T>
@@ -123,7 +146,7 @@ k_risk_pass2(const T *__restrict__ x, int64_t n, double mean, int nsel, const Se
 //   end      candidates that differ from the threshold only in the last digit all equal value(prefix | b): their tail
 //            contribution comes from the last histogram alone
 // Between passes: a grid barrier, then EVERY CTA picks the digit from the global histogram itself (2048 bins, one block
-// scan) -- no second barrier, no single-thread walk (k_risk_pick above is 10-24 us per pass: 150 of the 283 us a 4M-value
+// scan) -- no second barrier, no single-thread walk (the one-thread k_risk_pick of round 1 was 10-24 us per pass: 150 of the 283 us a 4M-value
 // call took).  Sums are folded in a fixed order (per-CTA partials, then one ordered sum), so a launch geometry is
 // bitwise reproducible.  Measured on B200: see DESIGN.md section 4.4.
 #ifndef B200MC_RISK_DEFAULT_CTAS
@@ -695,7 +718,7 @@ static int risk_run(b200mc_handle *h, const T *x_dev, const int64_t n_loc, doubl
     for (int pass = 7; pass >= 0; --pass) {
         k_risk_hist<<<(unsigned)grid, RK_THREADS, 0, h->stream>>>(keys, n_loc, pass, nsel, st);
         if (sharded) B200MC_TRY(peer_allreduce_async(h, &st->hist[0][0], 256 * nsel, true));
-        k_risk_pick<<<1, 32, 0, h->stream>>>(pass, nsel, st);
+        k_risk_pick<<<1, 256, 0, h->stream>>>(pass, nsel, st);
         h->launches += 2;
     }
     B200MC_CUDA(h, cudaGetLastError());
