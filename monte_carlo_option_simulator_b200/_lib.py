@@ -659,7 +659,7 @@ class ReferenceDraws:
         self.h, self.n, self.steps = handle, int(n_paths), int(n_steps)
         N = self.n * self.steps
         self.nbytes = 4 * N * 8 + 16 * self.n * 8
-        self.buf = self._take(handle, self.nbytes)
+        self.capacity, self.buf = self._take(handle, self.nbytes)
         self.Z1, self.Z2, self.Zjs, self.Zj = (self.buf + i * N * 8 for i in range(4))
         self.S = self.buf + 4 * N * 8
         self.v = self.S + self.n * 8
@@ -706,11 +706,11 @@ class ReferenceDraws:
         slot = getattr(handle, "_draws_pool", None)
         if slot is not None and slot[0] >= nbytes:
             handle._draws_pool = None
-            return slot[1]
+            return slot
         if slot is not None:
             handle._draws_pool = None
             handle.free(slot[1])
-        return handle.malloc(nbytes)
+        return nbytes, handle.malloc(nbytes)
 
     def close(self):
         if self.buf:
@@ -718,7 +718,7 @@ class ReferenceDraws:
                 self.buf = 0
                 return
             old = getattr(self.h, "_draws_pool", None)
-            self.h._draws_pool = (self.nbytes, self.buf)
+            self.h._draws_pool = (self.capacity, self.buf)
             self.buf = 0
             if old is not None:
                 self.h.free(old[1])
