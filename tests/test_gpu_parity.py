@@ -956,3 +956,86 @@ def test_full_size_linearity_property(H, L, golden):
     mean_s = whole[L.SUMS_FIELDS.index("sum_s")] / n
     sd_s = math.sqrt(whole[L.SUMS_FIELDS.index("sum_ss")] / n - mean_s ** 2)
     assert abs(mean_s - 2500.0 * math.exp(p.r - p.q)) <= 4 * sd_s / math.sqrt(n)
+
+
+def test_cfg2_full_size_greeks_linearity_fp32_and_fp64(H, L, golden):
+    """BASELINE config 2 at its full size (1e7 paths x 250 steps, call + every bump accumulator), fp32 and fp64 state:
+    three unequal shards of the path range add up to the whole-range sums (all 17 of them), the two precisions agree on
+    the same draws within the north star's fp32 tolerance, and the pathwise delta sits within 4 standard errors of
+    Black-Scholes' N(d1)."""
+    from monte_carlo_option_simulator_b200 import bs_delta
+    p, _ = _mode_params(golden, "gbm")
+    n = 10_000_000
+    bumps = L.Bumps(0.01, p.v0 + 0.01, max(p.v0 - 0.01, 0.001), p.r + 1e-4, max(p.r - 1e-4, 0))
+    cuts = [0, 1_234_567, 7_000_001, n]
+    rows = {}
+    for fl, name, tol in ((L.GREEKS, "f32", 2e-7), (L.GREEKS | L.FP64, "f64", 1e-11)):
+        whole = H.price_european(p, 2500.0, 1.0, 250, n, 42, [2500.0], True, fl, bumps)[0]
+        parts = sum(H.price_european(p, 2500.0, 1.0, 250, hi - lo, 42, [2500.0], True, fl, bumps, path_offset=lo)[0]
+                    for lo, hi in zip(cuts[:-1], cuts[1:]))
+        np.testing.assert_allclose(parts, whole, rtol=tol)        # fp32: per-thread partials regroup with the launch shape
+        rows[name] = whole
+    np.testing.assert_allclose(rows["f32"], rows["f64"], rtol=1e-4)
+    i_pw, i_n = L.SUMS_FIELDS.index("sum_pw_delta"), L.SUMS_FIELDS.index("n")
+    delta = math.exp(-p.r) * rows["f64"][i_pw] / rows["f64"][i_n]
+    assert abs(delta - bs_delta(2500.0, 2500.0, 1.0, p.r, p.q, math.sqrt(p.v0), True)) < 4 * 0.6 / math.sqrt(n) + 1e-4
+
+
+def test_cfg5_full_size_eight_way_split_adds_up(H, L, golden):
+    """BASELINE config 5's smallest point (1e8 total paths x 250 steps) the way eight GPUs take it: the eight contiguous
+    shards of dist.shard_range, launched one after the other here, add up to the single whole-range launch."""
+    from monte_carlo_option_simulator_b200.dist import shard_range
+    p, _ = _mode_params(golden, "gbm")
+    n = 100_000_000
+    whole = H.price_european(p, 2500.0, 1.0, 250, n, 7, [2500.0], True, 0)[0]
+    parts = 0
+    covered = 0
+    for r in range(8):
+        lo, hi = shard_range(n, r, 8)
+        assert lo == covered
+        covered = hi
+        parts = parts + H.price_european(p, 2500.0, 1.0, 250, hi - lo, 7, [2500.0], True, 0, path_offset=lo)[0]
+    assert covered == n and parts[L.SUMS_FIELDS.index("n")] == n
+    np.testing.assert_allclose(parts, whole, rtol=2e-7)
+    price = math.exp(-p.r) * whole[L.SUMS_FIELDS.index("sum_a")] / n
+    from monte_carlo_option_simulator_b200 import bs_price
+    assert abs(price - bs_price(2500.0, 2500.0, 1.0, p.r, p.q, math.sqrt(p.v0), True)) < 4 * 570.0 / math.sqrt(n)
+
+
+def test_cfg4_full_size_store_properties(H, L, golden):
+    """BASELINE config 4 at its full size (4M paths x 251 columns, fp32, reference layout), checked on the device through
+    properties that do not need a 4 GB oracle: column 0 is the spot, the last column is the terminal mode's value for the
+    same path (two different kernels: additive log state vs multiplicative carry) within the fp32 tolerance, interior
+    columns are martingales up to the drift, a shard stored on its own equals the same rows of the full store bit for
+    bit, and paths -> option P&L -> VaR / CVaR on the device equals a sort of the same P&L vector."""
+    import torch
+    p, _ = _mode_params(golden, "gbm")
+    n, steps, S0 = 4_000_000, 250, 2500.0
+    mat = torch.empty((n, steps + 1), dtype=torch.float32, device="cuda")
+    H.generate_paths(p, S0, 1.0, steps, n, 42, 0, np.float32, out_dev=mat.data_ptr())
+    term = torch.empty(n, dtype=torch.float32, device="cuda")
+    H.simulate_terminal(p, S0, 1.0, steps, n, 42, 0, np.float32, dev_ptrs=(term.data_ptr(), 0, 0))
+    H.synchronize()
+    assert bool((mat[:, 0] == S0).all()) and bool((mat > 0).all())
+    rel = (mat[:, -1].double() / term.double() - 1).abs()
+    assert float(rel.max()) < 1e-4 and float(rel.median()) < 2e-6
+    for c in (1, 50, 125, 250):
+        col = mat[:, c].double()
+        fwd = S0 * math.exp((p.r - p.q) * c / steps)
+        assert abs(float(col.mean()) - fwd) < 4 * float(col.std()) / math.sqrt(n) + 1e-3
+    lo, hi = 1_234_567, 1_300_000
+    part = torch.empty((hi - lo, steps + 1), dtype=torch.float32, device="cuda")
+    H.generate_paths(p, S0, 1.0, steps, hi - lo, 42, 0, np.float32, path_offset=lo, out_dev=part.data_ptr())
+    H.synchronize()
+    assert torch.equal(part, mat[lo:hi])
+    pnl = torch.empty(n, dtype=torch.float64, device="cuda")
+    disc, premium = math.exp(-p.r), 374.0712289657911
+    H.option_pnl(mat.data_ptr() + steps * 4, n, 2500.0, True, disc, premium, pnl.data_ptr(), dtype_in=np.float32, stride=steps + 1)
+    got = H.risk_metrics(pnl.data_ptr(), 0.99, n=n, dtype=np.float64)
+    want_pnl = disc * torch.clamp(mat[:, -1].double() - 2500.0, min=0.0) - premium
+    assert bool(torch.allclose(want_pnl, pnl, rtol=1e-15, atol=1e-12))      # (the kernel may contract multiply and subtract)
+    srt = torch.sort(pnl).values
+    cut = int(n * (1 - 0.99))
+    assert got[0] == pytest.approx(-float(srt[cut]), rel=1e-12)
+    assert got[1] == pytest.approx(-float(srt[:cut].mean()), rel=1e-9)
+    assert got[6] == pytest.approx(float(pnl.mean()), rel=1e-9, abs=1e-9)
