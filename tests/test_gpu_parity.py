@@ -1039,3 +1039,33 @@ def test_cfg4_full_size_store_properties(H, L, golden):
     assert got[0] == pytest.approx(-float(srt[cut]), rel=1e-12)
     assert got[1] == pytest.approx(-float(srt[:cut].mean()), rel=1e-9)
     assert got[6] == pytest.approx(float(pnl.mean()), rel=1e-9, abs=1e-9)
+
+
+def test_cfg3_full_size_grid_properties(golden):
+    """BASELINE config 3 at its full size (64 strikes x 16 expiries, 1M paths per expiry shared across the strikes):
+    on shared paths call - put equals D (mean S_T - K) path set by path set, so the two grids must satisfy put-call
+    parity against the SAME run's forward to rounding; calls fall and are convex in the strike, both are within 4
+    standard errors of Black-Scholes, and the independent-cells reading agrees with the shared-paths one statistically."""
+    from monte_carlo_option_simulator_b200 import MonteCarloEngine, SVJParams, bs_price
+    p = SVJParams(**golden["params"]["gbm_cfg1"])
+    strikes = np.linspace(0.7 * 2500.0, 1.3 * 2500.0, 64)
+    mats = np.linspace(1 / 12, 2.0, 16)
+    eng = MonteCarloEngine(p, 1_000_000, 250, seed=11, use_sobol=False, use_antithetic=False, use_control_variate=False, rng="philox")
+    calls = eng.price_grid(2500.0, strikes, mats, True)
+    puts = eng.price_grid(2500.0, strikes, mats, False)
+    assert calls["prices"].shape == (16, 64)
+    for j, T in enumerate(mats):
+        D = math.exp(-p.r * T)
+        # the forward of THIS path set, from the deepest in-the-money call and put of the row (parity at one strike) ...
+        fwd = (calls["prices"][j, 0] - puts["prices"][j, 0]) / D + strikes[0]
+        # ... must then hold at every other strike of the row, to fp32-sum rounding
+        np.testing.assert_allclose(calls["prices"][j] - puts["prices"][j], D * (fwd - strikes), rtol=0, atol=2e-3)
+        assert abs(fwd - 2500.0 * math.exp((p.r - p.q) * T)) < 4 * 2500.0 * math.sqrt(p.v0 * T) * 1.2 / 1e3
+        c = calls["prices"][j]
+        assert np.all(np.diff(c) < 0) and np.all(np.diff(c, 2) > -1e-3)                  # monotone, convex (same paths)
+        bs = np.array([bs_price(2500.0, K, T, p.r, p.q, math.sqrt(p.v0), True) for K in strikes])
+        assert np.all(np.abs(c - bs) < 4 * calls["std_errors"][j] + 1e-3 * bs + 1e-6)
+    ind = MonteCarloEngine(p, 200_000, 250, seed=11, use_sobol=False, use_antithetic=False, use_control_variate=False,
+                           rng="philox").price_grid(2500.0, strikes[::8], mats[::4], True, independent_cells=True)
+    sub = calls["prices"][::4, ::8]
+    assert np.all(np.abs(ind["prices"] - sub) < 5 * np.hypot(ind["std_errors"], calls["std_errors"][::4, ::8]) + 1e-6)
