@@ -233,11 +233,35 @@ def _ptr(a) -> Optional[int]:
     return a.ctypes.data
 
 
+class _SerialLib:
+    """The library as seen through ONE handle: every call holds the handle's lock.  The C side keeps per-handle scratch
+    buffers and allows one call in flight per handle (include/b200mc.h); the reference's own callers are serial, but a web
+    server's thread pool sharing the process-wide handle is not, and ctypes releases the GIL during a call.  Threads that
+    share a handle therefore take turns at call granularity; the GPU work stays ordered by the handle's stream."""
+
+    def __init__(self, lib, lock):
+        self.__dict__["_lib"] = lib
+        self.__dict__["_lock"] = lock
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        lock = self._lock
+
+        def call(*args):
+            with lock:
+                return fn(*args)
+        self.__dict__[name] = call               # next time a plain attribute hit
+        return call
+
+
 class Handle:
-    """One b200mc_handle: one device, one stream, scratch.  Not thread-safe (one call in flight)."""
+    """One b200mc_handle: one device, one stream, scratch.  Calls from several threads are serialised per handle
+    (`_SerialLib`); a sequence of calls that belongs together (an asynchronous launch and the read-back of its result) is
+    one method here and runs under `self.lock` where it matters."""
 
     def __init__(self, device: int = 0):
-        self.lib = load()
+        self.lock = threading.RLock()
+        self.lib = _SerialLib(load(), self.lock)
         h = _vp()
         rc = self.lib.b200mc_create(int(device), C.byref(h))
         if rc != OK:

@@ -270,6 +270,20 @@ __device__ __forceinline__ double rf_block_sum(double v, double *red)
     return t;
 }
 
+// exact sum of 64-bit integers over the CTA's threads (associative: the order of the additions cannot matter)
+__device__ __forceinline__ long long rf_block_sum_ll(long long v, unsigned long long *red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = (unsigned long long)v;
+    __syncthreads();
+    long long t = 0;
+    for (int w = 0; w < RF_THREADS / 32; ++w) t += (long long)red[w];
+    return t;
+}
+
 // every CTA: find, in the global histogram h (nbins bins), the bin that holds order statistic `rank`; returns the bin and
 // the number of elements in lower bins.  4 bins per thread + one block scan.
 template <bool GLOBAL = true>
@@ -461,6 +475,11 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
             // memory (at most 4 keys per thread), a microsecond per digit.  (A bitonic sort of the 2048 keys in
             // shared memory took 23 us per selection.)
             if (blockIdx.x == 0) {
+                K cand_lo[2], cand_hi[2];                                    // the key range the gathered candidates lie in
+                for (int sel = 0; sel < nsel; ++sel) {
+                    cand_lo[sel] = prefix[sel];
+                    cand_hi[sel] = prefix[sel] | (((K)1 << up) - (K)1);
+                }
                 for (int sel = 0; sel < nsel; ++sel) {
                     const int nc = (int)__ldcg(&st->ncand[sel]);
                     for (int dd = d; dd < NPASS; ++dd) {
@@ -480,17 +499,43 @@ k_risk_fused(const T *__restrict__ x, long long n, double confidence, FusedState
                         rank[sel] -= s_below[sel];
                     }
                     const K thr_key = prefix[sel];
+                    // The candidates arrive in the order of a global atomic counter, so their tail sum must not depend on
+                    // the order of its additions: every term is turned into a 64-bit fixed-point integer, summed exactly
+                    // (high and low halves apart: 2048 terms cannot overflow either) and rounded ONCE.  Values: the
+                    // candidates share their leading digit(s), i.e. sign and all but the last exponent bit, so with the
+                    // scale taken from the largest magnitude the prefix allows v 2^sc is an exact integer below 2^62.
+                    // Logarithms (|log| < 2^10): scale 2^50, exact from |log| >= 4 and within 2^-51 below.
+                    int sc = 50;
+                    bool exact = true;
+                    if (sel == 0) {
+                        const double vmax = fmax(fabs(KT::value(cand_lo[sel])), fabs(KT::value(cand_hi[sel])));
+                        exact = vmax < 1.7976931348623157e308;            // (an infinity among the inputs: plain sums)
+                        sc = (exact && vmax > 0.0) ? 61 - ilogb(vmax) : 0;
+                    }
                     double cb = 0.0, ab = 0.0;
+                    long long shi = 0, slo = 0;
                     for (int i = tid; i < nc; i += RF_THREADS) {
                         const K key = (K)__ldcg(&st->cand[sel][i]);
                         if (key < thr_key) {
                             const double v = KT::value(key);
+                            const double x = sel == 0 ? v : log(fabs(v));
                             cb += 1.0;
-                            ab += sel == 0 ? v : log(fabs(v));
+                            if (exact) {
+                                const long long q = llrint(scalbn(x, sc));
+                                slo += q & 0xffffffffll;
+                                shi += q >> 32;
+                            } else {
+                                ab += x;
+                            }
                         }
                     }
                     cnt[sel] += cb;
-                    acc[sel] += ab;
+                    if (exact) {
+                        const long long thi = rf_block_sum_ll(shi, scan), tlo = rf_block_sum_ll(slo, scan);
+                        if (tid == 0) acc[sel] += scalbn((double)thi * 4294967296.0 + (double)tlo, -sc);
+                    } else {
+                        acc[sel] += ab;
+                    }
                 }
                 __syncthreads();
             }
