@@ -65,3 +65,74 @@ def test_tail_metrics_are_bitwise_reproducible(n):
                 np.testing.assert_array_equal(again, first)
     finally:
         h.close()
+
+
+def test_handles_do_not_leak_device_memory():
+    """Create / use / destroy cycles: scratch, staging, pinned buffers, the tail-metric state and a pooled draws buffer are
+    all released by b200mc_destroy."""
+    import torch
+    from monte_carlo_option_simulator_b200 import SVJParams, _lib
+
+    def cycle(seed):
+        h = _lib.Handle(0)
+        try:
+            p = SVJParams()
+            h.price_european(p, 2500.0, 0.5, 60, 50_000, seed, [2400.0, 2500.0], True, _lib.GREEKS,
+                             _lib.Bumps(0.01, p.v0 + 0.01, p.v0 - 0.01, p.r + 1e-4, p.r - 1e-4))
+            S = h.simulate_terminal(p, 2500.0, 0.5, 60, 100_000, seed, 0, np.float64)[0]
+            h.risk_metrics(S - 2500.0, 0.99)
+            h.generate_paths(SVJParams.gbm(0.3), 2500.0, 1.0, 250, 20_000, seed, 0, np.float32)
+            d = _lib.ReferenceDraws(h, seed, 5000, 50)
+            d.simulate(p, 2500.0, 0.25)
+            d.close()                                    # parks its buffer in the handle's one-slot pool
+            h.numpy_fill(seed, 100_000)
+        finally:
+            h.close()
+
+    cycle(0)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for i in range(25):
+        cycle(i + 1)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 32 << 20, f"{(free0 - free1) >> 20} MiB lost over 25 handle cycles"
+
+
+def test_two_handles_on_one_device_run_concurrently():
+    """One Handle per thread is the way to overlap work on one device: each has its own stream and scratch.  Includes the
+    cooperative tail-metric kernel on both at once."""
+    from monte_carlo_option_simulator_b200 import SVJParams, _lib
+    hs = [_lib.Handle(0), _lib.Handle(0)]
+    try:
+        p = SVJParams()
+        x = np.random.default_rng(5).standard_t(4, size=1_000_001) * 0.01
+
+        def run(h, seed):
+            row = h.price_european(p, 2500.0, 0.5, 100, 400_000, seed, [2500.0], True, _lib.FP64)
+            return row.copy(), h.risk_metrics(x, 0.99).copy()
+
+        want = [run(hs[0], 1), run(hs[0], 2)]
+        got = [[None] * 8, [None] * 8]
+        errs = []
+
+        def worker(k):
+            try:
+                for i in range(8):
+                    got[k][i] = run(hs[k], k + 1)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=120)
+        assert not errs and not any(t.is_alive() for t in ts), errs
+        for k in range(2):
+            for r in got[k]:
+                np.testing.assert_array_equal(r[0], want[k][0])
+                np.testing.assert_array_equal(r[1], want[k][1])
+    finally:
+        for h in hs:
+            h.close()
