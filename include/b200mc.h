@@ -14,7 +14,9 @@
  *     the last failed b200mc_create on this thread).  The string is valid until the next call on the handle.
  *   - A handle is bound to one CUDA device and owns one stream plus scratch; it is NOT thread-safe (one call
  *     in flight per handle), matching the reference where every caller is serial (engine/app.py:130-236,
- *     engine/calibration.py:202).  Calls are synchronous unless the name ends in _async.
+ *     engine/calibration.py:202).  Callers that share a handle between threads serialise their calls (the Python
+ *     binding does: a lock per handle); several handles on one device may be used concurrently, one per thread.
+ *     Calls are synchronous unless the name ends in _async.
  *   - Host pointers may be pageable or pinned.  *_dev variants take device pointers valid on the handle's
  *     device and run on the handle's stream.
  *   - There is no CPU fallback: without a usable sm_100 device b200mc_create fails with B200MC_ENODEVICE.
