@@ -301,10 +301,12 @@ ALGO = {
     # fp64 path state: the same draws, each widened (F2F, XU-rate pipe) and added in fp64 (DADD)
     "gbm_f64_greeks": {"imad_wide": 17 / 8, "alu": (20 + 4 * 2) / 8, "fp32": 4 * 3 / 8 + 1.0, "xu": 2.0, "loop": 4 / 8,
                        "f2f": 1.0, "fp64": 1.0},
-    # one pair (Z1, Z2) per step, 4 steps per call; 8 FP32 to form the two scaled draws; per state 4 FMA + 1 FMNMX + 1 MUFU.SQRT
-    "heston_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 8 + 2 * 4, "xu": 4.0 + 2, "loop": 4 / 4},
+    # one pair (Z1, Z2) per step, 4 steps per call; 5 FP32 + 3 MUFU (lg2, sin, cos) to prepare the step's draws -- the
+    # Box-Muller radius is never formed: per state sqrt(v+ L) replaces sqrt(v+) and sqrt(L) --; per state 5 FP32 + 1 FMNMX +
+    # 1 MUFU.SQRT
+    "heston_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 5 + 2 * 5, "xu": 3.0 + 2, "loop": 4 / 4},
     # the same step loop: the jumps (drawn per JUMP, not per step) are summed per path outside it (~1 % of the instructions)
-    "svj_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 8 + 2 * 4, "xu": 4.0 + 2, "loop": 4 / 4},
+    "svj_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 5 + 2 * 5, "xu": 3.0 + 2, "loop": 4 / 4},
 }
 SASS_NAME = {"gbm_f32_greeks": "k_europeanILi0ELb0ELb1EfLb1E", "gbm_f64_greeks": "k_europeanILi0ELb0ELb1EdLb1E",
              "heston_f32_antithetic": "k_europeanILi2ELb1ELb0EfLb1E", "svj_f32_antithetic": "k_europeanILi3ELb1ELb0EfLb1E"}

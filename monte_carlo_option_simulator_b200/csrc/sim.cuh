@@ -69,45 +69,57 @@ template <bool ANTI, bool GREEKS> struct StateLayout {
     static constexpr int DN_IDX = UP_IDX + 1;
 };
 
-// One stochastic-variance step for all states.  zs1 = sqrt(dt) Z1 and zsc = xi sqrt(dt) (rho Z1 + sqrt(1-rho^2) Z2) are
-// scaled ONCE per step by the caller (scaled_draws below), not once per state.  Lean form of monte_carlo.py:223-238:
+// One stochastic-variance step for all states.  Lean form of monte_carlo.py:223-238:
 //   * the constant drift (r - q - lambda k) dt is NOT added here: n_steps * drift_dt is added once at the end;
 //   * v is carried unclamped -- the clamp of :238 is the max(v, 0) of :223 at the next step (and of the final v_T);
 //   * jumps are added by the caller inside the (rare) branch that detects them.
+// The draws of the step arrive as StepDraws (scaled_draws below), prepared ONCE per step, not once per state:
+//   fp64 state   a = sqrt(dt) Z1, b = xi sqrt(dt) (rho Z1 + sqrt(1-rho^2) Z2), and every state takes q = sqrt(v+);
+//   fp32 state   both noise terms of :230,237 carry sqrt(v+) times the Box-Muller radius sqrt(-2 ln u), and
+//                sqrt(v+) sqrt(L) = sqrt(v+ L): the radius is never formed -- a = sqrt(dt) cos, b = xi sqrt(dt)
+//                (rho cos + sqrt(1-rho^2) sin), L = -lg2 u (constants folded), q = sqrt(v+ L).  One MUFU less per step
+//                than radius + sqrt(v+) (5 instead of 6 for an antithetic pair), the same FP32 count.
 // 5 FP32 + 1 MUFU per state and step.
+template <typename R> struct StepDraws { R a, b, L; };
+
 template <typename R, bool ANTI, bool GREEKS>
 __device__ __forceinline__ void sv_step(R (&x)[StateLayout<ANTI, GREEKS>::NS], R (&v)[StateLayout<ANTI, GREEKS>::NS],
-                                        const Consts<R> &c, R zs1, R zsc)
+                                        const Consts<R> &c, const StepDraws<R> &d)
 {
     constexpr int NS = StateLayout<ANTI, GREEKS>::NS;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const bool neg = ANTI && k == 1;                 // twin: -Z1, -Z2  (:323)
         const R vp = rmax(v[k], (R)0);                   // :223
-        const R sv = rsqrt_of(vp);                       // :224
+        R sv;
+        if constexpr (sizeof(R) == 4) sv = rsqrt_of(vp * d.L);
+        else sv = rsqrt_of(vp);                          // :224
         const R t = x[k] - c.half_dt * vp;               // :229 without the constant part
         const R mr = vp * c.one_m_kdt + c.kdt_theta;     // v+ + kappa (theta - v+) dt      :237
-        x[k] = neg ? t - sv * zs1 : t + sv * zs1;        // :230,236
-        v[k] = neg ? mr - sv * zsc : mr + sv * zsc;      // :237
+        x[k] = neg ? t - sv * d.a : t + sv * d.a;        // :230,236
+        v[k] = neg ? mr - sv * d.b : mr + sv * d.b;      // :237
     }
 }
 
-// The two scaled draws of a step from its Box-Muller word.  fp64 state: from the fp32 pair exactly as b200mc_dump_normals
-// exports it (Z = BM_SCALE * (double)raw), so the oracle fed the dumped draws agrees to rounding.  fp32 state: the
-// constants are folded into the radius first (5 FP32 per step in all; the results differ from the fp64 route by fp32
-// rounding only, far inside the 1e-4 band).
+// The draws of a step from its Box-Muller word.  fp64 state: from the fp32 pair exactly as b200mc_dump_normals exports
+// it (Z = BM_SCALE * (double)raw), so the oracle fed the dumped draws agrees to rounding.  fp32 state: see sv_step (the
+// results differ from the fp64 route by fp32 rounding only, far inside the 1e-4 band).
 template <typename R>
-__device__ __forceinline__ void scaled_draws(uint32_t w, const Consts<R> &c, R &zs1, R &zsc)
+__device__ __forceinline__ StepDraws<R> scaled_draws(uint32_t w, const Consts<R> &c)
 {
+    StepDraws<R> d;
     if constexpr (sizeof(R) == 4) {
-        const BM3 b = box_muller_parts(w);
-        zs1 = (b.rad * c.sqrt_dt_s) * b.cs;
-        zsc = b.rad * fmaf(c.xs_crho, b.sn, c.xs_rho * b.cs);
+        const BM3L b = box_muller_parts_l(w);
+        d.L = b.L;
+        d.a = c.sqrt_dt_s * b.cs;
+        d.b = fmaf(c.xs_crho, b.sn, c.xs_rho * b.cs);
     } else {
         const BM2 b = box_muller_word(w);
-        zs1 = c.sqrt_dt_s * (R)b.rc;
-        zsc = c.xi_sqrt_dt_s * (c.rho * (R)b.rc + c.crho * (R)b.rs);
+        d.L = (R)1;
+        d.a = c.sqrt_dt_s * (R)b.rc;
+        d.b = c.xi_sqrt_dt_s * (c.rho * (R)b.rc + c.crho * (R)b.rs);
     }
+    return d;
 }
 
 // Draw layout (part of the ABI, include/b200mc.h "Random numbers"): Philox counter = (path_lo, path_hi, block, stream),
@@ -279,9 +291,8 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
             for (int t = 0; t < 4; ++t) {
                 const int s = 4 * j + t;
                 if (t == 0 || s < n_steps) {
-                    R zs1, zsc;
-                    scaled_draws<R>(ww[t], c, zs1, zsc);
-                    sv_step<R, ANTI, GREEKS>(x, v, c, zs1, zsc);
+                    const StepDraws<R> dr = scaled_draws<R>(ww[t], c);
+                    sv_step<R, ANTI, GREEKS>(x, v, c, dr);
                     if constexpr (MODE == MODE_SVJ && Rec::enabled) {             // a recorded path takes its jumps in place
                         if (s == jmp.next) {                                             // :233-234, rare
                             const R jsz = c.sigma_j_s * (R)jmp.size_raw();
