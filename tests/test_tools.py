@@ -52,3 +52,16 @@ def test_probe_library_is_separate_from_the_product_abi():
     import ctypes as C
     v = C.c_double()
     assert lib.b200mc_probe_rate(0, 999, 16, C.byref(v)) == 4          # bad selector is refused before any CUDA call
+
+
+def test_every_ncu_summary_the_bench_line_cites_is_committed():
+    """bench.py copies `traffic_source` from profiles/r02_ncu_traffic.json; each entry names the ncu summary it came from."""
+    import json
+    import re
+    t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    assert len(t) >= 8
+    for key, v in t.items():
+        assert v["dram_bytes_per_launch"] > 0, key
+        for path in re.findall(r"profiles/[A-Za-z0-9_]+\.txt", v["source"]):
+            assert os.path.exists(os.path.join(ROOT, path)), f"{key}: {path} is cited but not committed"
+            assert "kernel:" in open(os.path.join(ROOT, path)).read()

@@ -3,7 +3,8 @@ of the fused kernels and to derive the instruction roofline in bench
 
     python tools/sass_mix.py [substring of the mangled kernel name] [--steps-per-iter N]
 
-The hot loop is taken to be the backward branch whose body holds the most IMAD.WIDE (= Philox rounds).
+The hot loop is the innermost loop around a Philox call (>= 10 IMAD.WIDE) with the most MUFU in its body (the step
+loop; the SVJ kernels also loop over a path's jump times, with few MUFU).
 Classes: heavy = IMAD* (fmaheavy pipe), alu = LOP3/IADD3/SHF/ISETP/SEL/MOV/PRMT/FMNMX..., fp32 = FFMA/FMUL/FADD
 (either FMA pipe), xu = MUFU, fp64 = D*, uni = uniform-datapath instructions, lsu = LD*/ST*, ctl = BRA/BAR/...
 """
@@ -66,7 +67,12 @@ def hot_loop(ins):
         if any(t2 >= tgt and a2 < addr for t2, a2 in loops if (t2, a2) != (tgt, addr)):
             continue
         body = [i for i in ins if tgt <= i[0] <= addr]
-        score = sum(1 for i in body if i[1].startswith("IMAD.WIDE"))
+        wide = sum(1 for i in body if i[1].startswith("IMAD.WIDE"))
+        if wide < 10:
+            continue                                  # not a loop around a Philox call
+        # the SVJ kernels hold two such loops: the step loop and the (short, MUFU-poor) loop that walks a path's jump
+        # times before it -- the step loop is the one with the Box-Muller transforms
+        score = (sum(1 for i in body if i[1].startswith("MUFU")), wide)
         if best is None or score > best[0]:
             best = (score, body)
     return best[1] if best else []
