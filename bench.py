@@ -304,9 +304,9 @@ ALGO = {
     # one pair (Z1, Z2) per step, 4 steps per call; 5 FP32 + 3 MUFU (lg2, sin, cos) to prepare the step's draws -- the
     # Box-Muller radius is never formed: per state sqrt(v+ L) replaces sqrt(v+) and sqrt(L) --; per state 5 FP32 + 1 FMNMX +
     # 1 MUFU.SQRT
-    "heston_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 5 + 2 * 5, "xu": 3.0 + 2, "loop": 4 / 4},
+    "heston_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 5 + 2 * 5, "xu": 3.0 + 2, "loop": 3 / 4},
     # the same step loop: the jumps (drawn per JUMP, not per step) are summed per path outside it (~1 % of the instructions)
-    "svj_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 5 + 2 * 5, "xu": 3.0 + 2, "loop": 4 / 4},
+    "svj_f32_antithetic": {"imad_wide": 17 / 4, "alu": (20 + 4 * 2) / 4 + 2, "fp32": 5 + 2 * 5, "xu": 3.0 + 2, "loop": 3 / 4},
 }
 SASS_NAME = {"gbm_f32_greeks": "k_europeanILi0ELb0ELb1EfLb1E", "gbm_f64_greeks": "k_europeanILi0ELb0ELb1EdLb1E",
              "heston_f32_antithetic": "k_europeanILi2ELb1ELb0EfLb1E", "svj_f32_antithetic": "k_europeanILi3ELb1ELb0EfLb1E"}

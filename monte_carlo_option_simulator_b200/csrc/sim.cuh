@@ -281,30 +281,38 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
             }
         }
         constexpr uint32_t STREAM = MODE == MODE_HESTON ? B200MC_STREAM_HESTON : B200MC_STREAM_SVJ;
-        const int nblk = (n_steps + 3) >> 2;
-        U4 u = philox4x32_10(c0, c1, 0u, STREAM, key);
-        for (int j = 0; j < nblk; ++j) {
-            U4 un = u;
-            if (j + 1 < nblk) un = philox4x32_10(c0, c1, (uint32_t)(j + 1), STREAM, key);
-            const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+        // one step from its word (the recorder and, for a recorded SVJ path, the in-place jump ride along)
+        auto step = [&](uint32_t w, int s) {
+            const StepDraws<R> dr = scaled_draws<R>(w, c);
+            sv_step<R, ANTI, GREEKS>(x, v, c, dr);
+            if constexpr (MODE == MODE_SVJ && Rec::enabled) {                     // a recorded path takes its jumps in place
+                if (s == jmp.next) {                                                     // :233-234, rare
+                    const R jsz = c.sigma_j_s * (R)jmp.size_raw();
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int s = 4 * j + t;
-                if (t == 0 || s < n_steps) {
-                    const StepDraws<R> dr = scaled_draws<R>(ww[t], c);
-                    sv_step<R, ANTI, GREEKS>(x, v, c, dr);
-                    if constexpr (MODE == MODE_SVJ && Rec::enabled) {             // a recorded path takes its jumps in place
-                        if (s == jmp.next) {                                             // :233-234, rare
-                            const R jsz = c.sigma_j_s * (R)jmp.size_raw();
-#pragma unroll
-                            for (int k = 0; k < NS; ++k) x[k] += (ANTI && k == 1) ? c.mu_j - jsz : c.mu_j + jsz;
-                            jmp.advance(c0, c1, key, inv_lg2_q, s);
-                        }
-                    }
-                    if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }
+                    for (int k = 0; k < NS; ++k) x[k] += (ANTI && k == 1) ? c.mu_j - jsz : c.mu_j + jsz;
+                    jmp.advance(c0, c1, key, inv_lg2_q, s);
                 }
             }
+            if constexpr (Rec::enabled) { dacc += c.drift_dt; rec(s, x[0] + dacc); }
+        };
+        // Full blocks of four steps run without a per-step bound test (three compares and branches per block: 4 % of the
+        // loop); the last 1-3 steps of a path are a separate tail.  The Philox rounds of block j + 1 are issued before the
+        // steps of block j, as in the GBM loop.
+        const int nfull = n_steps >> 2, rem = n_steps & 3, nblk = nfull + (rem ? 1 : 0);
+        U4 u = philox4x32_10(c0, c1, 0u, STREAM, key);
+        for (int j = 0; j < nfull; ++j) {
+            U4 un = u;
+            if (j + 1 < nblk) un = philox4x32_10(c0, c1, (uint32_t)(j + 1), STREAM, key);
+            step(u.x, 4 * j);
+            step(u.y, 4 * j + 1);
+            step(u.z, 4 * j + 2);
+            step(u.w, 4 * j + 3);
             u = un;
+        }
+        if (rem) {
+            step(u.x, 4 * nfull);
+            if (rem > 1) step(u.y, 4 * nfull + 1);
+            if (rem > 2) step(u.z, 4 * nfull + 2);
         }
         {
             const R total_drift = (R)((double)n_steps * m.drift_dt);
