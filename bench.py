@@ -296,8 +296,10 @@ def pipe_bounds(rates, n_wide, n_other, n_alu, n_xu, n_f2f=0.0, n_fp64=0.0):
 # 17 IMAD.WIDE (first round's multiplies loop-invariant / warp-uniform) + 20 LOP3; a Box-Muller word = 2 ALU (field
 # extraction) + 4 MUFU + FP32 glue.
 ALGO = {
-    # 8 normals per call; per pair 3 FP32 (2 - f, angle FMA, range FMUL) + 2 to scale and accumulate
-    "gbm_f32_greeks": {"imad_wide": 17 / 8, "alu": (20 + 4 * 2) / 8, "fp32": 4 * 5 / 8, "xu": 2.0, "loop": 4 / 8},
+    # 8 normals per call; per word (two normals, of which only the SUM enters a constant-variance terminal value:
+    # rad (cos a + sin a) = sqrt(2) rad sin(a + pi/4)) 3 FP32 (2 - f, angle FMA, range FMUL) + 1 to accumulate and 3 MUFU
+    # (lg2, sqrt, sin)
+    "gbm_f32_greeks": {"imad_wide": 17 / 8, "alu": (20 + 4 * 2) / 8, "fp32": 4 * 4 / 8, "xu": 1.5, "loop": 4 / 8},
     # fp64 path state: the same draws, each widened (F2F, XU-rate pipe) and added in fp64 (DADD)
     "gbm_f64_greeks": {"imad_wide": 17 / 8, "alu": (20 + 4 * 2) / 8, "fp32": 4 * 3 / 8 + 1.0, "xu": 2.0, "loop": 4 / 8,
                        "f2f": 1.0, "fp64": 1.0},

@@ -186,15 +186,26 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         // Software-pipelined: the Philox rounds of block j+1 (IMAD.WIDE / LOP3) are issued in the same loop body as
         // the Box-Muller transforms of block j (MUFU), so every warp feeds the XU pipe at an even rate instead of
         // in bursts (ncu: mio_throttle was the top stall with the two phases back to back).
+        // fp32 state: only the SUM of the draws enters x_T, and the two normals of a word add up to sqrt(2) rad sin(a + pi/4)
+        // (philox.cuh, box_muller_word_sum): full blocks take 3 MUFU and one accumulation per word instead of 4 and two.
+        // The fp64 state adds every widened normal on its own, as b200mc_dump_normals exports them (parity to rounding).
         R sumz = (R)0;
+        float sumw = 0.f;                                  // sum over whole words of rad sin(a + pi/4)   (fp32 state only)
         const int nb = (n_steps + 7) >> 3;                 // blocks, the last one possibly partial
         U4 u = philox4x32_10(c0, c1, 0u, B200MC_STREAM_GBM, key);
         for (int j = 1; j < nb; ++j) {
             const U4 un = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
-            const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
-                      b3 = box_muller_word(u.w);
-            sumz += (R)b0.rc; sumz += (R)b0.rs; sumz += (R)b1.rc; sumz += (R)b1.rs;
-            sumz += (R)b2.rc; sumz += (R)b2.rs; sumz += (R)b3.rc; sumz += (R)b3.rs;
+            if constexpr (sizeof(R) == 4) {
+                sumw += box_muller_word_sum(u.x);
+                sumw += box_muller_word_sum(u.y);
+                sumw += box_muller_word_sum(u.z);
+                sumw += box_muller_word_sum(u.w);
+            } else {
+                const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
+                          b3 = box_muller_word(u.w);
+                sumz += (R)b0.rc; sumz += (R)b0.rs; sumz += (R)b1.rc; sumz += (R)b1.rs;
+                sumz += (R)b2.rc; sumz += (R)b2.rs; sumz += (R)b3.rc; sumz += (R)b3.rs;
+            }
             u = un;
         }
         {
@@ -206,6 +217,7 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
             for (int t = 0; t < 8; ++t)
                 if (t < rem) sumz += z[t];
         }
+        if constexpr (sizeof(R) == 4) sumz = fmaf(sumw, B200MC_SQRT2_F, sumz);
         sumz_out = sumz;
         xT[0] = (R)m.x_drift[0] + (R)m.x_w[0] * sumz;
         if constexpr (ANTI) xT[1] = (R)m.x_drift[0] - (R)m.x_w[0] * sumz;
