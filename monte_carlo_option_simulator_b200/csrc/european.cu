@@ -141,7 +141,7 @@ k_european(const __grid_constant__ EuroArgs a, const double *__restrict__ wtab_g
         }
         for (int64_t i = (int64_t)blockIdx.x * EU_THREADS + tid; i < a.n_paths; i += (int64_t)gridDim.x * EU_THREADS) {
             R xT[NS], vT[NS], sumz;
-            simulate_path<MODE, ANTI, GREEKS, R, NoRec, WIDE>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT,
+            simulate_path<MODE, ANTI, GREEKS, R, NoRec, WIDE, sizeof(R) == 4>(a.m, a.key, a.path0 + (uint64_t)i, a.n_steps, wtab, a.wld, xT,
                                                               vT, sumz, NoRec());
             R sv[NS];
 #pragma unroll

@@ -133,7 +133,9 @@ __device__ __forceinline__ StepDraws<R> scaled_draws(uint32_t w, const Consts<R>
 // (GBM / DETVAR: vT is left untouched); sumz_out = sum of the raw draws (GBM only; feeds the pathwise vega).
 // wtab: DETVAR weights, wtab[k * wld + s] = sqrt(v_s^{(k)} dt) * BM_SCALE in shared memory (wld = steps rounded up to 8,
 // zero padded).  rec: after every step s, rec(s, x0) gets the primary state's log return (path store).
-template <int MODE, bool ANTI, bool GREEKS, typename R, typename Rec, bool WIDE = false>
+// PAIRED (GBM): two Philox blocks per loop iteration (see the GBM branch); chosen by the caller -- it pays in the
+// single-strike fp32 kernel (+3.6 %) and costs 1.5-3 % where the loop is XU bound (fp64 state) or short of registers (multi-strike).
+template <int MODE, bool ANTI, bool GREEKS, typename R, typename Rec, bool WIDE = false, bool PAIRED = false>
 __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKey &key, uint64_t path, int n_steps,
                                               const R *wtab, int wld,
                                               R (&xT)[StateLayout<ANTI, GREEKS>::NS],
@@ -192,21 +194,41 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         R sumz = (R)0;
         float sumw = 0.f;                                  // sum over whole words of rad sin(a + pi/4)   (fp32 state only)
         const int nb = (n_steps + 7) >> 3;                 // blocks, the last one possibly partial
-        U4 u = philox4x32_10(c0, c1, 0u, B200MC_STREAM_GBM, key);
-        for (int j = 1; j < nb; ++j) {
-            const U4 un = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+        auto whole = [&](const U4 &q) {                    // all eight draws of a block
             if constexpr (sizeof(R) == 4) {
-                sumw += box_muller_word_sum(u.x);
-                sumw += box_muller_word_sum(u.y);
-                sumw += box_muller_word_sum(u.z);
-                sumw += box_muller_word_sum(u.w);
+                sumw += box_muller_word_sum(q.x);
+                sumw += box_muller_word_sum(q.y);
+                sumw += box_muller_word_sum(q.z);
+                sumw += box_muller_word_sum(q.w);
             } else {
-                const BM2 b0 = box_muller_word(u.x), b1 = box_muller_word(u.y), b2 = box_muller_word(u.z),
-                          b3 = box_muller_word(u.w);
+                const BM2 b0 = box_muller_word(q.x), b1 = box_muller_word(q.y), b2 = box_muller_word(q.z),
+                          b3 = box_muller_word(q.w);
                 sumz += (R)b0.rc; sumz += (R)b0.rs; sumz += (R)b1.rc; sumz += (R)b1.rs;
                 sumz += (R)b2.rc; sumz += (R)b2.rs; sumz += (R)b3.rc; sumz += (R)b3.rs;
             }
-            u = un;
+        };
+        // two blocks per iteration, the two word sets alternating between u and un: no register copies at the loop end
+        // (they were 5 of the 85 instructions of an iteration, and the issue port is what this loop is bound by)
+        U4 u = philox4x32_10(c0, c1, 0u, B200MC_STREAM_GBM, key);
+        if constexpr (PAIRED) {
+            int j = 1;
+            for (; j + 1 < nb; j += 2) {
+                const U4 un = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+                whole(u);
+                u = philox4x32_10(c0, c1, (uint32_t)(j + 1), B200MC_STREAM_GBM, key);
+                whole(un);
+            }
+            if (j < nb) {
+                const U4 un = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+                whole(u);
+                u = un;
+            }
+        } else {
+            for (int j = 1; j < nb; ++j) {
+                const U4 un = philox4x32_10(c0, c1, (uint32_t)j, B200MC_STREAM_GBM, key);
+                whole(u);
+                u = un;
+            }
         }
         {
             const int rem = n_steps - 8 * (nb - 1);        // 1..8 draws of the last block are used

@@ -19,8 +19,10 @@ def test_sass_mix_of_the_headline_kernel():
     m = list(mixes.values())[0]
     # one Philox4x32-10 call per loop iteration = 8 steps: 4 words x 3 MUFU (lg2, sqrt, ONE sine for the sum of the word's
     # two normals), at most 20 wide multiplies
-    assert m["philox_calls"] == 1 and m["xu"] == 12 and 17 <= m["imad_wide"] <= 20
-    assert 75 <= m["total"] <= 100, m           # 85 today; a jump means the hot loop changed -- re-measure before shipping
+    # (the loop body holds TWO calls: the word sets alternate between two register sets instead of being copied)
+    calls = m["philox_calls"]
+    assert calls == 2 and m["xu"] == 12 * calls and 17 * calls <= m["imad_wide"] <= 20 * calls
+    assert 75 * calls <= m["total"] <= 90 * calls, m   # 160 today; a jump means the hot loop changed -- re-measure before shipping
 
 
 def test_ptxas_logs_report_no_spills_in_the_hot_kernels():
