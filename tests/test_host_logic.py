@@ -523,3 +523,22 @@ def test_expired_option_returns_the_intrinsic_value_like_the_reference():
         assert [x["price"] for x in b] == [5.0, 0.0] and b[0]["strike"] == 100.0 and b[0]["bs_ref"] == 5.0
     e = MonteCarloEngine(SVJParams(), 1000, 252, 42, use_control_variate=False, rng="philox")
     assert set(e.price(95.0, 100.0, 0.0, False)) == {"price", "std_error", "num_paths_used", "num_steps"}
+
+
+def test_parameter_helpers_equal_the_reference():
+    """jump_compensation / feller_satisfied / to_array / from_array / validate of the parameter container against
+    the values the reference's dataclass gave (tests/golden/make_params_golden.py; engine/models.py:46-84)."""
+    import json
+    from monte_carlo_option_simulator_b200.models import SVJParams as P
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "params_golden.json"), encoding="utf-8"))
+    assert len(gold) >= 10
+    for name, g in gold.items():
+        p = P(**g["kwargs"])
+        assert p.jump_compensation == g["jump_compensation"], name
+        assert p.feller_satisfied is g["feller_satisfied"], name
+        arr = p.to_array()
+        assert arr.dtype == np.float64 and arr.tolist() == g["to_array"], name
+        assert p.validate() == g["validate"], name
+        back = P.from_array(arr, r=0.02, q=0.005)
+        assert {f: getattr(back, f) for f in g["from_array_fields"]} == g["from_array_fields"], name
+    assert P.from_array(P().to_array()) == P()          # defaults of r, q are the reference's market constants
