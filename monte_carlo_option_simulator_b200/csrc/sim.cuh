@@ -20,6 +20,12 @@
 #pragma once
 #include "common.cuh"
 
+// fp64 state of the constant-variance terminal kernels: 1 = a word's two normals enter as their exact fp32 sum (TwoSum,
+// philox.cuh box_muller_word_twosum), 0 = each normal widened and added on its own
+#ifndef B200MC_FP64_TWOSUM
+#define B200MC_FP64_TWOSUM 0
+#endif
+
 namespace b200mc {
 
 enum { MODE_GBM = 0, MODE_DETVAR = 1, MODE_HESTON = 2, MODE_SVJ = 3 };
@@ -192,7 +198,8 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
         // (philox.cuh, box_muller_word_sum): full blocks take 3 MUFU and one accumulation per word instead of 4 and two.
         // The fp64 state adds every widened normal on its own, as b200mc_dump_normals exports them (parity to rounding).
         R sumz = (R)0;
-        float sumw = 0.f;                                  // sum over whole words of rad sin(a + pi/4)   (fp32 state only)
+        float sumw = 0.f;                                  // fp32 state: sum over whole words of rad sin(a + pi/4);
+                                                           // fp64 state (B200MC_FP64_TWOSUM): the words' TwoSum remainders
         const int nb = (n_steps + 7) >> 3;                 // blocks, the last one possibly partial
         auto whole = [&](const U4 &q) {                    // all eight draws of a block
             if constexpr (sizeof(R) == 4) {
@@ -201,10 +208,18 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                 sumw += box_muller_word_sum(q.z);
                 sumw += box_muller_word_sum(q.w);
             } else {
+#if B200MC_FP64_TWOSUM
+                // the exact fp32 sum of a word's two normals, widened once; the exact remainders go to an fp32 side sum
+                const BMSum b0 = box_muller_word_twosum(q.x), b1 = box_muller_word_twosum(q.y),
+                            b2 = box_muller_word_twosum(q.z), b3 = box_muller_word_twosum(q.w);
+                sumz += (R)b0.s; sumz += (R)b1.s; sumz += (R)b2.s; sumz += (R)b3.s;
+                sumw += (b0.e + b1.e) + (b2.e + b3.e);
+#else
                 const BM2 b0 = box_muller_word(q.x), b1 = box_muller_word(q.y), b2 = box_muller_word(q.z),
                           b3 = box_muller_word(q.w);
                 sumz += (R)b0.rc; sumz += (R)b0.rs; sumz += (R)b1.rc; sumz += (R)b1.rs;
                 sumz += (R)b2.rc; sumz += (R)b2.rs; sumz += (R)b3.rc; sumz += (R)b3.rs;
+#endif
             }
         };
         // two blocks per iteration, the two word sets alternating between u and un: no register copies at the loop end
@@ -240,6 +255,9 @@ __device__ __forceinline__ void simulate_path(const ModelArgs &m, const PhiloxKe
                 if (t < rem) sumz += z[t];
         }
         if constexpr (sizeof(R) == 4) sumz = fmaf(sumw, B200MC_SQRT2_F, sumz);
+#if B200MC_FP64_TWOSUM
+        else sumz += (R)sumw;                              // the words' exact remainders (fp64 state)
+#endif
         sumz_out = sumz;
         xT[0] = (R)m.x_drift[0] + (R)m.x_w[0] * sumz;
         if constexpr (ANTI) xT[1] = (R)m.x_drift[0] - (R)m.x_w[0] * sumz;

@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from monte_carlo_option_simulator_b200 import SVJParams, _lib  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+only = sys.argv[2] if len(sys.argv) > 2 else ""            # substring filter on the case names
 h = _lib.Handle(0)
 g = SVJParams.gbm(0.3, r=0.065)
 bumps = _lib.Bumps(0.01, g.v0 + 0.01, g.v0 - 0.01, g.r + 1e-4, g.r - 1e-4)
@@ -19,11 +20,16 @@ cases = [("gbm fp32 greeks", g, _lib.GREEKS, bumps, [2500.0], 2500.0, n),
          ("gbm fp32 price", g, 0, None, [2500.0], 2500.0, n),
          ("gbm fp32 anti", g, _lib.ANTITHETIC, None, [2500.0], 2500.0, n),
          ("gbm fp64 price", g, _lib.FP64, None, [2500.0], 2500.0, n),
+         ("gbm fp64 greeks", g, _lib.FP64 | _lib.GREEKS, bumps, [2500.0], 2500.0, n),
+         ("gbm fp64 anti", g, _lib.FP64 | _lib.ANTITHETIC, None, [2500.0], 2500.0, n),
          ("gbm fp32 64 strikes", g, _lib.ANTITHETIC, None, list(np.linspace(0.7, 1.3, 64) * 2500.0), 2500.0, n),
          ("heston fp32 anti", SVJParams(lambda_j=0.0), _lib.ANTITHETIC, None, [22500.0], 22500.0, n // 4),
          ("svj fp32 anti", SVJParams(), _lib.ANTITHETIC, None, [22500.0], 22500.0, n // 4),
          ("svj fp32 greeks", SVJParams(), _lib.GREEKS, _lib.Bumps(0.01, 0.05, 0.03, 0.0651, 0.0649), [22500.0], 22500.0, n // 4)]
+print("library:", _lib.LIB_PATH, flush=True)
 for name, p, fl, b, ks, s0, nn in cases:
+    if only not in name:
+        continue
     best = 1e9
     for r in range(4):
         h.timer_begin()

@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "monte_carlo_option_simulator_b200", "libb200mc.so")
+LIB = os.environ.get("B200MC_LIB") or os.path.join(ROOT, "monte_carlo_option_simulator_b200", "libb200mc.so")
 
 CLASSES = [
     ("xu", r"^MUFU"),
