@@ -352,8 +352,10 @@ extern "C" int b200mc_price_cells(b200mc_handle *h, const b200mc_cell *cells, in
     const size_t bytes = (size_t)n_cells * n_strikes * sizeof(b200mc_sums);
     B200MC_TRY(ensure(h, &h->d_result, &h->result_bytes, bytes));
     B200MC_TRY(ensure(h, &h->h_result, &h->h_result_bytes, bytes, true));
-    B200MC_TRY(launch_cells(h, cells, n_cells, strikes, n_strikes, flags, reinterpret_cast<double *>(h->d_result)));
-    B200MC_CUDA(h, cudaMemcpyAsync(h->h_result, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
+    double *mapped = result_mapped_ptr(h, bytes);      // common.cuh
+    B200MC_TRY(launch_cells(h, cells, n_cells, strikes, n_strikes, flags,
+                            mapped ? mapped : reinterpret_cast<double *>(h->d_result)));
+    if (!mapped) B200MC_CUDA(h, cudaMemcpyAsync(h->h_result, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
     memcpy(out, h->h_result, bytes);
     return 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b200mc.h"
@@ -85,6 +86,38 @@ inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pi
     }
     *have = sz;
     return 0;
+}
+
+// Where the synchronous entry points (b200mc_price_european, b200mc_price_cells with host results) let the kernels write
+// their few result doubles: "mapped" = straight into the pinned landing buffer h_result through the bus (pinned memory is
+// device-addressable under unified addressing; the last CTA's 17 stores per strike are posted writes), so the call is
+// launch -> synchronise -> memcpy with no device-to-host copy command in between; "copy" = into d_result, followed by a
+// cudaMemcpyAsync.  Small calls (calibration: 1e4-1e5 of them, 10-40 us of GPU work each) are bound by this fixed cost.
+// B200MC_RESULT=copy|mapped overrides the default; results larger than RESULT_MAPPED_MAX always take the copy.
+#ifndef B200MC_RESULT_MAPPED_DEFAULT
+#define B200MC_RESULT_MAPPED_DEFAULT 0
+#endif
+constexpr size_t RESULT_MAPPED_MAX = 64 * 1024;
+inline bool result_mapped_wanted()
+{
+    static const int v = [] {
+        const char *e = getenv("B200MC_RESULT");
+        if (e && !strcmp(e, "mapped")) return 1;
+        if (e && !strcmp(e, "copy")) return 0;
+        return B200MC_RESULT_MAPPED_DEFAULT;
+    }();
+    return v != 0;
+}
+// device address of the pinned landing buffer, or nullptr when the results have to go through d_result
+inline double *result_mapped_ptr(b200mc_handle *h, size_t bytes)
+{
+    if (!result_mapped_wanted() || bytes > RESULT_MAPPED_MAX || !h->h_result) return nullptr;
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, h->h_result, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return reinterpret_cast<double *>(dp);
 }
 
 // peer.cu: in-place sum over the ranks of n 8-byte elements (double, or unsigned long long with as_u64) at data_dev,

@@ -445,10 +445,11 @@ extern "C" int b200mc_price_european(b200mc_handle *h, const b200mc_svj_params *
     const size_t bytes = (size_t)n_strikes * sizeof(b200mc_sums);
     B200MC_TRY(ensure(h, &h->d_result, &h->result_bytes, bytes));
     B200MC_TRY(ensure(h, &h->h_result, &h->h_result_bytes, bytes, true));
+    double *mapped = result_mapped_ptr(h, bytes);      // common.cuh: the kernel writes the pinned landing buffer itself
     B200MC_TRY(launch_european(h, p, S0, T, n_steps, n_paths, seed, path_offset, strikes, n_strikes, is_call, flags,
-                               bumps, reinterpret_cast<double *>(h->d_result)));
+                               bumps, mapped ? mapped : reinterpret_cast<double *>(h->d_result)));
     // device -> PINNED host (a pageable destination makes the copy a staged, much slower one), then a plain memcpy
-    B200MC_CUDA(h, cudaMemcpyAsync(h->h_result, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (!mapped) B200MC_CUDA(h, cudaMemcpyAsync(h->h_result, h->d_result, bytes, cudaMemcpyDeviceToHost, h->stream));
     B200MC_CUDA(h, cudaStreamSynchronize(h->stream));
     memcpy(out, h->h_result, bytes);
     return 0;
