@@ -7,6 +7,7 @@ device is visible, every compute entry point raises -- it never silently routes 
 from __future__ import annotations
 
 import ctypes as C
+import operator
 import os
 import threading
 from typing import Optional
@@ -220,9 +221,15 @@ def sobol_tables(n_dims: int, seed: int):
     return sv, shift, int(eng.bits)
 
 
+_param_values = operator.attrgetter(*PARAM_FIELDS)
+
+
 def to_params(p) -> SvjParams:
     """Accepts the reference's SVJParams, ours, or anything with the ten fields (duck-typed)."""
-    return SvjParams(*(float(getattr(p, n)) for n, _ in SvjParams._fields_))
+    try:
+        return SvjParams(*_param_values(p))                 # one C-level attribute sweep (floats, ints, NumPy floats)
+    except TypeError:
+        return SvjParams(*(float(v) for v in _param_values(p)))     # anything else float() understands
 
 
 def _ptr(a) -> Optional[int]:
@@ -376,17 +383,27 @@ class Handle:
                        bumps: Optional[Bumps] = None, path_offset=0, out_dev: Optional[int] = None):
         """Returns a float64 array [n_strikes, NSUMS] (columns = SUMS_FIELDS), or None when `out_dev`
         (device pointer to n_strikes b200mc_sums) is given: then the launch is asynchronous."""
-        strikes = np.ascontiguousarray(np.atleast_1d(strikes), dtype=np.float64)
+        # Small calls (calibration, the web handlers) are bound by fixed costs, this marshalling among them: the strikes
+        # travel as a ctypes array (no ndarray and no `.ctypes` proxy object for the usual short list) and the sums land
+        # in a ctypes buffer that becomes the returned array.
+        if isinstance(strikes, (list, tuple)):
+            nk = len(strikes)
+            ks = (C.c_double * nk)(*strikes)
+        else:
+            kk = np.ascontiguousarray(np.atleast_1d(strikes), dtype=np.float64)
+            nk = int(kk.size)
+            ks = kk.ctypes.data                              # kk stays referenced until the call returns
         sp = to_params(params)
         bp = C.byref(bumps) if bumps is not None else None
-        args = (self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & (2 ** 64 - 1),
-                int(path_offset), strikes.ctypes.data, int(strikes.size), int(bool(is_call)), int(flags), bp)
+        args = (self.h, C.byref(sp), float(S0), float(T), int(n_steps), int(n_paths), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                int(path_offset), ks, nk, 1 if is_call else 0, int(flags), bp)
         if out_dev is not None:
             self._check(self.lib.b200mc_price_european_async(*args, _vp(out_dev)))
             return None
-        out = np.empty((strikes.size, NSUMS), dtype=np.float64)
-        self._check(self.lib.b200mc_price_european(*args, out.ctypes.data))
-        return out
+        buf = (C.c_double * (nk * NSUMS if nk > 0 else NSUMS))()
+        self._check(self.lib.b200mc_price_european(*args, buf))
+        return np.frombuffer(buf, dtype=np.float64, count=nk * NSUMS).reshape(nk, NSUMS) if nk > 0 else \
+            np.empty((0, NSUMS), dtype=np.float64)
 
     def price_cells(self, cells, strikes, flags=0, out_dev: Optional[int] = None):
         """cells: a structured array from make_cells(), or a sequence of dicts / objects with params, S0, T, n_steps,
@@ -754,10 +771,19 @@ class ReferenceDraws:
             pass
 
 
+_default_device: Optional[int] = None
+
+
 def default_handle(device: Optional[int] = None) -> Handle:
     """Process-wide handle per device (LOCAL_RANK picks the device under torchrun)."""
+    global _default_device
     if device is None:
-        device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        if _default_device is None:      # resolved once per process (an engine per calibration candidate asks every time)
+            _default_device = int(os.environ.get("B200MC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device = _default_device
+        h = _default.get(device)         # lock-free hit: dict reads are atomic, handles are only ever added or replaced
+        if h is not None and h.h is not None:
+            return h
     with _default_lock:
         h = _default.get(device)
         if h is None or h.h is None:

@@ -95,7 +95,7 @@ inline int ensure(b200mc_handle *h, void **p, size_t *have, size_t want, bool pi
 // cudaMemcpyAsync.  Small calls (calibration: 1e4-1e5 of them, 10-40 us of GPU work each) are bound by this fixed cost.
 // B200MC_RESULT=copy|mapped overrides the default; results larger than RESULT_MAPPED_MAX always take the copy.
 #ifndef B200MC_RESULT_MAPPED_DEFAULT
-#define B200MC_RESULT_MAPPED_DEFAULT 0
+#define B200MC_RESULT_MAPPED_DEFAULT 1
 #endif
 constexpr size_t RESULT_MAPPED_MAX = 64 * 1024;
 inline bool result_mapped_wanted()

@@ -50,7 +50,7 @@ class GreeksEngine:
     def _fused(self, spot, strike, T, is_call, spot_bump=0.01, v0_bump=0.01, r_bump=0.0001) -> np.ndarray:
         p = self.params
         key = (float(spot), float(strike), float(T), bool(is_call), spot_bump, v0_bump, r_bump,
-               tuple(float(getattr(p, f)) for f, _ in _lib.SvjParams._fields_), self.num_paths, self.num_steps, self.seed)
+               _lib._param_values(p), self.num_paths, self.num_steps, self.seed)
         if key == self._cache_key:
             return self._cache_row
         bumps = Bumps(spot_bump, p.v0 + v0_bump, max(p.v0 - v0_bump, 0.001),      # greeks.py:124-125
@@ -65,6 +65,7 @@ class GreeksEngine:
         else:
             row = self.handle.price_european(p, float(spot), float(T), steps, n, self.seed, [float(strike)], is_call,
                                              flags, bumps)[0]
+        row = row.tolist()                   # plain floats for the scalar algebra of delta / vega / gamma below
         self._cache_key, self._cache_row = key, row
         return row
 

@@ -38,6 +38,8 @@ DEFAULT_NUM_PATHS = 500_000      # engine/config.py:23
 DEFAULT_NUM_STEPS = 252          # engine/config.py:24
 
 _COL = {n: i for i, n in enumerate(SUMS_FIELDS)}
+_I_N, _I_A, _I_B, _I_AA, _I_BB, _I_AB = (_COL[k] for k in ("n", "sum_a", "sum_b", "sum_aa", "sum_bb", "sum_ab"))
+_I_S, _I_SS, _I_PS = (_COL[k] for k in ("sum_s", "sum_ss", "sum_ps"))
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -292,8 +294,9 @@ class MonteCarloEngine:
     def _moments(row: np.ndarray, anti: bool):
         """mean and population variance of the combined payoff, mean of the primary payoff, variance of
         (combined - primary): everything price()/price_batch() need, from the five sums."""
-        n = row[_COL["n"]]
-        sa, sb, saa, sbb, sab = (row[_COL[k]] for k in ("sum_a", "sum_b", "sum_aa", "sum_bb", "sum_ab"))
+        n, sa, sb, saa, sbb, sab = row[_I_N], row[_I_A], row[_I_B], row[_I_AA], row[_I_BB], row[_I_AB]
+        if not n > 0:
+            n = float("nan")                 # no paths: NaN results as the reference's empty reductions give, no exception
         mean_a = sa / n
         if anti:
             mean = 0.5 * (sa + sb) / n
@@ -324,6 +327,8 @@ class MonteCarloEngine:
 
     def _result(self, row, p, spot, strike, T, is_call, steps) -> Dict[str, float]:
         """The dict of price() from one b200mc_sums row."""
+        if isinstance(row, np.ndarray):
+            row = row.tolist()               # plain floats: the same IEEE arithmetic at a third of NumPy's scalar cost
         n, mean, var, mean_a, dvar = self._moments(row, self.use_antithetic)
         discount = math.exp(-p.r * T)                                          # :327
         raw_price = discount * mean                                            # :342
@@ -450,14 +455,16 @@ class MonteCarloEngine:
         """NEW keys: regression control variate on S_T, whose mean S0 e^{(r-q)T} is known for every SVJ
         parameter set (the jump drift is compensated, monte_carlo.py:209-210)."""
         p = p or self.params
-        n = row[_COL["n"]]
+        n = row[_I_N]
+        if not n > 0:
+            return {}
         anti = self.use_antithetic
-        pay_mean = (0.5 * (row[_COL["sum_a"]] + row[_COL["sum_b"]]) if anti else row[_COL["sum_a"]]) / n
+        pay_mean = (0.5 * (row[_I_A] + row[_I_B]) if anti else row[_I_A]) / n
         if anti:
-            pay_sq = 0.25 * (row[_COL["sum_aa"]] + 2 * row[_COL["sum_ab"]] + row[_COL["sum_bb"]]) / n
+            pay_sq = 0.25 * (row[_I_AA] + 2 * row[_I_AB] + row[_I_BB]) / n
         else:
-            pay_sq = row[_COL["sum_aa"]] / n
-        s_mean, s_sq, ps = row[_COL["sum_s"]] / n, row[_COL["sum_ss"]] / n, row[_COL["sum_ps"]] / n
+            pay_sq = row[_I_AA] / n
+        s_mean, s_sq, ps = row[_I_S] / n, row[_I_SS] / n, row[_I_PS] / n
         var_s = s_sq - s_mean * s_mean
         if not var_s > 0:
             return {}
@@ -480,14 +487,31 @@ class MonteCarloEngine:
         discount = math.exp(-p.r * T)
         sigma_bs = math.sqrt(p.v0)
         results = []
+        # The per-strike algebra is scalar Python (a smile has 11-64 strikes; for the small calls of a calibration this
+        # loop costs as much as the launch), so everything that does not depend on the strike is hoisted: the Black-
+        # Scholes reference below is bs_price() term for term -- the same operations in the same order, bit-identical.
+        anti, cv, moments, sqrt = self.use_antithetic, self.use_control_variate, self._moments, math.sqrt
+        S = float(spot)
+        if cv and T > 0:
+            sT = sigma_bs * sqrt(T)
+            drift = (p.r - p.q + 0.5 * sigma_bs ** 2) * T
+            S_eq, e_r = S * math.exp(-p.q * T), math.exp(-p.r * T)
+        strikes = list(strikes)
         for lo in range(0, ks.size, 256):                                      # at most 256 strikes per launch
             rows = self._sums(spot, ks[lo:lo + 256], T, is_call, steps)
-            for K, row in zip(list(strikes)[lo:lo + 256], rows):
-                n, mean, var, mean_a, _ = self._moments(row, self.use_antithetic)
+            for K, row in zip(strikes[lo:lo + 256], rows.tolist()):
+                n, mean, var, mean_a, _ = moments(row, anti)
                 raw = discount * mean
-                res = {"strike": K, "price": raw, "std_error": discount * math.sqrt(var) / math.sqrt(n)}   # :438-441
-                if self.use_control_variate:                                   # :443-448
-                    bs_ref = bs_price(float(spot), float(K), T, p.r, p.q, sigma_bs, is_call)
+                res = {"strike": K, "price": raw, "std_error": discount * sqrt(var) / sqrt(n)}             # :438-441
+                if cv:                                                         # :443-448
+                    Kf = float(K)
+                    if T > 0:
+                        d1 = (math.log(S / Kf) + drift) / sT
+                        d2 = d1 - sT
+                        bs_ref = S_eq * _ncdf(d1) - Kf * e_r * _ncdf(d2) if is_call else \
+                            Kf * e_r * _ncdf(-d2) - S_eq * _ncdf(-d1)
+                    else:
+                        bs_ref = bs_price(S, Kf, T, p.r, p.q, sigma_bs, is_call)
                     res["price"] = raw - (discount * mean_a - bs_ref)
                     res["bs_ref"] = bs_ref
                 results.append(res)
@@ -557,7 +581,7 @@ class MonteCarloEngine:
             for T, block in zip(Ts, sums):
                 discount = math.exp(-p.r * T)
                 out = []
-                for K, row in zip(ks, block):
+                for K, row in zip(ks, block.tolist()):
                     nn, mean, var, mean_a, _ = self._moments(row, self.use_antithetic)
                     res = {"strike": K, "price": discount * mean, "std_error": discount * math.sqrt(var) / math.sqrt(nn)}
                     if self.use_control_variate:
