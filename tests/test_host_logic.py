@@ -542,3 +542,50 @@ def test_parameter_helpers_equal_the_reference():
         back = P.from_array(arr, r=0.02, q=0.005)
         assert {f: getattr(back, f) for f in g["from_array_fields"]} == g["from_array_fields"], name
     assert P.from_array(P().to_array()) == P()          # defaults of r, q are the reference's market constants
+
+
+def test_price_european_marshalling_without_a_device():
+    """Handle.price_european hands the library a ctypes strike array (lists / tuples) or the ndarray's address, plain
+    Python scalars, and returns the landing buffer as a writable [n_strikes, NSUMS] array -- checked against a recording
+    stand-in for the C entry point (no device, no compute)."""
+    import ctypes as C
+
+    class RecordingLib:
+        def __init__(self):
+            self.calls = []
+
+        def b200mc_price_european(self, h, sp, S0, T, n_steps, n_paths, seed, path_offset, ks, nk, is_call, flags, bumps, out):
+            strikes = [ks[i] for i in range(nk)] if not isinstance(ks, int) else \
+                list((C.c_double * nk).from_address(ks))
+            self.calls.append(dict(S0=S0, T=T, n_steps=n_steps, n_paths=n_paths, seed=seed, path_offset=path_offset,
+                                   strikes=strikes, is_call=is_call, flags=flags, v0=sp._obj.v0, bumps=bumps))
+            for i in range(nk):
+                for j in range(_lib.NSUMS):
+                    out[i * _lib.NSUMS + j] = 1000.0 * strikes[i] + j
+            return 0
+
+        def b200mc_destroy(self, h):
+            return 0
+
+    h = _lib.Handle.__new__(_lib.Handle)
+    h.h, h.lib = C.c_void_p(1), RecordingLib()
+    p = SVJParams(v0=0.0625)
+    for strikes in ([1.0, 2.0, 3.0], (1.0, np.float64(2.0), 3), np.array([1.0, 2.0, 3.0]), np.array([1, 2, 3], dtype=np.int32)):
+        out = h.price_european(p, np.float32(22500.0), 1, np.int64(50), np.int32(1000), 2 ** 64 + 5, strikes, np.bool_(True),
+                               _lib.ANTITHETIC, None, path_offset=np.int64(7))
+        c = h.lib.calls[-1]
+        assert c["strikes"] == [1.0, 2.0, 3.0] and c["v0"] == 0.0625 and c["seed"] == 5 and c["path_offset"] == 7
+        assert (c["S0"], c["T"], c["n_steps"], c["n_paths"], c["is_call"], c["flags"]) == (22500.0, 1.0, 50, 1000, 1, 1)
+        assert all(type(c[k]) is t for k, t in (("S0", float), ("T", float), ("n_steps", int), ("n_paths", int)))
+        assert out.shape == (3, _lib.NSUMS) and out.dtype == np.float64 and out.flags.writeable
+        assert out[2, 4] == 3004.0 and out[0, 0] == 1000.0
+    one = h.price_european(p, 22500.0, 1.0, 50, 1000, 42, 2500.0, False)          # a scalar strike
+    assert one.shape == (1, _lib.NSUMS) and h.lib.calls[-1]["is_call"] == 0
+
+    class Loose:                                                                  # fields float() understands only
+        pass
+    q = Loose()
+    for f in _lib.PARAM_FIELDS:
+        setattr(q, f, "0.25")
+    assert _lib.to_params(q).kappa == 0.25 and _lib.to_params(SVJParams()).rho == -0.7
+    h.h = None
