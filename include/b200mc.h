@@ -209,7 +209,11 @@ int b200mc_numpy_ziggurat_tables(uint64_t ki[256], double wi[256], double fi[256
  * [path_offset, path_offset + n_paths) for n_steps steps of dt = T / n_steps (the caller applies the
  * reference's steps rule, monte_carlo.py:287) and writes one b200mc_sums per strike into out[n_strikes]
  * (host memory).  `bumps` may be NULL unless B200MC_GREEKS is set.  is_call: 1 call, 0 put.
- * No path matrix touches HBM.  Sums of disjoint path ranges add (multi-GPU: all-reduce the structs). */
+ * No path matrix touches HBM.  Sums of disjoint path ranges add (multi-GPU: all-reduce the structs).
+ * The call returns after the kernel has finished; the sums reach the host without a copy command (the kernel's last
+ * CTA stores them into a pinned, device-mapped landing buffer of the handle, which is then copied into `out`): a
+ * 10k-path x 50-step call takes ~20 us end to end on B200.  B200MC_RESULT=copy in the environment selects a device
+ * buffer + cudaMemcpyAsync instead (the same numbers, ~8 us more per call). */
 int b200mc_price_european(b200mc_handle *h, const b200mc_svj_params *p, double S0, double T,
                           int32_t n_steps, int64_t n_paths, uint64_t seed, uint64_t path_offset,
                           const double *strikes, int32_t n_strikes, int is_call, uint32_t flags,
