@@ -483,7 +483,7 @@ class MonteCarloEngine:
             return self._price_batch_reference(spot, strikes, T, is_call)
         p = self.params
         steps = steps_for(self.num_steps, T)
-        ks = np.asarray(strikes, dtype=np.float64).ravel()
+        strikes = np.asarray(strikes).ravel().tolist() if isinstance(strikes, np.ndarray) else list(strikes)
         discount = math.exp(-p.r * T)
         sigma_bs = math.sqrt(p.v0)
         results = []
@@ -496,10 +496,10 @@ class MonteCarloEngine:
             sT = sigma_bs * sqrt(T)
             drift = (p.r - p.q + 0.5 * sigma_bs ** 2) * T
             S_eq, e_r = S * math.exp(-p.q * T), math.exp(-p.r * T)
-        strikes = list(strikes)
-        for lo in range(0, ks.size, 256):                                      # at most 256 strikes per launch
-            rows = self._sums(spot, ks[lo:lo + 256], T, is_call, steps)
-            for K, row in zip(strikes[lo:lo + 256], rows.tolist()):
+        for lo in range(0, len(strikes), 256):                                 # at most 256 strikes per launch
+            chunk = strikes[lo:lo + 256]
+            rows = self._sums(spot, chunk, T, is_call, steps)
+            for K, row in zip(chunk, rows.tolist()):
                 n, mean, var, mean_a, _ = moments(row, anti)
                 raw = discount * mean
                 res = {"strike": K, "price": raw, "std_error": discount * sqrt(var) / sqrt(n)}             # :438-441

@@ -24,15 +24,20 @@ def _batched_objectives(calib):
     SVJParams are taken from the patched module itself."""
     import numpy as np
 
+    def _floats(a):
+        """Plain floats: the objectives run 1e4-1e5 times per calibration on a handful of numbers, where NumPy scalars
+        cost three times what floats do (the arithmetic is the same IEEE double either way)."""
+        return a.tolist() if isinstance(a, np.ndarray) else [float(v) for v in a]
+
     def _sum_sq(engine, spot, strikes, T, market_prices, weights, is_call):
         try:
-            rows = engine.price_batch(spot, np.asarray(strikes, dtype=float), T, is_call=is_call)
+            rows = engine.price_batch(spot, _floats(strikes), T, is_call=is_call)
         except Exception:
             return float(len(strikes))                      # every strike "failed": +1.0 each (:88-89)
-        return float(sum(weights[i] * (rows[i]["price"] - market_prices[i]) ** 2 for i in range(len(strikes))))
+        return float(sum(w * (row["price"] - m) ** 2 for w, row, m in zip(_floats(weights), rows, _floats(market_prices))))
 
     def _heston_objective(x, spot, strikes, T, market_prices, weights, r, q, is_call, num_paths=100_000, num_steps=100):
-        kappa, theta, xi, rho, v0 = x
+        kappa, theta, xi, rho, v0 = _floats(x)
         feller_penalty = 0.0
         if not calib.check_feller(kappa, theta, xi):
             feller_penalty = 10.0 * (xi ** 2 - 2 * kappa * theta) ** 2
@@ -46,8 +51,8 @@ def _batched_objectives(calib):
 
     def _svj_objective(x_jump, heston_params, spot, strikes, T, market_prices, weights, r, q, is_call,
                        num_paths=100_000, num_steps=100):
-        lambda_j, mu_j, sigma_j = x_jump
-        kappa, theta, xi, rho, v0 = heston_params
+        lambda_j, mu_j, sigma_j = _floats(x_jump)
+        kappa, theta, xi, rho, v0 = _floats(heston_params)
         params = calib.SVJParams(kappa=kappa, theta=theta, xi=xi, rho=rho, v0=v0, lambda_j=lambda_j, mu_j=mu_j,
                                  sigma_j=sigma_j, r=r, q=q)
         engine = calib.MonteCarloEngine(params, num_paths=num_paths, num_steps=num_steps, use_sobol=True,
