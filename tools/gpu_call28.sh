@@ -2,6 +2,8 @@
 # round 2, call 28 (the last GPU minutes of the round): A/B of the fp64 TwoSum build (csrc -DB200MC_FP64_TWOSUM=1,
 # libb200mc_twosum.so through B200MC_LIB) against the shipped build, the full GPU suite on the variant (the gate for
 # making it the default), then the bench line and smoke() of whichever build ships.
+# (build the variant in the container first: make -C monte_carlo_option_simulator_b200/csrc BUILD=build_twosum \
+#  OUT=../libb200mc_twosum.so EXTRA=-DB200MC_FP64_TWOSUM=1 -- the .so travels with the snapshot)
 set -x
 mkdir -p gpurun_out
 V=$PWD/monte_carlo_option_simulator_b200/libb200mc_twosum.so
