@@ -589,3 +589,19 @@ def test_price_european_marshalling_without_a_device():
         setattr(q, f, "0.25")
     assert _lib.to_params(q).kappa == 0.25 and _lib.to_params(SVJParams()).rho == -0.7
     h.h = None
+
+
+def test_price_batch_reference_price_is_bs_price_bit_for_bit():
+    """price_batch hoists the strike-independent terms of the Black-Scholes reference out of its strike loop; the result
+    must be bs_price() to the last bit (same operations, same order), for calls and puts, lists and arrays."""
+    p = SVJParams(kappa=2.0, theta=0.05, xi=0.4, rho=-0.5, v0=0.0625, lambda_j=0.3, mu_j=-0.02, sigma_j=0.07, r=0.031, q=0.017)
+    e = MonteCarloEngine(p, 400, 40, 7, use_sobol=False, rng="philox", handle=OracleBackedHandle())
+    ks = [70.0 + 3.7 * i for i in range(17)]
+    for is_call in (True, False):
+        for strikes in (ks, np.array(ks), tuple(ks)):
+            rows = e.price_batch(100.0, strikes, 0.37, is_call)
+            assert [r["strike"] for r in rows] == ks
+            for r, K in zip(rows, ks):
+                assert r["bs_ref"] == MC.bs_price(100.0, K, 0.37, p.r, p.q, math.sqrt(p.v0), is_call)
+                one = e.price(100.0, K, 0.37, is_call)
+                assert r["price"] == pytest.approx(one["price"], rel=1e-12) and r["bs_ref"] == one["bs_ref"]
