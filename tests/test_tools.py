@@ -68,3 +68,18 @@ def test_every_ncu_summary_the_bench_line_cites_is_committed():
         for path in re.findall(r"profiles/[A-Za-z0-9_]+\.txt", v["source"]):
             assert os.path.exists(os.path.join(ROOT, path)), f"{key}: {path} is cited but not committed"
             assert "kernel:" in open(os.path.join(ROOT, path)).read()
+
+
+@pytest.mark.skipif(not shutil.which("gcc"), reason="no gcc")
+def test_host_layer_runs_end_to_end_against_the_stand_in_library():
+    """tools/host_overhead_probe.py drives price / price_batch / the Greeks / a stress report through the real binding with
+    a stand-in library that returns constant sums (no device): every host code path of the small calls executes here."""
+    import subprocess
+    env = dict(os.environ, B200MC_HOST_PROBE_QUICK="1")
+    env.pop("B200MC_LIB", None)
+    env.pop("B200MC_HOST_PROBE", None)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "host_overhead_probe.py")], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if "us of host time per call" in ln]
+    assert len(lines) == 7 and "stand-in" in res.stdout

@@ -71,6 +71,7 @@ def greeks(i=[0]):
 
 
 G = globals()
+QUICK = os.environ.get("B200MC_HOST_PROBE_QUICK") == "1"          # tests/test_tools.py: a few calls of every entry, no timing claim
 print(f"library: {_lib.LIB_PATH} (stand-in: returns at once)")
 for what, stmt, n in (("Handle.price_european, 1 strike", "h.price_european(p, 22500.0, 1.0, 50, 10000, 42, [22500.0], True, 1)", 20000),
                       ("MonteCarloEngine.price", "e.price(22500.0, 22400.0, 1.0)", 20000),
@@ -79,5 +80,7 @@ for what, stmt, n in (("Handle.price_european, 1 strike", "h.price_european(p, 2
                       ("price_batch, 5 strikes (ndarray)", "e.price_batch(22500.0, ks5, 0.08)", 5000),
                       ("MonteCarloEngine(...) constructor", "MonteCarloEngine(p, 100000, 100)", 20000),
                       ("StressTestEngine.full_stress_report (11 cells)", "st.full_stress_report(22500.0, 22500.0, 0.25)", 500)):
-    us = min(timeit.repeat(stmt, globals=G, number=n, repeat=5)) / n * 1e6
+    if QUICK:
+        n = max(n // 500, 3)
+    us = min(timeit.repeat(stmt, globals=G, number=n, repeat=2 if QUICK else 5)) / n * 1e6
     print(f"{what:52s} {us:8.2f} us of host time per call")
